@@ -1,0 +1,167 @@
+"""Synthetic SRTM / HydroSHEDS / groves rasters for parity tests and bench.py.
+
+There is no network and the reference's input tiles are stripped from the
+repo, so every workload above the bundled 519x508
+tile is synthetic.  The recipe follows SURVEY.md section 8(d) with one
+addition, stated in DESIGN.md: a 0.3 m white-noise term on the SRTM surface
+(real SRTM carries ~1 m of sensor noise).  Without it the high-frequency half
+of the spectrum sits at the float32 FFT rounding floor and the Fourier
+peak detector (centre > 4 x hollow mean) thresholds pure rounding noise.
+
+Everything is a pure function of (ny, nx, seed) and can be produced one row
+band at a time (``rows=(r0, r1)``), which is how the row-band sharded runs
+and the 36000^2 mosaic generate their inputs.
+"""
+import numpy as np
+
+_BLOCK = 256          # row granularity of the per-cell random streams
+
+
+def _bilinear(coarse, step, r0, r1, nx):
+    """Rows r0..r1 of ``coarse`` (nodes every ``step`` cells) upsampled bilinearly."""
+    y = np.arange(r0, r1, dtype=np.float64) / step
+    x = np.arange(nx, dtype=np.float64) / step
+    iy = y.astype(np.int64); fy = (y - iy).astype(np.float32)
+    ix = x.astype(np.int64); fx = (x - ix).astype(np.float32)
+    top = coarse[iy][:, ix] * (1 - fx) + coarse[iy][:, ix + 1] * fx
+    bot = coarse[iy + 1][:, ix] * (1 - fx) + coarse[iy + 1][:, ix + 1] * fx
+    return top * (1 - fy)[:, None] + bot * fy[:, None]
+
+
+class SynthScene:
+    """One synthetic scene: SRTM surface with stripes and groves, the matching
+    HydroSHEDS raster with lagoon plateaus and voids, the groves class and an
+    (empty) rivers raster."""
+
+    def __init__(self, ny, nx, seed):
+        self.ny, self.nx, self.seed = int(ny), int(nx), int(seed)
+        rng = np.random.default_rng([self.seed, 1])
+        self._octaves = []
+        for k in range(6):
+            step = 2 ** (9 - k)
+            cy, cx = self.ny // step + 3, self.nx // step + 3
+            self._octaves.append((step, np.float32(8.0 * 0.5 ** k),
+                                  rng.standard_normal((cy, cx)).astype(np.float32)))
+        cells = self.ny * self.nx
+        # groves: thin rectangles, ~1 % coverage
+        rg = np.random.default_rng([self.seed, 2])
+        n_groves = max(1, cells // 40000)
+        self._groves = []
+        for _ in range(n_groves):
+            hgt, wid = (int(rg.integers(3, 9)), int(rg.integers(20, 120)))
+            if rg.random() < 0.5:
+                hgt, wid = wid, hgt
+            hgt, wid = min(hgt, self.ny), min(wid, self.nx)
+            y0 = int(rg.integers(0, self.ny - hgt + 1)); x0 = int(rg.integers(0, self.nx - wid + 1))
+            self._groves.append((y0, x0, hgt, wid, np.float32(rg.uniform(2.0, 6.0))))
+        # lagoons: discs flattened to their minimum
+        rl = np.random.default_rng([self.seed, 3])
+        n_lag = max(1, cells // 50000)
+        self._lagoons = [(int(rl.integers(0, self.ny)), int(rl.integers(0, self.nx)),
+                          float(rl.uniform(6.0, 40.0))) for _ in range(n_lag)]
+        self._lagoon_level = None
+        # voids: -32768 at density 2e-5, never on the frame
+        rv = np.random.default_rng([self.seed, 4])
+        n_void = max(1, int(round(cells * 2e-5))) if min(self.ny, self.nx) > 2 else 0
+        self._voids = np.stack([rv.integers(1, max(2, self.ny - 1), n_void),
+                                rv.integers(1, max(2, self.nx - 1), n_void)], axis=1)
+
+    # ---- pieces -----------------------------------------------------------------
+    def _rows(self, rows):
+        r0, r1 = (0, self.ny) if rows is None else rows
+        assert 0 <= r0 <= r1 <= self.ny
+        return r0, r1
+
+    def base(self, rows=None):
+        """Smooth terrain: trend + 6 octaves of bilinear value noise (float32)."""
+        r0, r1 = self._rows(rows)
+        x = np.arange(self.nx, dtype=np.float32)
+        y = np.arange(r0, r1, dtype=np.float32)
+        out = (np.float32(100.0) + np.float32(1e-4) * x[None, :] + np.float32(5e-5) * y[:, None]).astype(np.float32)
+        for step, amp, coarse in self._octaves:
+            out += amp * _bilinear(coarse, step, r0, r1, self.nx).astype(np.float32)
+        return out
+
+    def _white(self, rows, stream, scale):
+        r0, r1 = self._rows(rows)
+        out = np.empty((r1 - r0, self.nx), dtype=np.float32)
+        b = r0 // _BLOCK
+        while b * _BLOCK < r1:
+            rng = np.random.default_rng([self.seed, stream, b])
+            blk = rng.standard_normal((_BLOCK, self.nx), dtype=np.float32)
+            lo, hi = max(r0, b * _BLOCK), min(r1, (b + 1) * _BLOCK)
+            out[lo - r0:hi - r0] = blk[lo - b * _BLOCK:hi - b * _BLOCK]
+            b += 1
+        return out * np.float32(scale)
+
+    def groves(self, rows=None):
+        """Groves classification, uint8 0/1 (image_srtm.py:177 reads it with GDAL)."""
+        r0, r1 = self._rows(rows)
+        g = np.zeros((r1 - r0, self.nx), dtype=np.uint8)
+        for (y0, x0, hgt, wid, _) in self._groves:
+            a, b = max(y0, r0), min(y0 + hgt, r1)
+            if a < b:
+                g[a - r0:b - r0, x0:x0 + wid] = 1
+        return g
+
+    def srtm(self, rows=None):
+        """Raw SRTM: base + stripes + sensor noise + tree canopy over groves (float32)."""
+        r0, r1 = self._rows(rows)
+        out = self.base(rows)
+        x = np.arange(self.nx, dtype=np.float64)[None, :]
+        y = np.arange(r0, r1, dtype=np.float64)[:, None]
+        out += (0.5 * np.sin(2 * np.pi * (0.11 * x + 0.07 * y))
+                + 0.3 * np.sin(2 * np.pi * (0.031 * x - 0.052 * y))).astype(np.float32)
+        out += self._white(rows, 5, 0.3)
+        for (y0, x0, hgt, wid, canopy) in self._groves:
+            a, b = max(y0, r0), min(y0 + hgt, r1)
+            if a < b:
+                out[a - r0:b - r0, x0:x0 + wid] += canopy
+        return out
+
+    def _levels(self):
+        if self._lagoon_level is None:
+            lev = []
+            for (cy, cx, rad) in self._lagoons:
+                r = int(np.ceil(rad))
+                a, b = max(cy - r, 0), min(cy + r + 1, self.ny)
+                blk = np.round(self.base((a, b)))
+                yy = np.arange(a, b)[:, None] - cy
+                xx = np.arange(self.nx)[None, :] - cx
+                disc = (yy * yy + xx * xx) <= rad * rad
+                lev.append(np.float32(blk[disc].min()) if disc.any() else np.float32(0))
+            self._lagoon_level = lev
+        return self._lagoon_level
+
+    def hsheds(self, rows=None):
+        """HydroSHEDS-style raster: integer metres as float32, lagoon plateaus, voids."""
+        r0, r1 = self._rows(rows)
+        out = np.round(self.base(rows)).astype(np.float32)
+        for (cy, cx, rad), lev in zip(self._lagoons, self._levels()):
+            r = int(np.ceil(rad))
+            a, b = max(cy - r, r0), min(cy + r + 1, r1)
+            if a >= b:
+                continue
+            x0, x1 = max(cx - r, 0), min(cx + r + 1, self.nx)
+            yy = np.arange(a, b)[:, None] - cy
+            xx = np.arange(x0, x1)[None, :] - cx
+            disc = (yy * yy + xx * xx) <= rad * rad
+            blk = out[a - r0:b - r0, x0:x1]
+            blk[disc] = lev
+        for (vy, vx) in self._voids:
+            if r0 <= vy < r1:
+                out[vy - r0, vx] = np.float32(-32768.0)
+        return out
+
+    def rivers(self, rows=None):
+        """Rasterised rivers: zeros (RouteRivers is out of scope)."""
+        r0, r1 = self._rows(rows)
+        return np.zeros((r1 - r0, self.nx), dtype=np.float32)
+
+
+def make_scene(ny, nx, seed):
+    return SynthScene(ny, nx, seed)
+
+
+# seeds fixed by SURVEY.md section 8(d)
+CONFIG_SEEDS = {"C2": 1002, "C3": 1003, "C4": 1004, "C5": 1005}

@@ -1,0 +1,77 @@
+"""ctypes binding of libhydrodem_b200.so (the C ABI declared in include/hydrodem_b200.h).
+
+The product path fails loudly: if the library has not been built, or a call
+returns a negative status, a DeviceError / reference exception is raised.
+Nothing here falls back to the CPU.
+"""
+import ctypes
+import os
+
+from .exceptions import DeviceError, WindowSizeEvenError, WindowSizeHighError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhydrodem_b200.so")
+
+# hd_status / hd_dtype / op codes (mirrors of the header enums)
+HD_OK, HD_ERR_NULL, HD_ERR_WINDOW_HIGH, HD_ERR_WINDOW_EVEN = 0, -1, -2, -3
+HD_ERR_ALIGN, HD_ERR_CUDA, HD_ERR_UNSUPPORTED, HD_ERR_ARG, HD_ERR_WORKSPACE = -4, -5, -6, -7, -8
+U8, F32, F64, I64, C64, C128, I32 = range(7)
+OP_COPY, OP_MUL, OP_ADD, OP_RSUB, OP_LT, OP_GT, OP_ABS, OP_RINT, OP_XOR = range(9)
+MORPH_ERODE, MORPH_DILATE, MORPH_CLOSE, MORPH_OPEN = range(4)
+
+_p, _i, _i64, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+
+# name -> (restype, argtypes).  tests/test_abi.py checks this table against the header.
+SIGNATURES = {
+    "hd_version": (_i, []),
+    "hd_status_string": (ctypes.c_char_p, [_i]),
+    "hd_last_cuda_error": (_i, []),
+    "hd_last_cuda_error_string": (ctypes.c_char_p, []),
+    "hd_device_count": (_i, []),
+    "hd_launch_count": (_i64, []),
+    "hd_reset_launch_count": (None, []),
+    "hd_pitch_elems": (_i64, [_i64, _i]),
+    "hd_memcpy2d_h2d": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
+    "hd_memcpy2d_d2h": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
+    "hd_stream_synchronize": (_i, [_p]),
+    "hd_elementwise": (_i, [_i, _p, _i, _i64, _p, _i, _i64, _d, _p, _i, _i64, _i64, _i64, _p]),
+    "hd_expand": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i64, _i, _p]),
+    "hd_majority": (_i, [_p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),
+    "hd_nanfix": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),
+    "hd_isolated": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),
+    "hd_binary_morph": (_i, [_p, _i, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _p]),
+    "hd_max_filter": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
+    "hd_convolve3": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, ctypes.POINTER(_d), _d, _i, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises DeviceError if it was never built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DeviceError(f"{LIB_PATH} is missing: run `python -m hydrodem_b200.build` "
+                              "(there is no CPU fallback for the conditioning path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(status, *, window_size=None, shape=None):
+    """Map a negative hd_status to the reference's exception classes."""
+    if status == HD_OK:
+        return
+    lib = load()
+    if status == HD_ERR_WINDOW_HIGH:
+        raise WindowSizeHighError(window_size, shape)
+    if status == HD_ERR_WINDOW_EVEN:
+        raise WindowSizeEvenError(window_size)
+    msg = lib.hd_status_string(status).decode()
+    if status == HD_ERR_CUDA:
+        msg += f": {lib.hd_last_cuda_error_string().decode()} ({lib.hd_last_cuda_error()})"
+    raise DeviceError(f"libhydrodem_b200: {msg}")

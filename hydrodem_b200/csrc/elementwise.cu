@@ -1,0 +1,105 @@
+// Elementwise filters of the reference (filters/simple_filters.py, extension_filters.py:12-130) as one
+// dtype-generic kernel.  These are HBM-bound streaming ops; inside the fused chain they never run alone
+// (they are folded into the neighbouring stencil kernels) -- this entry point exists so that each
+// reference class has a device implementation behind the same Filter.apply() API.
+#include "common.cuh"
+
+namespace {
+
+struct cplx { double re, im; };
+
+__device__ __forceinline__ cplx load_as(const void* p, int dtype, int64_t idx)
+{
+    switch (dtype) {
+        case HD_U8: return {(double)((const uint8_t*)p)[idx], 0.0};
+        case HD_F32: return {(double)((const float*)p)[idx], 0.0};
+        case HD_F64: return {((const double*)p)[idx], 0.0};
+        case HD_I64: return {(double)((const int64_t*)p)[idx], 0.0};
+        case HD_I32: return {(double)((const int32_t*)p)[idx], 0.0};
+        case HD_C64: { float2 v = ((const float2*)p)[idx]; return {(double)v.x, (double)v.y}; }
+        default: { double2 v = ((const double2*)p)[idx]; return {v.x, v.y}; }
+    }
+}
+__device__ __forceinline__ int64_t load_int(const void* p, int dtype, int64_t idx)
+{
+    switch (dtype) {
+        case HD_U8: return ((const uint8_t*)p)[idx];
+        case HD_I32: return ((const int32_t*)p)[idx];
+        default: return ((const int64_t*)p)[idx];
+    }
+}
+__device__ __forceinline__ void store_as(void* p, int dtype, int64_t idx, cplx v)
+{
+    switch (dtype) {
+        case HD_U8: ((uint8_t*)p)[idx] = (uint8_t)v.re; break;
+        case HD_F32: ((float*)p)[idx] = (float)v.re; break;
+        case HD_F64: ((double*)p)[idx] = v.re; break;
+        case HD_I64: ((int64_t*)p)[idx] = (int64_t)v.re; break;
+        case HD_I32: ((int32_t*)p)[idx] = (int32_t)v.re; break;
+        case HD_C64: ((float2*)p)[idx] = make_float2((float)v.re, (float)v.im); break;
+        default: ((double2*)p)[idx] = make_double2(v.re, v.im); break;
+    }
+}
+
+__global__ void __launch_bounds__(256) elementwise_kernel(int op, const void* __restrict__ a, int a_dtype,
+                                                          int64_t a_pitch, const void* __restrict__ b, int b_dtype,
+                                                          int64_t b_pitch, double b_scalar, void* __restrict__ out,
+                                                          int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx)
+{
+    const int64_t total = ny * nx;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t y = t / nx, x = t - y * nx;
+        const int64_t ia = y * a_pitch + x, io = y * out_pitch + x;
+        if (op == HD_OP_XOR) {
+            const int64_t va = load_int(a, a_dtype, ia);
+            const int64_t vb = b ? load_int(b, b_dtype, y * b_pitch + x) : (int64_t)b_scalar;
+            const int64_t r = va ^ vb;
+            if (out_dtype == HD_U8) ((uint8_t*)out)[io] = (uint8_t)r;
+            else if (out_dtype == HD_I32) ((int32_t*)out)[io] = (int32_t)r;
+            else ((int64_t*)out)[io] = r;
+            continue;
+        }
+        const cplx va = load_as(a, a_dtype, ia);
+        const cplx vb = b ? load_as(b, b_dtype, y * b_pitch + x) : cplx{b_scalar, 0.0};
+        cplx r{0.0, 0.0};
+        switch (op) {
+            case HD_OP_COPY: r = va; break;
+            case HD_OP_MUL:
+                r.re = __dsub_rn(__dmul_rn(vb.re, va.re), __dmul_rn(vb.im, va.im));
+                r.im = __dadd_rn(__dmul_rn(vb.re, va.im), __dmul_rn(vb.im, va.re));
+                break;
+            case HD_OP_ADD: r = {vb.re + va.re, vb.im + va.im}; break;
+            case HD_OP_RSUB: r = {vb.re - va.re, vb.im - va.im}; break;
+            case HD_OP_LT: r.re = va.re < vb.re ? 1.0 : 0.0; break;
+            case HD_OP_GT: r.re = va.re > vb.re ? 1.0 : 0.0; break;
+            case HD_OP_ABS: r.re = (va.im == 0.0) ? fabs(va.re) : hypot(va.re, va.im); break;
+            case HD_OP_RINT: r.re = rint(va.re); break;
+            default: break;
+        }
+        store_as(out, out_dtype, io, r);
+    }
+}
+
+}  // namespace
+
+extern "C" int hd_elementwise(int op, const void* a, int a_dtype, int64_t a_pitch, const void* b, int b_dtype,
+                              int64_t b_pitch, double b_scalar, void* out, int out_dtype, int64_t out_pitch, int64_t ny,
+                              int64_t nx, void* stream)
+{
+    if (!a || !out) return HD_ERR_NULL;
+    if (op < HD_OP_COPY || op > HD_OP_XOR) return HD_ERR_ARG;
+    if (!hd_dtype_size(a_dtype) || !hd_dtype_size(out_dtype) || (b && !hd_dtype_size(b_dtype))) return HD_ERR_ARG;
+    if (ny < 0 || nx < 0 || a_pitch < nx || out_pitch < nx || (b && b_pitch < nx)) return HD_ERR_ARG;
+    if (op == HD_OP_XOR) {
+        auto is_int = [](int d) { return d == HD_U8 || d == HD_I64 || d == HD_I32; };
+        if (!is_int(a_dtype) || (b && !is_int(b_dtype)) || !is_int(out_dtype)) return HD_ERR_UNSUPPORTED;
+    }
+    if (ny == 0 || nx == 0) return HD_OK;
+    const int64_t total = ny * nx;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    elementwise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(op, a, a_dtype, a_pitch, b, b_dtype, b_pitch, b_scalar,
+                                                                 out, out_dtype, out_pitch, ny, nx);
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}

@@ -1,0 +1,170 @@
+// MajorityFilter.apply  (filters/custom_filters.py:48-73) on the corner-less "circular" window
+// (sliding_window.py:475-499).
+//
+// The reference builds a Counter over the ws*ws window (4 corners NaN'ed, each NaN its own key) and keeps
+// the mode only if count > (ws^2-1)*0.7, i.e. the winner always holds more than half of the window.  A value
+// with an absolute majority is the Boyer-Moore candidate, and Boyer-Moore summaries (candidate, counter)
+// are mergeable, so the kernel
+//   1. builds one summary per window COLUMN (2h-1 inner rows, and all 2h+1 rows) -- shared by the 2h+1
+//      windows that contain that column,
+//   2. merges 2h+1 column summaries per output cell (the two outer columns use the inner-row summary:
+//      that is exactly the corner-less footprint),
+//   3. verifies the candidate with an exact count only where the summary counter leaves the threshold
+//      reachable: true_count <= (n_window + counter) / 2.
+// This kernel is ALU / shared-memory bound, not HBM bound: ~8 B/cell of HBM traffic
+// against a few hundred shared-memory operations per cell.
+#include "common.cuh"
+#include "tile_common.cuh"
+
+namespace {
+
+constexpr int STRIP = 8;   // output rows per column-summary work item
+
+struct BM { float c; int n; };
+
+__device__ __forceinline__ void bm_push(BM& s, float v)
+{
+    if (s.n == 0) { s.c = v; s.n = 1; }
+    else if (v == s.c) ++s.n;            // NaN == x is false: every NaN is its own key (custom_filters.py:69)
+    else --s.n;
+}
+__device__ __forceinline__ void bm_merge(BM& s, float c2, int n2)
+{
+    if (c2 == s.c) s.n += n2;
+    else if (n2 > s.n) { s.c = c2; s.n = n2 - s.n; }
+    else s.n -= n2;
+}
+
+template <int H, typename OutT>
+__global__ void __launch_bounds__(NT) majority_kernel(const __grid_constant__ CUtensorMap tm_in, OutT* __restrict__ out,
+                                                      int64_t out_pitch, int64_t ny, int64_t nx, int min_count,
+                                                      int tiles_x, int ntiles)
+{
+    constexpr int WS = 2 * H + 1;
+    constexpr int CW = TW + 2 * H;                 // window columns touched by a tile
+    constexpr int IN_W = (CW + 3) / 4 * 4;
+    constexpr int IN_H = TH + 2 * H;
+    constexpr int NWIN = WS * WS - 4;              // cells of the corner-less window
+    constexpr uint32_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    float* cand_in = reinterpret_cast<float*>(smem + 2 * STAGE);       // [TH][CW] summary over the 2H-1 inner rows
+    float* cand_fu = cand_in + TH * CW;                                // [TH][CW] summary over all 2H+1 rows
+    uint8_t* cnt_in = reinterpret_cast<uint8_t*>(cand_fu + TH * CW);
+    uint8_t* cnt_fu = cnt_in + TH * CW;
+
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * 4), H, H}};
+    tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        const float* tile = reinterpret_cast<const float*>(st);
+        // ---- 1. column summaries ---------------------------------------------------------------
+        for (int item = threadIdx.x; item < CW * (TH / STRIP); item += NT) {
+            const int c = item % CW, s = item / CW;
+            float v[STRIP + 2 * H];
+#pragma unroll
+            for (int r = 0; r < STRIP + 2 * H; ++r) v[r] = tile[(s * STRIP + r) * IN_W + c];
+#pragma unroll
+            for (int o = 0; o < STRIP; ++o) {
+                BM b{0.f, 0};
+#pragma unroll
+                for (int r = 1; r <= 2 * H - 1; ++r) bm_push(b, v[o + r]);
+                const int ro = s * STRIP + o;
+                cand_in[ro * CW + c] = b.c;
+                cnt_in[ro * CW + c] = (uint8_t)b.n;
+                bm_push(b, v[o]);
+                bm_push(b, v[o + 2 * H]);
+                cand_fu[ro * CW + c] = b.c;
+                cnt_fu[ro * CW + c] = (uint8_t)b.n;
+            }
+        }
+        __syncthreads();
+        // ---- 2. merge + 3. verify -------------------------------------------------------------------
+#pragma unroll 1
+        for (int rep = 0; rep < TH * TW / NT; ++rep) {
+            const int idx = rep * NT + threadIdx.x;
+            const int ro = idx / TW, xo = idx % TW;
+            const int64_t y = ty0 + ro, x = tx0 + xo;
+            if (y >= ny || x >= nx) continue;
+            float result = 0.f;                                        // np.zeros border / no majority (:66)
+            if (y >= H && y < ny - H && x >= H && x < nx - H) {
+                const int base = ro * CW + xo;
+                BM b{cand_in[base], (int)cnt_in[base]};
+#pragma unroll
+                for (int d = 1; d <= 2 * H - 1; ++d) bm_merge(b, cand_fu[base + d], (int)cnt_fu[base + d]);
+                bm_merge(b, cand_in[base + 2 * H], (int)cnt_in[base + 2 * H]);
+                // true count of the candidate <= (NWIN + counter) / 2
+                if (NWIN + b.n >= 2 * min_count) {
+                    const float* w = tile + ro * IN_W + xo;            // top-left of the window
+                    int count = 0;
+                    float first = b.c;
+                    bool found = false;
+#pragma unroll
+                    for (int dy = 0; dy < WS; ++dy) {
+#pragma unroll
+                        for (int dx = 0; dx < WS; ++dx) {
+                            if ((dy == 0 || dy == WS - 1) && (dx == 0 || dx == WS - 1)) continue;   // NaN corners
+                            const float v = w[dy * IN_W + dx];
+                            const bool eq = (v == b.c);
+                            // Counter keeps the first-inserted key of an == class (0.0 vs -0.0)
+                            if (eq && !found) { first = v; found = true; }
+                            count += eq;
+                        }
+                    }
+                    if (count >= min_count) result = first;            // count > (ws^2-1)*0.7  (:71-72)
+                }
+            }
+            out[y * out_pitch + x] = (OutT)result;
+        }
+    });
+}
+
+template <int H, typename OutT>
+int launch(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx, int min_count,
+           cudaStream_t stream)
+{
+    constexpr int CW = TW + 2 * H, IN_W = (CW + 3) / 4 * 4, IN_H = TH + 2 * H;
+    constexpr size_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
+    constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * 4 + 2 * TH * CW;
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, HD_F32, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    HD_CUDA_OK(cudaFuncSetAttribute(majority_kernel<H, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    majority_kernel<H, OutT><<<grid_for(ntiles, 2), NT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, ny, nx, min_count,
+                                                                        tiles_x, ntiles);
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+template <typename OutT>
+int dispatch(int h, const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx, int min_count,
+             cudaStream_t s)
+{
+    switch (h) {
+        case 1: return launch<1, OutT>(in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+        case 2: return launch<2, OutT>(in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+        case 3: return launch<3, OutT>(in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+        case 4: return launch<4, OutT>(in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+        case 5: return launch<5, OutT>(in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+        case 6: return launch<6, OutT>(in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+        case 7: return launch<7, OutT>(in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+        default: return HD_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+extern "C" int hd_majority(const void* in, int64_t in_pitch, void* out, int out_dtype, int64_t out_pitch, int64_t ny,
+                           int64_t nx, int ws, int min_count, void* stream)
+{
+    if (!in || !out) return HD_ERR_NULL;
+    if (int e = check_window(ny, nx, ws)) return e;
+    if (in_pitch < nx || out_pitch < nx || min_count < 1) return HD_ERR_ARG;
+    // Boyer-Moore needs the winner to hold an absolute majority of the ws*ws-4 window cells; the
+    // reference threshold (ws^2-1)*0.7 always does.
+    if (2 * min_count <= ws * ws - 4) return HD_ERR_UNSUPPORTED;
+    const int h = ws / 2;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (out_dtype == HD_F32) return dispatch<float>(h, in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+    if (out_dtype == HD_F64) return dispatch<double>(h, in, in_pitch, out, out_pitch, ny, nx, min_count, s);
+    return HD_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,346 @@
+// Binary / flat morphology of the conditioning chain on bit-packed tiles.
+//
+//   hd_expand      ExpandFilter.apply                 custom_filters.py:102-125
+//   hd_binary_morph BinaryErosion / BinaryClosing     extension_filters.py:218-235, :276-293 (scipy.ndimage)
+//   hd_max_filter  GreyDilation(size=(s,s))           extension_filters.py:328-345 (scipy.ndimage.grey_dilation)
+//
+// All three are HBM-bound: a 32x128 tile (+halo) is staged by TMA, thresholded to one bit per cell with
+// warp ballots, and the window logic runs on 32-cell words (funnel shifts / ORs), a few hundred word
+// operations per 4096-cell tile.  Output is written with 16-byte (or 4-byte for u8) coalesced stores.
+#include "common.cuh"
+#include "tile_common.cuh"
+
+namespace {
+
+constexpr int MAX_HALO = 8;
+constexpr int MAX_IN_H = TH + 2 * MAX_HALO;            // 48
+constexpr int MAX_IN_W = TW + 2 * MAX_HALO;            // 144
+constexpr int NWORD = (MAX_IN_W + 31) / 32;            // 5
+constexpr int STAGE_BYTES = MAX_IN_H * MAX_IN_W * 4;   // sized for f32, u8 uses a quarter
+
+// threshold one staged tile to bits: bits[r * NWORD + k] bit i  <->  tile cell (r, 32k + i)
+template <typename InT, class Pred>
+__device__ __forceinline__ void tile_to_bits(const InT* tile, int in_w, int in_h, uint32_t* bits, Pred pred)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < in_h; r += NT / 32) {
+#pragma unroll
+        for (int k = 0; k < NWORD; ++k) {
+            const int c = 32 * k + lane;
+            const bool p = (c < in_w) && pred(tile[r * in_w + c]);
+            const uint32_t w = __ballot_sync(0xffffffffu, p);
+            if (lane == 0) bits[r * NWORD + k] = w;
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t win64(const uint32_t* row, int k)
+{
+    const uint32_t lo = row[k], hi = (k + 1 < NWORD) ? row[k + 1] : 0u;
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// write a TH x TW tile of 0/1 results held as bit words res[ro * 4 + k]
+template <typename OutT>
+__device__ __forceinline__ void write_bits(const uint32_t* res, OutT* out, int64_t out_pitch, int ty0, int tx0,
+                                           int64_t ny, int64_t nx, int border)
+{
+#pragma unroll
+    for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+        const int idx = rep * NT + threadIdx.x;
+        const int ro = idx >> 5, c4 = idx & 31;
+        const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+        if (y >= ny || x >= nx) continue;
+        const uint32_t nib = (res[ro * 4 + (c4 >> 3)] >> ((c4 & 7) * 4)) & 15u;
+        const bool yin = (y >= border) && (y < ny - border);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (yin && (x + j >= border) && (x + j < nx - border) && ((nib >> j) & 1u)) ? 1.f : 0.f;
+        store4<OutT>(out, out_pitch, y, x, nx, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ expand
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(NT) expand_kernel(const __grid_constant__ CUtensorMap tm_in, OutT* __restrict__ out,
+                                                    int64_t out_pitch, int64_t ny, int64_t nx, int h, int in_w, int in_h,
+                                                    int tiles_x, int ntiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t bits[MAX_IN_H * NWORD];
+    __shared__ uint32_t hfull[MAX_IN_H * 4], hinner[MAX_IN_H * 4];
+    __shared__ uint32_t res[TH * 4];
+    const uint32_t stage_bytes = STAGE_BYTES;
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(InT)), h, h}};
+    tile_loop<1>(smem, stage_bytes, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        const InT* tile = reinterpret_cast<const InT*>(st);
+        // window[~isnan(window)] > 0  (custom_filters.py:122-123): NaN > 0 is false
+        tile_to_bits<InT>(tile, in_w, in_h, bits, [](InT v) { return (float)v > 0.f; });
+        __syncthreads();
+        // horizontal: output column xo looks at tile columns xo .. xo+2h (full) / xo+1 .. xo+2h-1 (top & bottom rows)
+        for (int t = threadIdx.x; t < in_h * 4; t += NT) {
+            const int r = t >> 2, k = t & 3;
+            const uint64_t w = win64(&bits[r * NWORD], k);
+            uint64_t f = 0, in = 0;
+            for (int s = 0; s <= 2 * h; ++s) {
+                f |= w >> s;
+                if (s >= 1 && s <= 2 * h - 1) in |= w >> s;
+            }
+            hfull[t] = (uint32_t)f;
+            hinner[t] = (uint32_t)in;
+        }
+        __syncthreads();
+        if (threadIdx.x < TH * 4) {
+            const int ro = threadIdx.x >> 2, k = threadIdx.x & 3;
+            uint32_t acc = hinner[ro * 4 + k] | hinner[(ro + 2 * h) * 4 + k];   // corner-less top / bottom rows
+            for (int r = ro + 1; r <= ro + 2 * h - 1; ++r) acc |= hfull[r * 4 + k];
+            res[threadIdx.x] = acc;
+        }
+        __syncthreads();
+        write_bits<OutT>(res, out, out_pitch, ty0, tx0, ny, nx, h);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ erosion / closing
+struct MorphProgram {
+    int nsteps;
+    unsigned char dilate[MAX_HALO];   // 1 = dilation, 0 = erosion
+    unsigned char full[MAX_HALO];     // 1 = 3x3 square, 0 = cross
+};
+
+template <typename InT>
+__global__ void __launch_bounds__(NT) morph_kernel(const __grid_constant__ CUtensorMap tm_in, uint8_t* __restrict__ out,
+                                                   int64_t out_pitch, int64_t ny, int64_t nx, MorphProgram prog, int in_w,
+                                                   int in_h, int tiles_x, int ntiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t bufA[(MAX_IN_H + 2) * NWORD], bufB[(MAX_IN_H + 2) * NWORD];
+    __shared__ uint32_t res[TH * 4];
+    const int h = prog.nsteps;
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(InT)), h, h}};
+    // rows 0 and in_h+1 of the bit buffers are zero guards
+    for (int t = threadIdx.x; t < NWORD; t += NT) {
+        bufA[t] = bufB[t] = 0u;
+    }
+    tile_loop<1>(smem, STAGE_BYTES, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        const InT* tile = reinterpret_cast<const InT*>(st);
+        uint32_t* cur = bufA + NWORD;
+        uint32_t* nxt = bufB + NWORD;
+        // scipy: "non-zero elements are True" -- NaN != 0 is true; cells outside the image arrive as 0
+        tile_to_bits<InT>(tile, in_w, in_h, cur, [](InT v) { return v != (InT)0; });
+        if (threadIdx.x < NWORD) { cur[in_h * NWORD + threadIdx.x] = 0u; nxt[in_h * NWORD + threadIdx.x] = 0u; }
+        __syncthreads();
+        for (int s = 0; s < prog.nsteps; ++s) {
+            const bool dil = prog.dilate[s], full = prog.full[s];
+            for (int t = threadIdx.x; t < in_h * NWORD; t += NT) {
+                const int r = t / NWORD, k = t - r * NWORD;
+                auto hcomb = [&](const uint32_t* row) {       // centre | left | right (or &)
+                    const uint32_t c = row[k];
+                    const uint32_t lft = (c << 1) | (k > 0 ? row[k - 1] >> 31 : 0u);
+                    const uint32_t rgt = (c >> 1) | (k + 1 < NWORD ? row[k + 1] << 31 : 0u);
+                    return dil ? (c | lft | rgt) : (c & lft & rgt);
+                };
+                const uint32_t* rc = cur + r * NWORD;
+                const uint32_t* ru = rc - NWORD;              // guard row is zero (outside = False)
+                const uint32_t* rd = rc + NWORD;
+                uint32_t v;
+                if (full) {
+                    const uint32_t a = hcomb(ru), b = hcomb(rc), c = hcomb(rd);
+                    v = dil ? (a | b | c) : (a & b & c);
+                } else {
+                    const uint32_t b = hcomb(rc);
+                    v = dil ? (b | ru[k] | rd[k]) : (b & ru[k] & rd[k]);
+                }
+                if (dil) {
+                    // the dilated image only exists on the raster: outside stays border_value = 0
+                    const int64_t gy = (int64_t)ty0 - h + r;
+                    uint32_t m = 0u;
+                    if (gy >= 0 && gy < ny) {
+                        const int64_t gx0 = (int64_t)tx0 - h + 32 * k;      // global x of bit 0
+                        const int64_t lo = gx0 < 0 ? -gx0 : 0;
+                        const int64_t hi = (nx - gx0) < 32 ? (nx - gx0) : 32;   // exclusive
+                        if (hi > lo) m = (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
+                    }
+                    v &= m;
+                }
+                nxt[t] = v;
+            }
+            __syncthreads();
+            uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+        }
+        // extract the TH x TW core (tile offset h) into output words
+        if (threadIdx.x < TH * 4) {
+            const int ro = threadIdx.x >> 2, k = threadIdx.x & 3;
+            const uint64_t w = win64(cur + (ro + h) * NWORD, k);
+            res[threadIdx.x] = (uint32_t)(w >> h);
+        }
+        __syncthreads();
+        write_bits<uint8_t>(res, out, out_pitch, ty0, tx0, ny, nx, 0);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ max filter
+// mode='reflect' (d c b a | a b c d | d c b a): OOB cells of frame tiles are patched in shared memory from
+// their mirror cell, which always lies inside the same staged box (size <= min(ny, nx)).
+template <typename T> __device__ __forceinline__ T tmax(T a, T b);
+template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
+
+template <typename T>
+__global__ void __launch_bounds__(NT) maxfilter_kernel(const __grid_constant__ CUtensorMap tm_in, T* __restrict__ out,
+                                                       int64_t out_pitch, int64_t ny, int64_t nx, int h, int in_w, int in_h,
+                                                       int tiles_x, int ntiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    constexpr uint32_t STAGE = MAX_IN_H * MAX_IN_W * sizeof(T);
+    T* hmax = reinterpret_cast<T*>(smem + 2 * STAGE);          // [in_h][TW] horizontal maxima
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(T)), h, h}};
+    tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        T* tile = reinterpret_cast<T*>(st);
+        patch_reflect<T>(tile, in_w, in_h, ty0 - h, tx0 - h, ny, nx);
+        for (int t = threadIdx.x; t < in_h * TW; t += NT) {
+            const int r = t / TW, c = t - r * TW;
+            T m = tile[r * in_w + c];
+            for (int s = 1; s <= 2 * h; ++s) m = tmax<T>(m, tile[r * in_w + c + s]);
+            hmax[t] = m;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+            const int idx = rep * NT + threadIdx.x;
+            const int ro = idx >> 5, c4 = idx & 31;
+            const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+            if (y >= ny || x >= nx) continue;
+            T v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = hmax[ro * TW + 4 * c4 + j];
+            for (int s = 1; s <= 2 * h; ++s) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = tmax<T>(v[j], hmax[(ro + s) * TW + 4 * c4 + j]);
+            }
+            store4v<T>(out, out_pitch, y, x, nx, v);
+        }
+    });
+}
+
+template <typename InT, typename OutT>
+int launch_expand(const CUtensorMap& tm, void* out, int64_t out_pitch, int64_t ny, int64_t nx, int h, int in_w, int in_h,
+                  cudaStream_t stream)
+{
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    const size_t smem = 2 * STAGE_BYTES;
+    HD_CUDA_OK(cudaFuncSetAttribute(expand_kernel<InT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    expand_kernel<InT, OutT><<<grid_for(ntiles, 3), NT, smem, stream>>>(tm, (OutT*)out, out_pitch, ny, nx, h, in_w, in_h,
+                                                                        tiles_x, ntiles);
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+}  // namespace
+
+extern "C" int hd_expand(const void* in, int in_dtype, int64_t in_pitch, void* out, int out_dtype, int64_t out_pitch,
+                         int64_t ny, int64_t nx, int ws, void* stream)
+{
+    if (!in || !out) return HD_ERR_NULL;
+    if (int e = check_window(ny, nx, ws)) return e;
+    const int h = ws / 2;
+    if (h < 1 || h > MAX_HALO - 1) return HD_ERR_UNSUPPORTED;
+    if (in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    const int align = in_dtype == HD_U8 ? 16 : 4;
+    const int in_w = (TW + 2 * h + align - 1) / align * align, in_h = TH + 2 * h;
+    if (in_w > MAX_IN_W) return HD_ERR_UNSUPPORTED;
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, in_dtype, ny, nx, in_pitch, in_w, in_h, false)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+#define HD_EXPAND_CASE(IT, ITAG, OT, OTAG) \
+    if (in_dtype == ITAG && out_dtype == OTAG) return launch_expand<IT, OT>(tm, out, out_pitch, ny, nx, h, in_w, in_h, s);
+    HD_EXPAND_CASE(float, HD_F32, uint8_t, HD_U8)
+    HD_EXPAND_CASE(float, HD_F32, float, HD_F32)
+    HD_EXPAND_CASE(float, HD_F32, double, HD_F64)
+    HD_EXPAND_CASE(uint8_t, HD_U8, uint8_t, HD_U8)
+    HD_EXPAND_CASE(uint8_t, HD_U8, float, HD_F32)
+    HD_EXPAND_CASE(uint8_t, HD_U8, double, HD_F64)
+#undef HD_EXPAND_CASE
+    return HD_ERR_UNSUPPORTED;
+}
+
+extern "C" int hd_binary_morph(const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny,
+                               int64_t nx, int op, int full_structure, int iterations, void* stream)
+{
+    if (!in || !out) return HD_ERR_NULL;
+    if (ny <= 0 || nx <= 0 || in_pitch < nx || out_pitch < nx || iterations < 1) return HD_ERR_ARG;
+    MorphProgram prog{};
+    if (op == HD_MORPH_ERODE || op == HD_MORPH_DILATE) {
+        if (iterations > MAX_HALO) return HD_ERR_UNSUPPORTED;
+        prog.nsteps = iterations;
+        for (int i = 0; i < iterations; ++i) { prog.dilate[i] = (op == HD_MORPH_DILATE); prog.full[i] = full_structure != 0; }
+    } else if (op == HD_MORPH_CLOSE || op == HD_MORPH_OPEN) {
+        if (2 * iterations > MAX_HALO) return HD_ERR_UNSUPPORTED;
+        prog.nsteps = 2 * iterations;
+        for (int i = 0; i < 2 * iterations; ++i) {
+            const bool first = i < iterations;
+            prog.dilate[i] = (op == HD_MORPH_CLOSE) ? first : !first;
+            prog.full[i] = full_structure != 0;
+        }
+    } else {
+        return HD_ERR_ARG;
+    }
+    const int h = prog.nsteps;
+    const int align = in_dtype == HD_U8 ? 16 : 4;
+    const int in_w = (TW + 2 * h + align - 1) / align * align, in_h = TH + 2 * h;
+    if (in_w > MAX_IN_W) return HD_ERR_UNSUPPORTED;
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, in_dtype, ny, nx, in_pitch, in_w, in_h, false)) return e;
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    const size_t smem = 2 * STAGE_BYTES;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (in_dtype == HD_F32) {
+        HD_CUDA_OK(cudaFuncSetAttribute(morph_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        morph_kernel<float><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (uint8_t*)out, out_pitch, ny, nx, prog, in_w, in_h,
+                                                                 tiles_x, ntiles);
+    } else if (in_dtype == HD_U8) {
+        HD_CUDA_OK(cudaFuncSetAttribute(morph_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        morph_kernel<uint8_t><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (uint8_t*)out, out_pitch, ny, nx, prog, in_w, in_h,
+                                                                   tiles_x, ntiles);
+    } else {
+        return HD_ERR_UNSUPPORTED;
+    }
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+extern "C" int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny,
+                             int64_t nx, int size, void* stream)
+{
+    if (!in || !out) return HD_ERR_NULL;
+    if (size % 2 != 1 || size < 1) return HD_ERR_WINDOW_EVEN;
+    if (size > ny || size > nx) return HD_ERR_WINDOW_HIGH;
+    const int h = size / 2;
+    if (h > MAX_HALO) return HD_ERR_UNSUPPORTED;
+    if (in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    if (dtype != HD_F32 && dtype != HD_F64) return HD_ERR_UNSUPPORTED;
+    const size_t es = hd_dtype_size(dtype);
+    const int in_w = (TW + 2 * h + 3) / 4 * 4, in_h = TH + 2 * h;
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, in_w, in_h, false)) return e;
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    const size_t smem = 2 * MAX_IN_H * MAX_IN_W * es + MAX_IN_H * TW * es;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == HD_F32) {
+        HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        maxfilter_kernel<float><<<grid_for(ntiles, 2), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, h, in_w, in_h,
+                                                                     tiles_x, ntiles);
+    } else {
+        HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        maxfilter_kernel<double><<<grid_for(ntiles, 1), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, h, in_w, in_h,
+                                                                      tiles_x, ntiles);
+    }
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}

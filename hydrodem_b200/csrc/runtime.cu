@@ -1,0 +1,144 @@
+// hydrodem_b200 runtime: status strings, launch counter, pitched copies, TMA tensor-map encoding.
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+
+static thread_local int g_last_cuda_error = 0;
+static std::atomic<int64_t> g_launches{0};
+
+void hd_set_last_cuda_error(int e) { g_last_cuda_error = e; }
+void hd_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+size_t hd_dtype_size(int dtype)
+{
+    switch (dtype) {
+        case HD_U8: return 1;
+        case HD_F32: return 4;
+        case HD_I32: return 4;
+        case HD_F64: return 8;
+        case HD_I64: return 8;
+        case HD_C64: return 8;
+        case HD_C128: return 16;
+        default: return 0;
+    }
+}
+
+int hd_num_sms()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    });
+    return fn;
+}
+
+int hd_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t ny, int64_t nx, int64_t pitch_elems,
+                    int box_w, int box_h, bool nan_fill)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { hd_set_last_cuda_error((int)cudaErrorNotSupported); return HD_ERR_CUDA; }
+    CUtensorMapDataType dt;
+    switch (dtype) {
+        case HD_U8: dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
+        case HD_F32: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+        case HD_F64: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT64; break;
+        case HD_I32: dt = CU_TENSOR_MAP_DATA_TYPE_INT32; break;
+        default: return HD_ERR_UNSUPPORTED;
+    }
+    const size_t es = hd_dtype_size(dtype);
+    if (((uintptr_t)base & 15) || ((pitch_elems * es) & 15)) return HD_ERR_ALIGN;
+    if (box_w > 256 || box_h > 256 || ((box_w * es) & 15)) return HD_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)ny};
+    cuuint64_t strides[1] = {(cuuint64_t)(pitch_elems * es)};
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { hd_set_last_cuda_error((int)cudaErrorInvalidValue); return HD_ERR_CUDA; }
+    return HD_OK;
+}
+
+extern "C" {
+
+int hd_version(void) { return 100; }
+
+const char* hd_status_string(int s)
+{
+    switch (s) {
+        case HD_OK: return "ok";
+        case HD_ERR_NULL: return "null pointer argument";
+        case HD_ERR_WINDOW_HIGH: return "window size larger than the raster";
+        case HD_ERR_WINDOW_EVEN: return "window size is even";
+        case HD_ERR_ALIGN: return "pointer or pitch not 16-byte aligned";
+        case HD_ERR_CUDA: return "CUDA error";
+        case HD_ERR_UNSUPPORTED: return "unsupported parameter combination";
+        case HD_ERR_ARG: return "invalid argument";
+        case HD_ERR_WORKSPACE: return "workspace too small";
+        default: return "unknown status";
+    }
+}
+
+int hd_last_cuda_error(void) { return g_last_cuda_error; }
+const char* hd_last_cuda_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_cuda_error); }
+
+int hd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t hd_launch_count(void) { return g_launches.load(); }
+void hd_reset_launch_count(void) { g_launches.store(0); }
+
+int64_t hd_pitch_elems(int64_t nx, int dtype)
+{
+    const int64_t es = (int64_t)hd_dtype_size(dtype);
+    if (es == 0) return -1;
+    const int64_t q = 128 / es;  // 128-byte rows: every row starts on a cache line
+    return (nx + q - 1) / q * q;
+}
+
+int hd_memcpy2d_h2d(void* dst, int64_t dp, const void* src, int64_t sp, int64_t w, int64_t rows, void* stream)
+{
+    if (!dst || !src) return HD_ERR_NULL;
+    HD_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)dp, src, (size_t)sp, (size_t)w, (size_t)rows, cudaMemcpyHostToDevice,
+                                 (cudaStream_t)stream));
+    return HD_OK;
+}
+int hd_memcpy2d_d2h(void* dst, int64_t dp, const void* src, int64_t sp, int64_t w, int64_t rows, void* stream)
+{
+    if (!dst || !src) return HD_ERR_NULL;
+    HD_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)dp, src, (size_t)sp, (size_t)w, (size_t)rows, cudaMemcpyDeviceToHost,
+                                 (cudaStream_t)stream));
+    return HD_OK;
+}
+int hd_stream_synchronize(void* stream)
+{
+    HD_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return HD_OK;
+}
+
+}  // extern "C"

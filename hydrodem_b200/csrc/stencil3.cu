@@ -1,0 +1,207 @@
+// 3x3 stencils of the conditioning chain.
+//
+//   hd_nanfix     CorrectNANValues.apply   custom_filters.py:286-317   (bit-exact float32 mean, numpy order)
+//   hd_isolated   IsolatedPoints.apply     custom_filters.py:345-366
+//   hd_convolve3  Convolve.apply + Around  extension_filters.py:166-184, :113-130 (PostProcessingFinal)
+//
+// HBM-bound: 4 B read + 4 B written per cell (8 + 8 for float64 rasters).  A 32x128 tile with a one-cell
+// halo is staged by TMA; each thread produces 4 consecutive cells of 4 rows and stores them as one
+// 16-byte coalesced write.
+#include "common.cuh"
+#include "tile_common.cuh"
+
+namespace {
+
+constexpr int IN_H3 = TH + 2;
+
+// ---- CorrectNANValues ----------------------------------------------------------------------------
+// numpy float32 add.reduce over the compacted neighbour list (row-major, centre dropped, NaN and
+// negatives dropped): n < 8 -> left-to-right from -0.0; n == 8 -> ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).
+__device__ __forceinline__ float nanfix_mean(const float (&v)[8])
+{
+    bool ok[8];
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ok[k] = v[k] >= 0.f; n += ok[k]; }   // NaN >= 0 is false  (:314-315)
+    if (n == 0) return __int_as_float(0x7fc00000);                     // mean of empty slice
+    float s;
+    if (n == 8) {
+        s = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[1]), __fadd_rn(v[2], v[3])),
+                      __fadd_rn(__fadd_rn(v[4], v[5]), __fadd_rn(v[6], v[7])));
+    } else {
+        s = -0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (ok[k]) s = __fadd_rn(s, v[k]);
+    }
+    return __fdiv_rn(s, (float)n);                                     // float32 sum / count  (:316)
+}
+
+template <int MODE, typename T>   // MODE 0 = nanfix, 1 = isolated; T = raster dtype (windows are cast to float32)
+__global__ void __launch_bounds__(NT) fix3_kernel(const __grid_constant__ CUtensorMap tm_in, T* __restrict__ out,
+                                                  int64_t out_pitch, int64_t ny, int64_t nx, int in_w, int tiles_x,
+                                                  int ntiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    const uint32_t stage_bytes = (uint32_t)((in_w * IN_H3 * sizeof(T) + 127) / 128 * 128);
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * IN_H3 * sizeof(T)), 1, 1}};
+    tile_loop<1>(smem, stage_bytes, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        const T* tile = reinterpret_cast<const T*>(st);
+#pragma unroll
+        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+            const int idx = rep * NT + threadIdx.x;
+            const int ro = idx >> 5, c4 = idx & 31;
+            const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+            if (y >= ny || x >= nx) continue;
+            const T* c = tile + (ro + 1) * in_w + 4 * c4 + 1;
+            T v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float ctr = (float)c[j];                 // grid.astype('float32'), sliding_window.py:132
+                T r = c[j];
+                const bool interior = y >= 1 && y < ny - 1 && x + j >= 1 && x + j < nx - 1;
+                // iter_over_ones gate: int(v) == 1  (sliding_window.py:192)
+                const bool gate = MODE == 0 ? (ctr < 0.f) : (ctr >= 1.f && ctr < 2.f);
+                if (interior && gate) {
+                    const float nb[8] = {(float)c[j - in_w - 1], (float)c[j - in_w],     (float)c[j - in_w + 1],
+                                         (float)c[j - 1],        (float)c[j + 1],        (float)c[j + in_w - 1],
+                                         (float)c[j + in_w],     (float)c[j + in_w + 1]};
+                    if (MODE == 0) {
+                        r = (T)nanfix_mean(nb);
+                    } else {
+                        bool any = false;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) any |= nb[k] > 0.f;     // NaN > 0 false (:364-365)
+                        r = any ? (T)1 : (T)0;
+                    }
+                }
+                v[j] = r;
+            }
+            store4v<T>(out, out_pitch, y, x, nx, v);
+        }
+    });
+}
+
+// ---- Convolve (3x3, reflect) + Around --------------------------------------------------------------
+struct Conv3Params { double w[9]; double divisor; int do_round; };
+
+template <typename T> __device__ __forceinline__ T div_round(T v, double divisor, int do_round);
+template <> __device__ __forceinline__ float div_round<float>(float v, double divisor, int do_round)
+{
+    float r = __fdiv_rn(v, (float)divisor);
+    return do_round ? rintf(r) : r;
+}
+template <> __device__ __forceinline__ double div_round<double>(double v, double divisor, int do_round)
+{
+    double r = __ddiv_rn(v, divisor);
+    return do_round ? rint(r) : r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUtensorMap tm_in, T* __restrict__ out,
+                                                   int64_t out_pitch, int64_t ny, int64_t nx, Conv3Params p, int in_w,
+                                                   int tiles_x, int ntiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    const uint32_t stage_bytes = (uint32_t)((in_w * IN_H3 * sizeof(T) + 127) / 128 * 128);
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * IN_H3 * sizeof(T)), 1, 1}};
+    tile_loop<1>(smem, stage_bytes, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        T* tile = reinterpret_cast<T*>(st);
+        patch_reflect<T>(tile, in_w, IN_H3, ty0 - 1, tx0 - 1, ny, nx);
+#pragma unroll
+        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+            const int idx = rep * NT + threadIdx.x;
+            const int ro = idx >> 5, c4 = idx & 31;
+            const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+            if (y >= ny || x >= nx) continue;
+            const T* c = tile + ro * in_w + 4 * c4;          // top-left of the first window
+            T v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double acc = 0.0;                             // NI_Correlate: tmp = 0; tmp += in * w, row-major
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const double w = p.w[dy * 3 + dx];
+                        if (w != 0.0) acc = __dadd_rn(acc, __dmul_rn((double)c[dy * in_w + dx + j], w));
+                    }
+                v[j] = div_round<T>((T)acc, p.divisor, p.do_round);
+            }
+            store4v<T>(out, out_pitch, y, x, nx, v);
+        }
+    });
+}
+
+template <int MODE>
+int launch_fix3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
+                void* stream)
+{
+    if (!in || !out) return HD_ERR_NULL;
+    if (int e = check_window(ny, nx, 3)) return e;
+    if (in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    if (dtype != HD_F32 && dtype != HD_F64) return HD_ERR_UNSUPPORTED;
+    const size_t es = hd_dtype_size(dtype);
+    const int in_w = dtype == HD_F32 ? TW + 4 : TW + 2;       // 130 cells rounded up to 16 bytes
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, in_w, IN_H3, false)) return e;
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    const size_t smem = 2 * ((in_w * IN_H3 * es + 127) / 128 * 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == HD_F32) {
+        fix3_kernel<MODE, float><<<grid_for(ntiles, 4), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, in_w, tiles_x,
+                                                                      ntiles);
+    } else {
+        HD_CUDA_OK(cudaFuncSetAttribute(fix3_kernel<MODE, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fix3_kernel<MODE, double><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, in_w, tiles_x,
+                                                                       ntiles);
+    }
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+}  // namespace
+
+extern "C" int hd_nanfix(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny,
+                         int64_t nx, void* stream)
+{
+    return launch_fix3<0>(in, in_pitch, out, out_pitch, dtype, ny, nx, stream);
+}
+
+extern "C" int hd_isolated(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny,
+                           int64_t nx, void* stream)
+{
+    return launch_fix3<1>(in, in_pitch, out, out_pitch, dtype, ny, nx, stream);
+}
+
+extern "C" int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny,
+                            int64_t nx, const double* weights, double divisor, int do_round, void* stream)
+{
+    if (!in || !out || !weights) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    if (dtype != HD_F32 && dtype != HD_F64) return HD_ERR_UNSUPPORTED;
+    Conv3Params p;
+    for (int k = 0; k < 9; ++k) p.w[k] = weights[k];
+    p.divisor = divisor;
+    p.do_round = do_round;
+    const size_t es = hd_dtype_size(dtype);
+    const int in_w = dtype == HD_F32 ? TW + 4 : TW + 2;
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, in_w, IN_H3, false)) return e;
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    const size_t smem = 2 * ((in_w * IN_H3 * es + 127) / 128 * 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == HD_F32) {
+        conv3_kernel<float><<<grid_for(ntiles, 4), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, p, in_w, tiles_x, ntiles);
+    } else {
+        HD_CUDA_OK(cudaFuncSetAttribute(conv3_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv3_kernel<double><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, p, in_w, tiles_x,
+                                                                  ntiles);
+    }
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}

@@ -1,0 +1,128 @@
+/*
+ * hydrodem_b200 -- C ABI of the B200-native HydroDEM raster-conditioning hot path.
+ *
+ * This is the drop-in boundary.  The reference (CGuerreroCordova/HydroDEM) has no FFI: its hot
+ * path is the Python protocol  Filter.apply(ndarray) -> ndarray  (filters/__init__.py:23-39).  The
+ * entry points below are what a binding for that protocol calls, one per reference filter class;
+ * each declaration cites the reference code it replaces (paths under cguerrero/hydrodem/).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in the signatures; `stream` is a cudaStream_t passed as void*
+ *     (NULL = default stream).  All raster pointers are DEVICE pointers.
+ *   - rasters are row-major; `*_pitch` is the row stride in ELEMENTS.  Windowed filters stage tiles
+ *     with TMA, which needs the base pointer and the row stride in bytes to be multiples of 16
+ *     (hd_pitch_elems gives a conforming pitch); otherwise HD_ERR_ALIGN is returned.
+ *   - every function returns HD_OK (0) or a negative hd_status; nothing is allocated inside except
+ *     where a workspace argument says so.  Kernels are launched asynchronously on `stream`.
+ *   - there is no CPU fallback: without a CUDA device every compute call returns HD_ERR_CUDA.
+ */
+#ifndef HYDRODEM_B200_H
+#define HYDRODEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    HD_OK = 0,
+    HD_ERR_NULL = -1,         /* null pointer argument */
+    HD_ERR_WINDOW_HIGH = -2,  /* window larger than the raster: WindowSizeHighError, sliding_window.py:152-153 */
+    HD_ERR_WINDOW_EVEN = -3,  /* even window: WindowSizeEvenError, sliding_window.py:154-155 */
+    HD_ERR_ALIGN = -4,        /* base pointer / pitch not 16-byte aligned (TMA) */
+    HD_ERR_CUDA = -5,         /* CUDA runtime error, see hd_last_cuda_error() */
+    HD_ERR_UNSUPPORTED = -6,  /* parameter combination not implemented (e.g. window too large for the tile) */
+    HD_ERR_ARG = -7,          /* invalid argument value */
+    HD_ERR_WORKSPACE = -8     /* workspace too small */
+} hd_status;
+
+typedef enum {
+    HD_U8 = 0,   /* also numpy bool */
+    HD_F32 = 1,
+    HD_F64 = 2,
+    HD_I64 = 3,
+    HD_C64 = 4,  /* interleaved float re, im  */
+    HD_C128 = 5, /* interleaved double re, im */
+    HD_I32 = 6
+} hd_dtype;
+
+/* ---- runtime --------------------------------------------------------------------------------- */
+int hd_version(void);
+const char* hd_status_string(int status);
+int hd_last_cuda_error(void);
+const char* hd_last_cuda_error_string(void);
+int hd_device_count(void);
+/* kernels launched by this library since the last reset (bench.py's gpu_launches) */
+int64_t hd_launch_count(void);
+void hd_reset_launch_count(void);
+/* smallest pitch (elements) >= nx that satisfies the alignment rules for `dtype` rasters */
+int64_t hd_pitch_elems(int64_t nx, int dtype);
+/* pitched host<->device copies (cudaMemcpy2DAsync); pitches and width in BYTES */
+int hd_memcpy2d_h2d(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
+                    int64_t rows, void* stream);
+int hd_memcpy2d_d2h(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
+                    int64_t rows, void* stream);
+int hd_stream_synchronize(void* stream);
+
+/* ---- elementwise filters (filters/simple_filters.py, extension_filters.py:12-130) -------------- */
+typedef enum {
+    HD_OP_COPY = 0, /* out = (out_dtype) a                      -- dtype conversion                        */
+    HD_OP_MUL = 1,  /* out = b * a      ProductFilter.apply      simple_filters.py:165-180                 */
+    HD_OP_ADD = 2,  /* out = b + a      AdditionFilter.apply     simple_filters.py:214-229                 */
+    HD_OP_RSUB = 3, /* out = b - a      SubtractionFilter.apply  simple_filters.py:261-275 (b = minuend)   */
+    HD_OP_LT = 4,   /* out = a < b      LowerThan.apply          simple_filters.py:35-50                   */
+    HD_OP_GT = 5,   /* out = a > b      GreaterThan.apply        simple_filters.py:81-96                   */
+    HD_OP_ABS = 6,  /* out = |a|        AbsoluteValues.apply     extension_filters.py:78-95 (C64 -> F32)   */
+    HD_OP_RINT = 7, /* out = around(a)  Around.apply             extension_filters.py:113-130 (half-even)  */
+    HD_OP_XOR = 8   /* out = b ^ a      BitwiseXOR.apply         extension_filters.py:43-60 (U8/I64)       */
+} hd_elementwise_op;
+/* `b` may be NULL: then the scalar `b_scalar` is the second operand.  Arithmetic is done in double and
+ * rounded once to out_dtype (innocuous double rounding: identical to native float32 arithmetic). */
+int hd_elementwise(int op, const void* a, int a_dtype, int64_t a_pitch, const void* b, int b_dtype, int64_t b_pitch,
+                   double b_scalar, void* out, int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx, void* stream);
+
+/* ---- windowed filters (filters/custom_filters.py) ------------------------------------------------ */
+/* ExpandFilter.apply, custom_filters.py:102-125.  in: F32 or U8; out: U8 / F32 / F64, every cell written
+ * (1 where any non-NaN cell of the corner-less ws*ws window is > 0, else 0; ws/2 border = 0). */
+int hd_expand(const void* in, int in_dtype, int64_t in_pitch, void* out, int out_dtype, int64_t out_pitch, int64_t ny,
+              int64_t nx, int ws, void* stream);
+/* MajorityFilter.apply, custom_filters.py:48-73.  in: F32; out: F32 / F64, every cell written (mode of the
+ * corner-less window if its count >= min_count, else 0; border 0).  min_count = floor((ws*ws-1)*0.7)+1. */
+int hd_majority(const void* in, int64_t in_pitch, void* out, int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx,
+                int ws, int min_count, void* stream);
+/* CorrectNANValues.apply, custom_filters.py:286-317 (window 3).  dtype F32 or F64 (in and out alike),
+ * out-of-place Jacobi: out = in except interior cells whose float32 cast is < 0, which get the float32 mean
+ * (numpy summation order) of their non-NaN, >= 0 float32 neighbours; no such neighbour -> NaN. */
+int hd_nanfix(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
+              void* stream);
+/* IsolatedPoints.apply, custom_filters.py:345-366 (window 3).  dtype F32 or F64, out-of-place: interior cells
+ * with trunc(float32(v)) == 1 become 1 if any of the 8 neighbours is > 0 else 0; other cells are copied. */
+int hd_isolated(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
+                void* stream);
+
+/* ---- morphology (filters/extension_filters.py, scipy.ndimage) ------------------------------------ */
+typedef enum { HD_MORPH_ERODE = 0, HD_MORPH_DILATE = 1, HD_MORPH_CLOSE = 2, HD_MORPH_OPEN = 3 } hd_morph_op;
+/* BinaryErosion.apply, extension_filters.py:218-235 (scipy.ndimage.binary_erosion(iterations=n)) and
+ * BinaryClosing.apply, :276-293 (binary_closing(structure=None | ones((3,3)))).  in: F32 or U8, non-zero =
+ * True (NaN is True); out: U8 0/1.  Structuring element: 3x3 cross (full_structure = 0, scipy default) or
+ * 3x3 square; border_value = 0 throughout.  iterations <= 8 (erode/dilate) or <= 4 (close/open). */
+int hd_binary_morph(const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx,
+                    int op, int full_structure, int iterations, void* stream);
+/* GreyDilation.apply, extension_filters.py:328-345 with size=(s, s), s odd <= 17: flat s*s maximum filter,
+ * mode='reflect'.  dtype F32 or F64 (in and out alike).  NaN cells are skipped by the maximum (inputs are NaN-free in the chain). */
+int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
+                  int size, void* stream);
+/* Convolve.apply + Around.apply = PostProcessingFinal, extension_filters.py:166-184, :113-130,
+ * custom_filters.py:1124-1125.  3x3 correlation with `weights` (9 doubles, row-major, already reversed for
+ * a convolution), mode='reflect', double accumulator in row-major order (scipy NI_Correlate), result cast
+ * to the raster dtype, divided by `divisor` in that dtype, then rounded half-to-even if do_round.
+ * dtype: F32 or F64 (in and out alike). */
+int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
+                 const double* weights, double divisor, int do_round, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDRODEM_B200_H */

@@ -38,6 +38,8 @@ int hd_num_sms();
 size_t hd_dtype_size(int dtype);
 
 static inline int hd_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// x halo rounded up to a 16-byte multiple for elements of `es` bytes
+__host__ __device__ constexpr int hd_halo_x(int h, int es) { return (h * es + 15) / 16 * 16 / es; }
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
@@ -87,6 +89,10 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
 }
 
 // One input plane of a staged tile.
+// TMA rule (measured on B200, tools/probe/tma_probe.cu): the innermost box coordinate times the element size
+// must be a multiple of 16 bytes, otherwise the load traps with "illegal instruction".  Row coordinates are
+// free.  So the x halo of a plane is rounded up to 16 bytes (hd_halo_x) and kernels index the staged tile
+// with the offset hd_halo_x(h) - h.
 struct TilePlane {
     const CUtensorMap* tm;   // tensor map (kernel __grid_constant__ parameter)
     uint32_t smem_off;       // byte offset of this plane inside a stage (128-byte aligned)

@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(NT) majority_kernel(const __grid_constant__ CU
 {
     constexpr int WS = 2 * H + 1;
     constexpr int CW = TW + 2 * H;                 // window columns touched by a tile
-    constexpr int IN_W = (CW + 3) / 4 * 4;
+    constexpr int HX = hd_halo_x(H, 4);            // x halo of the staged box (16-byte TMA rule)
+    constexpr int XOFF = HX - H;
+    constexpr int IN_W = TW + 2 * HX;
     constexpr int IN_H = TH + 2 * H;
     constexpr int NWIN = WS * WS - 4;              // cells of the corner-less window
     constexpr uint32_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(NT) majority_kernel(const __grid_constant__ CU
     uint8_t* cnt_in = reinterpret_cast<uint8_t*>(cand_fu + TH * CW);
     uint8_t* cnt_fu = cnt_in + TH * CW;
 
-    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * 4), H, H}};
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * 4), HX, H}};
     tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const float* tile = reinterpret_cast<const float*>(st);
         // ---- 1. column summaries ---------------------------------------------------------------
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(NT) majority_kernel(const __grid_constant__ CU
             const int c = item % CW, s = item / CW;
             float v[STRIP + 2 * H];
 #pragma unroll
-            for (int r = 0; r < STRIP + 2 * H; ++r) v[r] = tile[(s * STRIP + r) * IN_W + c];
+            for (int r = 0; r < STRIP + 2 * H; ++r) v[r] = tile[(s * STRIP + r) * IN_W + c + XOFF];
 #pragma unroll
             for (int o = 0; o < STRIP; ++o) {
                 BM b{0.f, 0};
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(NT) majority_kernel(const __grid_constant__ CU
                 bm_merge(b, cand_in[base + 2 * H], (int)cnt_in[base + 2 * H]);
                 // true count of the candidate <= (NWIN + counter) / 2
                 if (NWIN + b.n >= 2 * min_count) {
-                    const float* w = tile + ro * IN_W + xo;            // top-left of the window
+                    const float* w = tile + ro * IN_W + xo + XOFF;     // top-left of the window
                     int count = 0;
                     float first = b.c;
                     bool found = false;
@@ -121,7 +123,7 @@ template <int H, typename OutT>
 int launch(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx, int min_count,
            cudaStream_t stream)
 {
-    constexpr int CW = TW + 2 * H, IN_W = (CW + 3) / 4 * 4, IN_H = TH + 2 * H;
+    constexpr int CW = TW + 2 * H, IN_W = TW + 2 * hd_halo_x(H, 4), IN_H = TH + 2 * H;
     constexpr size_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
     constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * 4 + 2 * TH * CW;
     CUtensorMap tm;

@@ -14,9 +14,9 @@ namespace {
 
 constexpr int MAX_HALO = 8;
 constexpr int MAX_IN_H = TH + 2 * MAX_HALO;            // 48
-constexpr int MAX_IN_W = TW + 2 * MAX_HALO;            // 144
+constexpr int MAX_IN_W = TW + 2 * 16;                  // 160: u8 planes need a 16-cell x halo
 constexpr int NWORD = (MAX_IN_W + 31) / 32;            // 5
-constexpr int STAGE_BYTES = MAX_IN_H * MAX_IN_W * 4;   // sized for f32, u8 uses a quarter
+constexpr int STAGE_BYTES = MAX_IN_H * (TW + 2 * MAX_HALO) * 4;   // sized for f32 (x halo <= 8), u8 needs less
 
 // threshold one staged tile to bits: bits[r * NWORD + k] bit i  <->  tile cell (r, 32k + i)
 template <typename InT, class Pred>
@@ -69,23 +69,24 @@ __global__ void __launch_bounds__(NT) expand_kernel(const __grid_constant__ CUte
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
     __shared__ uint32_t bits[MAX_IN_H * NWORD];
+    const int hx = hd_halo_x(h, sizeof(InT)), xoff = hx - h;
     __shared__ uint32_t hfull[MAX_IN_H * 4], hinner[MAX_IN_H * 4];
     __shared__ uint32_t res[TH * 4];
     const uint32_t stage_bytes = STAGE_BYTES;
-    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(InT)), h, h}};
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(InT)), hx, h}};
     tile_loop<1>(smem, stage_bytes, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const InT* tile = reinterpret_cast<const InT*>(st);
         // window[~isnan(window)] > 0  (custom_filters.py:122-123): NaN > 0 is false
         tile_to_bits<InT>(tile, in_w, in_h, bits, [](InT v) { return (float)v > 0.f; });
         __syncthreads();
-        // horizontal: output column xo looks at tile columns xo .. xo+2h (full) / xo+1 .. xo+2h-1 (top & bottom rows)
+        // horizontal: output column xo looks at tile columns xoff+xo .. xoff+xo+2h (full) / xo+1 .. xo+2h-1 (top & bottom rows)
         for (int t = threadIdx.x; t < in_h * 4; t += NT) {
             const int r = t >> 2, k = t & 3;
             const uint64_t w = win64(&bits[r * NWORD], k);
             uint64_t f = 0, in = 0;
             for (int s = 0; s <= 2 * h; ++s) {
-                f |= w >> s;
-                if (s >= 1 && s <= 2 * h - 1) in |= w >> s;
+                f |= w >> (s + xoff);
+                if (s >= 1 && s <= 2 * h - 1) in |= w >> (s + xoff);
             }
             hfull[t] = (uint32_t)f;
             hinner[t] = (uint32_t)in;
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(NT) morph_kernel(const __grid_constant__ CUten
     __shared__ uint64_t bars[2];
     __shared__ uint32_t bufA[(MAX_IN_H + 2) * NWORD], bufB[(MAX_IN_H + 2) * NWORD];
     __shared__ uint32_t res[TH * 4];
-    const int h = prog.nsteps;
-    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(InT)), h, h}};
+    const int h = prog.nsteps, hx = hd_halo_x(h, sizeof(InT));
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(InT)), hx, h}};
     // rows 0 and in_h+1 of the bit buffers are zero guards
     for (int t = threadIdx.x; t < NWORD; t += NT) {
         bufA[t] = bufB[t] = 0u;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(NT) morph_kernel(const __grid_constant__ CUten
                     const int64_t gy = (int64_t)ty0 - h + r;
                     uint32_t m = 0u;
                     if (gy >= 0 && gy < ny) {
-                        const int64_t gx0 = (int64_t)tx0 - h + 32 * k;      // global x of bit 0
+                        const int64_t gx0 = (int64_t)tx0 - hx + 32 * k;     // global x of bit 0
                         const int64_t lo = gx0 < 0 ? -gx0 : 0;
                         const int64_t hi = (nx - gx0) < 32 ? (nx - gx0) : 32;   // exclusive
                         if (hi > lo) m = (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(NT) morph_kernel(const __grid_constant__ CUten
         if (threadIdx.x < TH * 4) {
             const int ro = threadIdx.x >> 2, k = threadIdx.x & 3;
             const uint64_t w = win64(cur + (ro + h) * NWORD, k);
-            res[threadIdx.x] = (uint32_t)(w >> h);
+            res[threadIdx.x] = (uint32_t)(w >> hx);
         }
         __syncthreads();
         write_bits<uint8_t>(res, out, out_pitch, ty0, tx0, ny, nx, 0);
@@ -195,16 +196,17 @@ __global__ void __launch_bounds__(NT) maxfilter_kernel(const __grid_constant__ C
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
-    constexpr uint32_t STAGE = MAX_IN_H * MAX_IN_W * sizeof(T);
+    constexpr uint32_t STAGE = MAX_IN_H * (TW + 2 * MAX_HALO) * sizeof(T);
     T* hmax = reinterpret_cast<T*>(smem + 2 * STAGE);          // [in_h][TW] horizontal maxima
-    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(T)), h, h}};
+    const int hx = hd_halo_x(h, sizeof(T)), xoff = hx - h;
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(T)), hx, h}};
     tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         T* tile = reinterpret_cast<T*>(st);
-        patch_reflect<T>(tile, in_w, in_h, ty0 - h, tx0 - h, ny, nx);
+        patch_reflect<T>(tile, in_w, in_h, ty0 - h, tx0 - hx, ny, nx);
         for (int t = threadIdx.x; t < in_h * TW; t += NT) {
             const int r = t / TW, c = t - r * TW;
-            T m = tile[r * in_w + c];
-            for (int s = 1; s <= 2 * h; ++s) m = tmax<T>(m, tile[r * in_w + c + s]);
+            T m = tile[r * in_w + c + xoff];
+            for (int s = 1; s <= 2 * h; ++s) m = tmax<T>(m, tile[r * in_w + c + xoff + s]);
             hmax[t] = m;
         }
         __syncthreads();
@@ -250,8 +252,8 @@ extern "C" int hd_expand(const void* in, int in_dtype, int64_t in_pitch, void* o
     const int h = ws / 2;
     if (h < 1 || h > MAX_HALO - 1) return HD_ERR_UNSUPPORTED;
     if (in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
-    const int align = in_dtype == HD_U8 ? 16 : 4;
-    const int in_w = (TW + 2 * h + align - 1) / align * align, in_h = TH + 2 * h;
+    if (in_dtype != HD_U8 && in_dtype != HD_F32) return HD_ERR_UNSUPPORTED;
+    const int in_w = TW + 2 * hd_halo_x(h, (int)hd_dtype_size(in_dtype)), in_h = TH + 2 * h;
     if (in_w > MAX_IN_W) return HD_ERR_UNSUPPORTED;
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, in_dtype, ny, nx, in_pitch, in_w, in_h, false)) return e;
@@ -290,8 +292,8 @@ extern "C" int hd_binary_morph(const void* in, int in_dtype, int64_t in_pitch, v
         return HD_ERR_ARG;
     }
     const int h = prog.nsteps;
-    const int align = in_dtype == HD_U8 ? 16 : 4;
-    const int in_w = (TW + 2 * h + align - 1) / align * align, in_h = TH + 2 * h;
+    if (in_dtype != HD_U8 && in_dtype != HD_F32) return HD_ERR_UNSUPPORTED;
+    const int in_w = TW + 2 * hd_halo_x(h, (int)hd_dtype_size(in_dtype)), in_h = TH + 2 * h;
     if (in_w > MAX_IN_W) return HD_ERR_UNSUPPORTED;
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, in_dtype, ny, nx, in_pitch, in_w, in_h, false)) return e;
@@ -325,11 +327,11 @@ extern "C" int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_
     if (in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
     if (dtype != HD_F32 && dtype != HD_F64) return HD_ERR_UNSUPPORTED;
     const size_t es = hd_dtype_size(dtype);
-    const int in_w = (TW + 2 * h + 3) / 4 * 4, in_h = TH + 2 * h;
+    const int in_w = TW + 2 * hd_halo_x(h, (int)es), in_h = TH + 2 * h;
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, in_w, in_h, false)) return e;
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
-    const size_t smem = 2 * MAX_IN_H * MAX_IN_W * es + MAX_IN_H * TW * es;
+    const size_t smem = 2 * MAX_IN_H * (TW + 2 * MAX_HALO) * es + MAX_IN_H * TW * es;
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == HD_F32) {
         HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

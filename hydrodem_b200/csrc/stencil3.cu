@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(NT) fix3_kernel(const __grid_constant__ CUtens
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
     const uint32_t stage_bytes = (uint32_t)((in_w * IN_H3 * sizeof(T) + 127) / 128 * 128);
-    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * IN_H3 * sizeof(T)), 1, 1}};
+    constexpr int HX = hd_halo_x(1, sizeof(T));
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * IN_H3 * sizeof(T)), HX, 1}};
     tile_loop<1>(smem, stage_bytes, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const T* tile = reinterpret_cast<const T*>(st);
 #pragma unroll
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(NT) fix3_kernel(const __grid_constant__ CUtens
             const int ro = idx >> 5, c4 = idx & 31;
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
-            const T* c = tile + (ro + 1) * in_w + 4 * c4 + 1;
+            const T* c = tile + (ro + 1) * in_w + 4 * c4 + HX;
             T v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -106,17 +107,18 @@ __global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUten
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
     const uint32_t stage_bytes = (uint32_t)((in_w * IN_H3 * sizeof(T) + 127) / 128 * 128);
-    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * IN_H3 * sizeof(T)), 1, 1}};
+    constexpr int HX = hd_halo_x(1, sizeof(T));
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * IN_H3 * sizeof(T)), HX, 1}};
     tile_loop<1>(smem, stage_bytes, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         T* tile = reinterpret_cast<T*>(st);
-        patch_reflect<T>(tile, in_w, IN_H3, ty0 - 1, tx0 - 1, ny, nx);
+        patch_reflect<T>(tile, in_w, IN_H3, ty0 - 1, tx0 - HX, ny, nx);
 #pragma unroll
         for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
             const int idx = rep * NT + threadIdx.x;
             const int ro = idx >> 5, c4 = idx & 31;
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
-            const T* c = tile + ro * in_w + 4 * c4;          // top-left of the first window
+            const T* c = tile + ro * in_w + 4 * c4 + HX - 1;  // top-left of the first window
             T v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -144,7 +146,7 @@ int launch_fix3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, 
     if (in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
     if (dtype != HD_F32 && dtype != HD_F64) return HD_ERR_UNSUPPORTED;
     const size_t es = hd_dtype_size(dtype);
-    const int in_w = dtype == HD_F32 ? TW + 4 : TW + 2;       // 130 cells rounded up to 16 bytes
+    const int in_w = TW + 2 * hd_halo_x(1, (int)es);           // one-cell halo rounded up to 16 bytes per side
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, in_w, IN_H3, false)) return e;
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
@@ -188,7 +190,7 @@ extern "C" int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t
     p.divisor = divisor;
     p.do_round = do_round;
     const size_t es = hd_dtype_size(dtype);
-    const int in_w = dtype == HD_F32 ? TW + 4 : TW + 2;
+    const int in_w = TW + 2 * hd_halo_x(1, (int)es);
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, in_w, IN_H3, false)) return e;
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;

@@ -39,6 +39,21 @@ SIGNATURES = {
     "hd_majority": (_i, [_p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),
     "hd_nanfix": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),
     "hd_isolated": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),
+    "hd_quadratic": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
+    "hd_groves_correction": (_i, [_p, _i, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _i, _d, _p]),
+    "hd_median": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _i, _p]),
+    "hd_hollow_mean_detect": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _i, _d, _p]),
+    "hd_fourier_mask_assemble": (_i, [_p, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),
+    "hd_fft2_plan_create": (_i, [_i64, _i64, ctypes.POINTER(_p)]),
+    "hd_fft2_plan_destroy": (_i, [_p]),
+    "hd_fft2_workspace_bytes": (_i64, [_i64, _i64]),
+    "hd_fft2_forward_shift_abs": (_i, [_p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p]),
+    "hd_fft2_masked_inverse_abs": (_i, [_p, _p, _i64, _p, _i64, _p, _i, _i64, _p, _i64, _p]),
+    "hd_fft2_c2c": (_i, [_p, _p, _i, _i64, _p, _i64, _i, _p, _i64, _p]),
+    "hd_fftshift2": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
+    "hd_pdfill_workspace_bytes": (_i64, [_i64, _i64]),
+    "hd_pdfill": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _i, ctypes.POINTER(_i), _p]),
+    "hd_d8": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_binary_morph": (_i, [_p, _i, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _p]),
     "hd_max_filter": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
     "hd_convolve3": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, ctypes.POINTER(_d), _d, _i, _p]),

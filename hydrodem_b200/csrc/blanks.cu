@@ -1,0 +1,192 @@
+// Spectrum-peak detector of the Fourier stage and the mask assembly.
+//
+//   hd_hollow_mean_detect    BlanksFourier.apply        filters/custom_filters.py:395-427
+//   hd_fourier_mask_assemble FourierProcessQuarters     filters/custom_filters.py:968-1050
+//
+// BlanksFourier visits EVERY cell of a spectrum quarter with a 55x55 window clipped to the quarter (NaN
+// padding, sliding_window.py:400-418) whose central 5x5 block is blanked (InnerWindow + NoCenterWindow),
+// takes np.nanmean of what is left and flags the cell when centre > 4 * mean.
+//
+// Kernel: a 64x64 tile with a 27-cell halo is staged by TMA (zero fill outside the quarter = "not counted"),
+// a float64 integral image of the 118x120 box is built in shared memory with warp scans (rows, then
+// columns), and each output needs 8 integral-image reads: big box minus inner box.  The number of valid
+// cells is analytic (clipped 55x55 minus clipped 5x5).  float64 sums of float32 data are exact to ~1e-16, the
+// reference's float32 pairwise nanmean to ~1e-7: the stage is tolerance class, the mask is expected to be
+// identical (mismatch count reported by the tests).  NaN cells INSIDE the quarter are not skipped (they
+// poison the windows that contain them); |F| is NaN-free unless the DEM itself has NaN.
+//
+// Algorithmic HBM traffic per pass: 4 B read + 4 B (modified image) + 1 B (mask) written (+1 B previous mask).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BT = 64;          // tile edge (outputs)
+constexpr int BNT = 512;        // threads per CTA
+constexpr int WS = 55, INNER = 5, H = WS / 2, HI = INNER / 2;
+constexpr int HX = hd_halo_x(H, 4);                 // 28
+constexpr int XOFF = HX - H;                        // 1
+constexpr int IN_W = BT + 2 * HX;                   // 120
+constexpr int IN_H = BT + 2 * H;                    // 118
+constexpr int IS = IN_W + 1;                        // integral-image row stride (odd -> conflict-free column scans)
+constexpr uint32_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
+constexpr size_t SMEM = STAGE + (size_t)(IN_H + 1) * IS * sizeof(double);
+
+__device__ __forceinline__ double warp_inclusive_scan(double v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                        const uint8_t* __restrict__ mask_prev, int64_t prev_pitch,
+                                                        uint8_t* __restrict__ mask_out, int64_t mask_pitch,
+                                                        float* __restrict__ modified, int64_t mod_pitch, int64_t ny,
+                                                        int64_t nx, float factor, int tiles_x, int ntiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    double* I = reinterpret_cast<double*>(smem + STAGE);       // [(IN_H + 1)][IS], I[r][c] = sum tile[<r][<c]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * 4), HX, H}};
+    for (int t = threadIdx.x; t < IS; t += BNT) I[t] = 0.0;                    // row 0
+    for (int t = threadIdx.x; t <= IN_H; t += BNT) I[t * IS] = 0.0;            // column 0
+    tile_loop<1, 1>(smem, STAGE, bars, planes, BT, BT, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        const float* tile = reinterpret_cast<const float*>(st);
+        // ---- row prefix sums: I[r+1][c+1] = sum_{c' <= c} tile[r][c'] ----------------------------------
+        for (int r = warp; r < IN_H; r += BNT / 32) {
+            double carry = 0.0;
+#pragma unroll
+            for (int j = 0; j < (IN_W + 31) / 32; ++j) {
+                const int c = 32 * j + lane;
+                const double v = (c < IN_W) ? (double)tile[r * IN_W + c] : 0.0;
+                const double s = warp_inclusive_scan(v, lane) + carry;
+                if (c < IN_W) I[(r + 1) * IS + c + 1] = s;
+                carry = __shfl_sync(0xffffffffu, s, 31);
+            }
+        }
+        __syncthreads();
+        // ---- column prefix sums over the row prefixes -------------------------------------------------------
+        for (int c = warp + 1; c <= IN_W; c += BNT / 32) {
+            double carry = 0.0;
+#pragma unroll
+            for (int j = 0; j < (IN_H + 31) / 32; ++j) {
+                const int r = 32 * j + lane + 1;
+                const double v = (r <= IN_H) ? I[r * IS + c] : 0.0;
+                const double s = warp_inclusive_scan(v, lane) + carry;
+                if (r <= IN_H) I[r * IS + c] = s;
+                carry = __shfl_sync(0xffffffffu, s, 31);
+            }
+        }
+        __syncthreads();
+        // ---- outputs ----------------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int rep = 0; rep < BT * BT / BNT; ++rep) {
+            const int idx = rep * BNT + threadIdx.x;
+            const int ro = idx / BT, xo = idx % BT;
+            const int64_t y = ty0 + ro, x = tx0 + xo;
+            if (y >= ny || x >= nx) continue;
+            const int r0 = ro, r1 = ro + WS, c0 = xo + XOFF, c1 = c0 + WS;
+            const double big = (I[r1 * IS + c1] - I[r0 * IS + c1]) - (I[r1 * IS + c0] - I[r0 * IS + c0]);
+            const int q0 = r0 + H - HI, q1 = q0 + INNER, d0 = c0 + H - HI, d1 = d0 + INNER;
+            const double inner = (I[q1 * IS + d1] - I[q0 * IS + d1]) - (I[q1 * IS + d0] - I[q0 * IS + d0]);
+            // valid cells: clipped 55x55 minus clipped 5x5 (the NaN padding is never counted by nanmean)
+            auto span = [](int64_t p, int64_t n, int h) {
+                const int64_t lo = p - h < 0 ? 0 : p - h, hi = p + h > n - 1 ? n - 1 : p + h;
+                return (int)(hi - lo + 1);
+            };
+            const int cnt = span(y, ny, H) * span(x, nx, H) - span(y, ny, HI) * span(x, nx, HI);
+            const float mean = (float)((big - inner) / (double)cnt);               // np.nanmean -> float32  (:421)
+            const float ctr = tile[(ro + H) * IN_W + c0 + H];
+            const bool hit = ctr > __fmul_rn(factor, mean);                        // centre > 4 * mean      (:424)
+            const uint8_t prev = mask_prev ? mask_prev[y * prev_pitch + x] : (uint8_t)0;
+            mask_out[y * mask_pitch + x] = (uint8_t)(prev + (hit ? 1 : 0));        // final_mask += filtered (:461)
+            modified[y * mod_pitch + x] = __fmul_rn(ctr, hit ? 0.f : 1.f);         // image * (1 - mask)     (:426)
+        }
+    });
+}
+
+// ---- mask assembly ------------------------------------------------------------------------------------------
+// quarters[0] -> top-left block [:my-m, :mx-m]; quarters[1] -> top-right block, shifted by the margin;
+// bottom blocks are the point mirrors; the middle row / column of odd sizes stays 0.  (:986-991, :1002-1049)
+template <typename OutT>
+__global__ void __launch_bounds__(256) assemble_kernel(const uint8_t* __restrict__ m1, int64_t p1,
+                                                       const uint8_t* __restrict__ m2, int64_t p2, OutT* __restrict__ out,
+                                                       int64_t out_pitch, int ny, int nx, int margin, int invert)
+{
+    const int my = ny / 2, y_odd = ny & 1, mx = nx / 2, x_odd = nx & 1;
+    const int64_t total = (int64_t)ny * nx;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(t / nx), x = (int)(t - (int64_t)y * nx);
+        int v = 0;
+        // position inside one of the four (my, mx) blocks, or -1 on the odd middle row / column
+        int by = -1, bx = -1, top = 0, left = 0;
+        if (y < my) { by = y; top = 1; } else if (y >= my + y_odd) { by = y - my - y_odd; }
+        if (x < mx) { bx = x; left = 1; } else if (x >= mx + x_odd) { bx = x - mx - x_odd; }
+        if (by >= 0 && bx >= 0) {
+            // bottom blocks: c3 = flip(c2) sits bottom-left, c4 = flip(c1) bottom-right
+            const int qy = top ? by : my - 1 - by;
+            const int qx = top ? bx : mx - 1 - bx;
+            const bool use_first = top ? left : !left;
+            if (use_first) {
+                if (qy < my - margin && qx < mx - margin) v = m1[(int64_t)qy * p1 + qx];
+            } else {
+                if (qy < my - margin && qx >= margin) v = m2[(int64_t)qy * p2 + (qx - margin)];
+            }
+        }
+        out[(int64_t)y * out_pitch + x] = invert ? (OutT)(1 - v) : (OutT)v;
+    }
+}
+
+}  // namespace
+
+extern "C" int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch,
+                                     void* mask_out, int64_t mask_pitch, void* modified, int64_t mod_pitch, int64_t ny,
+                                     int64_t nx, int ws, int inner, double factor, void* stream)
+{
+    if (!in || !mask_out || !modified) return HD_ERR_NULL;
+    if (ws > ny || ws > nx) return HD_ERR_WINDOW_HIGH;
+    if (ws % 2 != 1) return HD_ERR_WINDOW_EVEN;
+    if (ws != WS || inner != INNER) return HD_ERR_UNSUPPORTED;     // the reference hard-codes 55 / 5 (:417-419, :457)
+    if (in_pitch < nx || mask_pitch < nx || mod_pitch < nx || (mask_prev && prev_pitch < nx)) return HD_ERR_ARG;
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, HD_F32, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
+    const int tiles_x = hd_cdiv(nx, BT), tiles_y = hd_cdiv(ny, BT), ntiles = tiles_x * tiles_y;
+    HD_CUDA_OK(cudaFuncSetAttribute(hollow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    const int grid = ntiles < hd_num_sms() ? ntiles : hd_num_sms();
+    hollow_kernel<<<grid, BNT, SMEM, (cudaStream_t)stream>>>(tm, (const uint8_t*)mask_prev, prev_pitch, (uint8_t*)mask_out,
+                                                           mask_pitch, (float*)modified, mod_pitch, ny, nx, (float)factor,
+                                                           tiles_x, ntiles);
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+extern "C" int hd_fourier_mask_assemble(const void* q1, int64_t q1_pitch, const void* q2, int64_t q2_pitch, void* out,
+                                        int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx, int margin, int invert,
+                                        void* stream)
+{
+    if (!q1 || !q2 || !out) return HD_ERR_NULL;
+    if (ny < 2 || nx < 2 || ny > 0x7fffffff || nx > 0x7fffffff || out_pitch < nx || margin < 0) return HD_ERR_ARG;
+    if (ny / 2 - margin < 1 || nx / 2 - margin < 1) return HD_ERR_ARG;
+    if (q1_pitch < nx / 2 - margin || q2_pitch < nx / 2 - margin) return HD_ERR_ARG;
+    const int64_t total = ny * nx;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+#define HD_ASM(T, TAG)                                                                                              \
+    if (out_dtype == TAG) {                                                                                         \
+        assemble_kernel<T><<<blocks, 256, 0, s>>>((const uint8_t*)q1, q1_pitch, (const uint8_t*)q2, q2_pitch, (T*)out, \
+                                                  out_pitch, (int)ny, (int)nx, margin, invert);                   \
+        HD_LAUNCH_CHECK();                                                                                          \
+        hd_count_launch();                                                                                          \
+        return HD_OK;                                                                                               \
+    }
+    HD_ASM(uint8_t, HD_U8)
+    HD_ASM(float, HD_F32)
+    HD_ASM(double, HD_F64)
+#undef HD_ASM
+    return HD_ERR_UNSUPPORTED;
+}

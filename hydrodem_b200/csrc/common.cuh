@@ -100,14 +100,17 @@ struct TilePlane {
     int halo_x, halo_y;      // box origin = tile origin - halo
 };
 
-// Persistent, double-buffered TMA tile loop.  All threads of the CTA call it.
+// Persistent TMA tile loop, NSTAGE = 2 (double buffered, default) or 1.  All threads of the CTA call it.
 //   stage s of the ring lives at smem + s * stage_bytes; bars[0..1] are the "full" barriers.
 //   body(stage_ptr, tile_y0, tile_x0) runs with the tile resident; it must not __syncthreads-diverge.
-template <int NPLANES, class Body>
+//   With NSTAGE = 1 (kernels whose scratch leaves no room for a second buffer) the next load is issued
+//   after the body; latency is then hidden only by other resident CTAs.
+template <int NPLANES, int NSTAGE = 2, class Body>
 __device__ __forceinline__ void tile_loop(unsigned char* smem, uint32_t stage_bytes, uint64_t* bars,
                                           const TilePlane (&planes)[NPLANES], int tile_w, int tile_h, int tiles_x,
                                           int ntiles, Body&& body)
 {
+    static_assert(NSTAGE == 1 || NSTAGE == 2, "one or two stages");
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -131,13 +134,14 @@ __device__ __forceinline__ void tile_loop(unsigned char* smem, uint32_t stage_by
     int tile = blockIdx.x;
     if (threadIdx.x == 0 && tile < ntiles) issue(tile, 0);
     for (int k = 0; tile < ntiles; ++k, tile += gridDim.x) {
-        const int s = k & 1;
+        const int s = NSTAGE == 2 ? (k & 1) : 0;
         const int next = tile + gridDim.x;
         // buffer s^1 was released by the __syncthreads that ended iteration k-1
-        if (threadIdx.x == 0 && next < ntiles) issue(next, s ^ 1);
-        mbar_wait(&bars[s], (k >> 1) & 1);
+        if (NSTAGE == 2 && threadIdx.x == 0 && next < ntiles) issue(next, s ^ 1);
+        mbar_wait(&bars[s], NSTAGE == 2 ? ((k >> 1) & 1) : (k & 1));
         body(smem + s * stage_bytes, (tile / tiles_x) * tile_h, (tile % tiles_x) * tile_w);
         __syncthreads();
+        if (NSTAGE == 1 && threadIdx.x == 0 && next < ntiles) issue(next, 0);
     }
 }
 

@@ -1,0 +1,478 @@
+// 2-D Fourier stage: hand-written shared-memory FFT (no cuFFT in the product path; tests check it against
+// cuFFT / scipy).
+//
+//   hd_fft2_forward_shift_abs   FourierInitial.apply         custom_filters.py:859-877
+//                               (fftpack.fft2 -> fftshift -> abs, extension_filters.py:379, :447, :95)
+//   hd_fft2_masked_inverse_abs  DetectApplyFourier tail      custom_filters.py:1097-1100
+//                               ((1 - mask) * F_shift -> ifftshift -> ifft2 -> abs)
+//   hd_fft2_c2c / hd_fftshift2  FourierTransform / FourierITransform / FourierShift / FourierIShift wrappers
+//
+// One CTA transforms one row held entirely in shared memory (complex64).  Power-of-two lengths use an
+// iterative radix-2 FFT; every other length (3601 = 13 * 277, 519 = 3 * 173 ...) uses Bluestein's chirp-z
+// identity  X[k] = w[k] * sum_n (x[n] w[n]) conj(w)[k - n],  w[n] = exp(-i pi n^2 / N),  evaluated as a
+// circular convolution of length M = 2^ceil(log2(2N - 1)):  DIF FFT (natural -> bit-reversed), pointwise
+// product with the pre-transformed chirp (stored bit-reversed, pre-scaled by 1/M), DIT inverse FFT
+// (bit-reversed -> natural).  No bit-reversal pass is ever executed.  Chirp and twiddle tables are computed
+// on the host in double precision (n^2 mod 2N in integers) and rounded once to float.
+//
+// The 2-D transform is rows -> tiled transpose -> rows -> tiled transpose; fftshift / ifftshift, |.|, and
+// the (1 - mask) product are folded into the load / store index arithmetic of those passes, so the shifted
+// spectrum is never materialised separately.
+#include <cmath>
+#include <complex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int FNT = 512;                 // threads per FFT CTA
+constexpr int MAX_M = 16384;             // 128 KB of complex64 in shared memory
+constexpr double PI = 3.14159265358979323846;
+
+struct Plan1D {
+    int n = 0, m = 0, log2m = 0;
+    bool bluestein = false;
+    float2* d_tw = nullptr;              // [m/2]  exp(-2 pi i k / m)
+    float2* d_w = nullptr;               // [n]    chirp exp(-i pi k^2 / n)                  (Bluestein only)
+    float2* d_bhat = nullptr;            // [m]    FFT_m(conj chirp) / m, bit-reversed order (Bluestein only)
+};
+
+struct Plan2D {
+    int64_t ny = 0, nx = 0;
+    Plan1D px, py;                       // along x (length nx), along y (length ny)
+};
+
+// ---- host-side table construction ---------------------------------------------------------------------------
+void host_fft(std::vector<std::complex<double>>& a)          // in-place radix-2, natural order in and out
+{
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double ang = -2.0 * PI * (double)k / (double)len;
+                const std::complex<double> w(std::cos(ang), std::sin(ang));
+                const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+}
+
+unsigned bitrev(unsigned v, int bits)
+{
+    unsigned r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+int upload(float2** dst, const std::vector<float2>& src)
+{
+    HD_CUDA_OK(cudaMalloc((void**)dst, src.size() * sizeof(float2)));
+    HD_CUDA_OK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return HD_OK;
+}
+
+void destroy1d(Plan1D& p)
+{
+    cudaFree(p.d_tw); cudaFree(p.d_w); cudaFree(p.d_bhat);
+    p = Plan1D{};
+}
+
+int build1d(Plan1D& p, int64_t n)
+{
+    if (n < 1) return HD_ERR_ARG;
+    const bool pow2 = (n & (n - 1)) == 0;
+    int64_t m = 1;
+    if (pow2) m = n;
+    else while (m < 2 * n - 1) m <<= 1;
+    if (m > MAX_M) return HD_ERR_UNSUPPORTED;       // longer rows need a multi-pass (four-step) FFT: not built yet
+    p.n = (int)n; p.m = (int)m; p.bluestein = !pow2;
+    p.log2m = 0;
+    while ((1 << p.log2m) < m) ++p.log2m;
+    std::vector<float2> tw(m / 2 > 0 ? m / 2 : 1);
+    for (int64_t k = 0; k < m / 2; ++k) {
+        const double ang = -2.0 * PI * (double)k / (double)m;
+        tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    if (int e = upload(&p.d_tw, tw)) return e;
+    if (p.bluestein) {
+        std::vector<std::complex<double>> chirp(n);
+        for (int64_t k = 0; k < n; ++k) {
+            const int64_t q = (k * k) % (2 * n);                      // exact phase index
+            const double ang = -PI * (double)q / (double)n;
+            chirp[k] = std::complex<double>(std::cos(ang), std::sin(ang));
+        }
+        std::vector<std::complex<double>> b(m, std::complex<double>(0, 0));
+        b[0] = std::conj(chirp[0]);
+        for (int64_t k = 1; k < n; ++k) b[k] = b[m - k] = std::conj(chirp[k]);
+        host_fft(b);
+        std::vector<float2> w(n), bhat(m);
+        for (int64_t k = 0; k < n; ++k) w[k] = make_float2((float)chirp[k].real(), (float)chirp[k].imag());
+        for (int64_t i = 0; i < m; ++i) {
+            const std::complex<double> v = b[bitrev((unsigned)i, p.log2m)] / (double)m;
+            bhat[i] = make_float2((float)v.real(), (float)v.imag());
+        }
+        if (int e = upload(&p.d_w, w)) return e;
+        if (int e = upload(&p.d_bhat, bhat)) return e;
+    }
+    return HD_OK;
+}
+
+// ---- device: complex helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b)   // a * conj(b)
+{
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+
+// DIF, natural order in -> bit-reversed order out, kernel exp(-2 pi i / m)
+__device__ __forceinline__ void fft_dif(float2* s, int m, const float2* __restrict__ tw)
+{
+    int tstep = 1;
+    for (int half = m >> 1; half >= 1; half >>= 1, tstep <<= 1) {
+        for (int t = threadIdx.x; t < (m >> 1); t += FNT) {
+            const int j = t & (half - 1);
+            const int i = ((t - j) << 1) + j;
+            const float2 a = s[i], b = s[i + half];
+            const float2 w = __ldg(&tw[j * tstep]);
+            s[i] = make_float2(a.x + b.x, a.y + b.y);
+            s[i + half] = cmul(make_float2(a.x - b.x, a.y - b.y), w);
+        }
+        __syncthreads();
+    }
+}
+// DIT, bit-reversed order in -> natural order out; conj_tw = true gives the exp(+2 pi i / m) kernel
+__device__ __forceinline__ void fft_dit(float2* s, int m, const float2* __restrict__ tw, bool conj_tw)
+{
+    int tstep = m >> 1;
+    for (int half = 1; half < m; half <<= 1, tstep >>= 1) {
+        for (int t = threadIdx.x; t < (m >> 1); t += FNT) {
+            const int j = t & (half - 1);
+            const int i = ((t - j) << 1) + j;
+            const float2 w = __ldg(&tw[j * tstep]);
+            const float2 a = s[i];
+            const float2 b = conj_tw ? cmul_conj(s[i + half], w) : cmul(s[i + half], w);
+            s[i] = make_float2(a.x + b.x, a.y + b.y);
+            s[i + half] = make_float2(a.x - b.x, a.y - b.y);
+        }
+        __syncthreads();
+    }
+}
+
+enum LoadMode { LOAD_REAL = 0, LOAD_C64 = 1, LOAD_MASKED_SHIFTED = 2 };
+
+struct RowsArgs {
+    const void* in;          // f32 (LOAD_REAL) or float2 rows
+    int64_t in_pitch;        // elements
+    float2* out;             // complex rows (may alias in for LOAD_C64) -- or float* when store_abs
+    int64_t out_pitch;
+    const uint8_t* mask;     // LOAD_MASKED_SHIFTED: 1 = blanked frequency, shifted layout
+    int64_t mask_pitch;
+    int nrows;
+    int shift_rows, shift_cols;   // LOAD_MASKED_SHIFTED: source = ((row + shift_rows) % nrows, (col + shift_cols) % n)
+    int inverse;             // conj in, conj out, scale 1/n
+    int store_abs;           // write |z| as float instead of z
+};
+
+template <int LOAD, bool BLUE>
+__global__ void __launch_bounds__(FNT) fft_rows_kernel(RowsArgs a, int n, int m, int log2m, const float2* __restrict__ tw,
+                                                       const float2* __restrict__ chirp, const float2* __restrict__ bhat)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    const float scale = a.inverse ? 1.0f / (float)n : 1.0f;
+    for (int row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+        // ---- load (+ conj for the inverse, + chirp for Bluestein) ---------------------------------------
+        for (int k = threadIdx.x; k < m; k += FNT) {
+            float2 v = make_float2(0.f, 0.f);
+            if (k < n) {
+                if (LOAD == LOAD_REAL) {
+                    v.x = reinterpret_cast<const float*>(a.in)[(int64_t)row * a.in_pitch + k];
+                } else if (LOAD == LOAD_C64) {
+                    v = reinterpret_cast<const float2*>(a.in)[(int64_t)row * a.in_pitch + k];
+                } else {
+                    int sr = row + a.shift_rows; if (sr >= a.nrows) sr -= a.nrows;
+                    int sc = k + a.shift_cols;   if (sc >= n) sc -= n;
+                    v = reinterpret_cast<const float2*>(a.in)[(int64_t)sr * a.in_pitch + sc];
+                    const float keep = 1.0f - (float)a.mask[(int64_t)sr * a.mask_pitch + sc];   // SubtractionFilter(minuend=1)
+                    v.x *= keep; v.y *= keep;                                                     // ProductFilter(factor=F_shift)
+                }
+                if (a.inverse) v.y = -v.y;
+                if (BLUE) v = cmul(v, __ldg(&chirp[k]));
+            }
+            if (BLUE) s[k] = v;
+            else s[log2m ? (__brev((unsigned)k) >> (32 - log2m)) : 0u] = v;   // DIT wants bit-reversed input
+        }
+        __syncthreads();
+        if (BLUE) {
+            fft_dif(s, m, tw);
+            for (int k = threadIdx.x; k < m; k += FNT) s[k] = cmul(s[k], __ldg(&bhat[k]));
+            __syncthreads();
+            fft_dit(s, m, tw, true);
+        } else if (m > 1) {
+            fft_dit(s, m, tw, false);
+        }
+        // ---- store -------------------------------------------------------------------------------------------
+        for (int k = threadIdx.x; k < n; k += FNT) {
+            float2 v = s[k];
+            if (BLUE) v = cmul(v, __ldg(&chirp[k]));
+            if (a.inverse) v.y = -v.y;
+            v.x *= scale; v.y *= scale;
+            if (a.store_abs) reinterpret_cast<float*>(a.out)[(int64_t)row * a.out_pitch + k] = hypotf(v.x, v.y);
+            else a.out[(int64_t)row * a.out_pitch + k] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- tiled transposes ---------------------------------------------------------------------------------------------
+// out[(x + sx) % nx_out_rows ...]: generic "transpose + cyclic shift" of a (rows x cols) array into (cols x rows).
+// Element in[r][c] lands at out[(c + shift_c) % cols][(r + shift_r) % rows].
+template <typename T, bool WITH_ABS>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int64_t in_pitch, T* __restrict__ out,
+                                                        int64_t out_pitch, float* __restrict__ out_abs, int64_t abs_pitch,
+                                                        int rows, int cols, int shift_r, int shift_c)
+{
+    __shared__ T tile[32][33];
+    const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    const int ntiles = tiles_c * tiles_r;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + ty + 8 * k, c = c0 + tx;
+            if (r < rows && c < cols) tile[ty + 8 * k][tx] = in[(int64_t)r * in_pitch + c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + ty + 8 * k, r = r0 + tx;            // out row = c, out col = r
+            if (r < rows && c < cols) {
+                int orow = c + shift_c; if (orow >= cols) orow -= cols;
+                int ocol = r + shift_r; if (ocol >= rows) ocol -= rows;
+                const T v = tile[tx][ty + 8 * k];
+                if (out) out[(int64_t)orow * out_pitch + ocol] = v;
+                if (WITH_ABS) {
+                    const float2 z = *reinterpret_cast<const float2*>(&v);
+                    out_abs[(int64_t)orow * abs_pitch + ocol] = hypotf(z.x, z.y);      // np.abs(complex64) -> float32
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) transpose_real_kernel(const float* __restrict__ in, int64_t in_pitch,
+                                                             OutT* __restrict__ out, int64_t out_pitch, int rows, int cols)
+{
+    __shared__ float tile[32][33];
+    const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    const int ntiles = tiles_c * tiles_r;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + ty + 8 * k, c = c0 + tx;
+            if (r < rows && c < cols) tile[ty + 8 * k][tx] = in[(int64_t)r * in_pitch + c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + ty + 8 * k, r = r0 + tx;
+            if (r < rows && c < cols) out[(int64_t)c * out_pitch + r] = (OutT)tile[tx][ty + 8 * k];
+        }
+        __syncthreads();
+    }
+}
+
+// cyclic shift without transpose (FourierShift / FourierIShift wrappers): out[(r+sr)%rows][(c+sc)%cols] = in[r][c]
+template <typename T>
+__global__ void __launch_bounds__(256) shift_kernel(const T* __restrict__ in, int64_t in_pitch, T* __restrict__ out,
+                                                    int64_t out_pitch, int rows, int cols, int sr, int sc)
+{
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / cols), c = (int)(t - (int64_t)r * cols);
+        int orow = r + sr; if (orow >= rows) orow -= rows;
+        int ocol = c + sc; if (ocol >= cols) ocol -= cols;
+        out[(int64_t)orow * out_pitch + ocol] = in[(int64_t)r * in_pitch + c];
+    }
+}
+
+// ---- host launch helpers -----------------------------------------------------------------------------------------
+int launch_rows(const Plan1D& p, const RowsArgs& a, int load, cudaStream_t s)
+{
+    const size_t smem = (size_t)p.m * sizeof(float2);
+    const int per_sm = smem > 0 ? (int)(200 * 1024 / (smem + 1024)) : 1;
+    int grid = hd_num_sms() * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+    if (grid > a.nrows) grid = a.nrows;
+    if (grid < 1) return HD_OK;
+#define HD_ROWS(LOADV, BLUEV)                                                                                     \
+    {                                                                                                             \
+        auto kern = fft_rows_kernel<LOADV, BLUEV>;                                                                \
+        HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        kern<<<grid, FNT, smem, s>>>(a, p.n, p.m, p.log2m, p.d_tw, p.d_w, p.d_bhat);                               \
+    }
+    if (p.bluestein) {
+        if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, true)
+        else if (load == LOAD_C64) HD_ROWS(LOAD_C64, true)
+        else HD_ROWS(LOAD_MASKED_SHIFTED, true)
+    } else {
+        if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, false)
+        else if (load == LOAD_C64) HD_ROWS(LOAD_C64, false)
+        else HD_ROWS(LOAD_MASKED_SHIFTED, false)
+    }
+#undef HD_ROWS
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+int transpose_grid(int rows, int cols)
+{
+    const int64_t nt = (int64_t)((rows + 31) / 32) * ((cols + 31) / 32);
+    const int64_t cap = (int64_t)hd_num_sms() * 8;
+    return (int)(nt < cap ? nt : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hd_fft2_plan_create(int64_t ny, int64_t nx, void** plan)
+{
+    if (!plan) return HD_ERR_NULL;
+    *plan = nullptr;
+    if (ny < 1 || nx < 1) return HD_ERR_ARG;
+    Plan2D* p = new Plan2D();
+    p->ny = ny; p->nx = nx;
+    int e = build1d(p->px, nx);
+    if (!e) e = build1d(p->py, ny);
+    if (e) { destroy1d(p->px); destroy1d(p->py); delete p; return e; }
+    *plan = p;
+    return HD_OK;
+}
+
+int hd_fft2_plan_destroy(void* plan)
+{
+    if (!plan) return HD_OK;
+    Plan2D* p = (Plan2D*)plan;
+    destroy1d(p->px); destroy1d(p->py);
+    delete p;
+    return HD_OK;
+}
+
+// two complex64 scratch arrays of ny * nx
+int64_t hd_fft2_workspace_bytes(int64_t ny, int64_t nx) { return 2 * ny * nx * (int64_t)sizeof(float2); }
+
+int hd_fft2_forward_shift_abs(void* plan, const void* in, int64_t in_pitch, void* fshift, int64_t fshift_pitch, void* fabs_out,
+                              int64_t fabs_pitch, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    if (!plan || !in || !fabs_out || !workspace) return HD_ERR_NULL;
+    Plan2D* p = (Plan2D*)plan;
+    const int ny = (int)p->ny, nx = (int)p->nx;
+    if (workspace_bytes < hd_fft2_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
+    if (in_pitch < nx || fabs_pitch < nx || (fshift && fshift_pitch < nx)) return HD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    float2* A = (float2*)workspace;                 // [ny][nx]
+    float2* At = A + (int64_t)ny * nx;              // [nx][ny]
+    RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, 0, 0};
+    if (int e = launch_rows(p->px, r1, LOAD_REAL, s)) return e;
+    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    RowsArgs r2{At, ny, At, ny, nullptr, 0, nx, 0, 0, 0, 0};
+    if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
+    // At[x][y] = F[y][x]; transpose back with fftshift folded in: F[y][x] -> Fs[(y + ny/2) % ny][(x + nx/2) % nx]
+    transpose_kernel<float2, true><<<transpose_grid(nx, ny), 256, 0, s>>>(At, ny, (float2*)fshift, fshift_pitch,
+                                                                         (float*)fabs_out, fabs_pitch, nx, ny, nx / 2, ny / 2);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+int hd_fft2_masked_inverse_abs(void* plan, const void* fshift, int64_t fshift_pitch, const void* mask, int64_t mask_pitch,
+                               void* out, int out_dtype, int64_t out_pitch, void* workspace, int64_t workspace_bytes,
+                               void* stream)
+{
+    if (!plan || !fshift || !mask || !out || !workspace) return HD_ERR_NULL;
+    Plan2D* p = (Plan2D*)plan;
+    const int ny = (int)p->ny, nx = (int)p->nx;
+    if (workspace_bytes < hd_fft2_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
+    if (fshift_pitch < nx || mask_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    if (out_dtype != HD_F32 && out_dtype != HD_F64) return HD_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    float2* A = (float2*)workspace;
+    float2* At = A + (int64_t)ny * nx;
+    // ifftshift: unshifted index k reads shifted index (k + n/2) % n
+    RowsArgs r1{fshift, fshift_pitch, A, nx, (const uint8_t*)mask, mask_pitch, ny, ny / 2, nx / 2, 1, 0};
+    if (int e = launch_rows(p->px, r1, LOAD_MASKED_SHIFTED, s)) return e;
+    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    float* absT = (float*)A;                        // [nx][ny] float, reuses A
+    RowsArgs r2{At, ny, (float2*)absT, ny, nullptr, 0, nx, 0, 0, 1, 1};
+    if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
+    if (out_dtype == HD_F32)
+        transpose_real_kernel<float><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (float*)out, out_pitch, nx, ny);
+    else
+        transpose_real_kernel<double><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (double*)out, out_pitch, nx, ny);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+int hd_fft2_c2c(void* plan, const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int inverse,
+                void* workspace, int64_t workspace_bytes, void* stream)
+{
+    if (!plan || !in || !out || !workspace) return HD_ERR_NULL;
+    Plan2D* p = (Plan2D*)plan;
+    const int ny = (int)p->ny, nx = (int)p->nx;
+    if (workspace_bytes < hd_fft2_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
+    if (in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    if (in_dtype != HD_F32 && in_dtype != HD_C64) return HD_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    float2* A = (float2*)workspace;
+    float2* At = A + (int64_t)ny * nx;
+    RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, inverse ? 1 : 0, 0};
+    if (int e = launch_rows(p->px, r1, in_dtype == HD_F32 ? LOAD_REAL : LOAD_C64, s)) return e;
+    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    RowsArgs r2{At, ny, At, ny, nullptr, 0, nx, 0, 0, inverse ? 1 : 0, 0};
+    if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
+    transpose_kernel<float2, false><<<transpose_grid(nx, ny), 256, 0, s>>>(At, ny, (float2*)out, out_pitch, nullptr, 0, nx, ny,
+                                                                          0, 0);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+int hd_fftshift2(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
+                 int inverse, void* stream)
+{
+    if (!in || !out) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || ny > 0x7fffffff || nx > 0x7fffffff || in_pitch < nx || out_pitch < nx || in == out) return HD_ERR_ARG;
+    // fftshift moves index k to (k + n/2) % n; ifftshift to (k + n - n/2) % n = (k + (n+1)/2) % n
+    const int sr = (int)(inverse ? (ny + 1) / 2 : ny / 2) % (int)ny, sc = (int)(inverse ? (nx + 1) / 2 : nx / 2) % (int)nx;
+    const int64_t total = ny * nx;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (hd_dtype_size(dtype)) {
+        case 4: shift_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, in_pitch, (float*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
+        case 8: shift_kernel<double><<<blocks, 256, 0, s>>>((const double*)in, in_pitch, (double*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
+        case 16: shift_kernel<double2><<<blocks, 256, 0, s>>>((const double2*)in, in_pitch, (double2*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
+        default: return HD_ERR_UNSUPPORTED;
+    }
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// QuadraticFilter.apply (filters/custom_filters.py:226-257) and the fused GrovesCorrection tail (:704-732).
+//
+// The reference evaluates, per window (cast to float32),
+//     s1 = sum w,  s2 = sum w x^2,  s3 = sum w y^2,
+//     smoothed = ((s2 + s3) r1 - s1 (r2 + r3)) / (2 r1^2 - r0 (r2 + r3))
+// with x, y = linspace(-ws/2 + 1, ws/2, ws) (half-pixel asymmetric offsets).  All three sums are separable:
+//     column pass : V1[y][x] = sum_dy w,  Vyy[y][x] = sum_dy y^2 w        (one pass down each tile column)
+//     row pass    : s1 = sum_dx V1,  s3 = sum_dx Vyy,  s2 = sum_dx x^2 V1
+// i.e. 2*ws taps instead of ws^2 per sum.  Accumulation is in double (the reference's s2, s3 are float64 and
+// the final expression cancels two ~1e9 terms), so agreement with the reference is ~1e-7 relative -- inside
+// the 1e-5 tolerance class of this stage.
+//
+// Groves tail (one GrovesCorrection iteration, fused -- the six elementwise filters never touch HBM):
+//     hi = dem - smooth;  tall = hi > 1.5;  keep = 1 - groves * tall;  out = keep * hi + smooth
+//
+// Algorithmic HBM traffic: 4 B read + 4 B written per cell (+1 B groves mask) for float32 rasters.
+#include "common.cuh"
+#include "tile_common.cuh"
+
+namespace {
+
+constexpr int STRIP = 8;
+constexpr int MAX_WS = 15;
+
+struct QuadParams {
+    double c2[MAX_WS];   // squared coordinate per tap
+    double r1, r23, den; // r1, r2 + r3, 2 r1^2 - r0 (r2 + r3)
+    double thr;          // tall-groves threshold (1.5)
+};
+
+template <int H, typename T, typename OutT, bool GROVES>
+__global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ CUtensorMap tm_in, OutT* __restrict__ out,
+                                                       int64_t out_pitch, const uint8_t* __restrict__ groves,
+                                                       int64_t groves_pitch, int64_t ny, int64_t nx, QuadParams p,
+                                                       int tiles_x, int ntiles)
+{
+    constexpr int WS = 2 * H + 1;
+    constexpr int CW = TW + 2 * H;
+    constexpr int HX = hd_halo_x(H, sizeof(T));
+    constexpr int XOFF = HX - H;
+    constexpr int IN_W = TW + 2 * HX;
+    constexpr int IN_H = TH + 2 * H;
+    constexpr uint32_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    double* v1 = reinterpret_cast<double*>(smem + 2 * STAGE);   // [TH][CW]  sum_dy w
+    double* vyy = v1 + TH * CW;                                  // [TH][CW]  sum_dy y^2 w
+
+    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * sizeof(T)), HX, H}};
+    tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        const T* tile = reinterpret_cast<const T*>(st);
+        // ---- column pass ----------------------------------------------------------------------------
+        for (int item = threadIdx.x; item < CW * (TH / STRIP); item += NT) {
+            const int c = item % CW, s = item / CW;
+            double v[STRIP + 2 * H];
+#pragma unroll
+            for (int r = 0; r < STRIP + 2 * H; ++r)
+                v[r] = (double)(float)tile[(s * STRIP + r) * IN_W + c + XOFF];      // window cast to float32
+#pragma unroll
+            for (int o = 0; o < STRIP; ++o) {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int r = 0; r < WS; ++r) {
+                    a += v[o + r];
+                    b = fma(p.c2[r], v[o + r], b);
+                }
+                v1[(s * STRIP + o) * CW + c] = a;
+                vyy[(s * STRIP + o) * CW + c] = b;
+            }
+        }
+        __syncthreads();
+        // ---- row pass: 4 consecutive outputs per thread -------------------------------------------------
+#pragma unroll 1
+        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+            const int idx = rep * NT + threadIdx.x;
+            const int ro = idx >> 5, c4 = idx & 31;
+            const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+            if (y >= ny || x >= nx) continue;
+            double a[WS + 3], b[WS + 3];
+            const double2* pa = reinterpret_cast<const double2*>(v1 + ro * CW + 4 * c4);
+            const double2* pb = reinterpret_cast<const double2*>(vyy + ro * CW + 4 * c4);
+#pragma unroll
+            for (int k = 0; k < (WS + 3) / 2; ++k) {
+                const double2 qa = pa[k], qb = pb[k];
+                a[2 * k] = qa.x; a[2 * k + 1] = qa.y;
+                b[2 * k] = qb.x; b[2 * k + 1] = qb.y;
+            }
+            OutT res[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const T ctr = tile[(ro + H) * IN_W + 4 * c4 + j + HX];
+                const bool interior = y >= H && y < ny - H && x + j >= H && x + j < nx - H;
+                T smooth = ctr;                                    // smoothed = dem.copy()  (:249)
+                if (interior) {
+                    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                    for (int d = 0; d < WS; ++d) {
+                        s1 += a[j + d];
+                        s2 = fma(p.c2[d], a[j + d], s2);
+                        s3 += b[j + d];
+                    }
+                    smooth = (T)(((s2 + s3) * p.r1 - s1 * p.r23) / p.den);   // (:255-256), stored in dem's dtype
+                }
+                if (GROVES) {
+                    const double g = (x + j < nx) ? (double)groves[y * groves_pitch + x + j] : 0.0;
+                    const T hi = ctr - smooth;                                        // SubtractionFilter (:725)
+                    const double tall = (hi > (T)p.thr) ? 1.0 : 0.0;                  // MaskTallGroves
+                    const double keep = 1.0 - g * tall;                               // Product, 1 - .
+                    res[j] = (OutT)__dadd_rn(__dmul_rn(keep, (double)hi), (double)smooth);   // x hi, + smooth (:729-731)
+                } else {
+                    res[j] = (OutT)smooth;
+                }
+            }
+            store4v<OutT>(out, out_pitch, y, x, nx, res);
+        }
+    });
+}
+
+template <int H, typename T, typename OutT, bool GROVES>
+int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_pitch, const void* groves,
+           int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t stream)
+{
+    constexpr int CW = TW + 2 * H, IN_W = TW + 2 * hd_halo_x(H, sizeof(T)), IN_H = TH + 2 * H;
+    constexpr size_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128;
+    constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * sizeof(double);
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    auto kern = quadratic_kernel<H, T, OutT, GROVES>;
+    HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    kern<<<grid_for(ntiles, 1), NT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, (const uint8_t*)groves, groves_pitch, ny, nx,
+                                                    p, tiles_x, ntiles);
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+template <typename T, typename OutT, bool GROVES>
+int dispatch_h(int h, const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_pitch, const void* groves,
+               int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t s)
+{
+    switch (h) {
+#define HD_Q_CASE(HH) \
+    case HH: return launch<HH, T, OutT, GROVES>(in, dtype, in_pitch, out, out_pitch, groves, groves_pitch, ny, nx, p, s);
+        HD_Q_CASE(1) HD_Q_CASE(2) HD_Q_CASE(3) HD_Q_CASE(4) HD_Q_CASE(5) HD_Q_CASE(6) HD_Q_CASE(7)
+#undef HD_Q_CASE
+        default: return HD_ERR_UNSUPPORTED;
+    }
+}
+
+// r0..r3 of custom_filters.py:240-246, evaluated like numpy: linspace(-ws/2 + 1, ws/2, ws)
+QuadParams make_params(int ws, double thr)
+{
+    QuadParams p{};
+    const double start = -ws / 2.0 + 1.0, stop = ws / 2.0;
+    const double step = (stop - start) / (ws - 1);
+    double vals[MAX_WS];
+    for (int k = 0; k < ws; ++k) vals[k] = (k == ws - 1) ? stop : start + k * step;
+    double r1 = 0, r2 = 0, r3 = 0;
+    for (int yy = 0; yy < ws; ++yy)
+        for (int xx = 0; xx < ws; ++xx) {
+            const double x2 = vals[xx] * vals[xx], y2 = vals[yy] * vals[yy];
+            r1 += x2;
+            r2 += x2 * x2;
+            r3 += x2 * y2;
+        }
+    for (int k = 0; k < ws; ++k) p.c2[k] = vals[k] * vals[k];
+    const double r0 = (double)ws * ws;
+    p.r1 = r1;
+    p.r23 = r2 + r3;
+    p.den = 2 * r1 * r1 - r0 * (r2 + r3);
+    p.thr = thr;
+    return p;
+}
+
+int run(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int in_dtype, int out_dtype, const void* groves,
+        int64_t groves_pitch, int64_t ny, int64_t nx, int ws, double thr, void* stream)
+{
+    if (!in || !out) return HD_ERR_NULL;
+    if (int e = check_window(ny, nx, ws)) return e;
+    if (ws < 3 || ws > MAX_WS) return HD_ERR_UNSUPPORTED;
+    if (in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    const QuadParams p = make_params(ws, thr);
+    const int h = ws / 2;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool g = groves != nullptr;
+#define HD_Q_T(TT, TTAG, OT, OTAG)                                                                                      \
+    if (in_dtype == TTAG && out_dtype == OTAG)                                                                          \
+        return g ? dispatch_h<TT, OT, true>(h, in, in_dtype, in_pitch, out, out_pitch, groves, groves_pitch, ny, nx, p, s) \
+                 : dispatch_h<TT, OT, false>(h, in, in_dtype, in_pitch, out, out_pitch, groves, groves_pitch, ny, nx, p, s);
+    HD_Q_T(float, HD_F32, float, HD_F32)
+    HD_Q_T(float, HD_F32, double, HD_F64)
+    HD_Q_T(double, HD_F64, double, HD_F64)
+#undef HD_Q_T
+    return HD_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+extern "C" int hd_quadratic(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny,
+                            int64_t nx, int ws, void* stream)
+{
+    return run(in, in_pitch, out, out_pitch, dtype, dtype, nullptr, 0, ny, nx, ws, 0.0, stream);
+}
+
+extern "C" int hd_groves_correction(const void* in, int in_dtype, int64_t in_pitch, const void* groves,
+                                    int64_t groves_pitch, void* out, int out_dtype, int64_t out_pitch, int64_t ny,
+                                    int64_t nx, int ws, double threshold, void* stream)
+{
+    if (!groves) return HD_ERR_NULL;
+    if (groves_pitch < nx) return HD_ERR_ARG;
+    return run(in, in_pitch, out, out_pitch, in_dtype, out_dtype, groves, groves_pitch, ny, nx, ws, threshold, stream);
+}

@@ -176,3 +176,23 @@ def download(raster, out=None):
         np.copyto(out, host, casting="unsafe")
         return out
     return host
+
+
+# ---- FFT plans and scratch --------------------------------------------------------------------------
+_FFT_PLANS = {}
+
+
+def fft_plan(ny, nx):
+    """Cached hd_fft2 plan (twiddle / chirp tables in device memory) for one raster shape."""
+    key = (torch.cuda.current_device(), int(ny), int(nx))
+    plan = _FFT_PLANS.get(key)
+    if plan is None:
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.load().hd_fft2_plan_create(ny, nx, ctypes.byref(handle)))
+        plan = _FFT_PLANS[key] = handle
+    return plan
+
+
+def scratch(nbytes):
+    """Uninitialised device scratch of at least ``nbytes`` (256-byte aligned by the caching allocator)."""
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device())

@@ -124,6 +124,105 @@ class IsolatedPoints(_InPlace3):
         self.window_size = window_size
 
 
+class QuadraticFilter(WindowFilter):
+    """Least-squares quadratic smoothing over a square window -- the "isotropic" filter
+    (custom_filters.py:202-257).  Result in the input's dtype, ws//2 border unchanged."""
+
+    def __init__(self, *, window_size):
+        self.window_size = window_size
+
+    def run_device(self, raster):
+        check_window(raster.shape, self.window_size)
+        ref = np.dtype(raster.ref_dtype)
+        if raster.dtype == _lib.F32 and ref in (np.float32, np.float64):
+            src = raster                                     # float32 storage (exact for the float32-cast windows)
+        else:
+            src = dev.convert(raster, _lib.F64)
+        out = dev.empty(raster.ny, raster.nx, src.dtype, ref)
+        _lib.check(_lib.load().hd_quadratic(src.ptr, src.pitch, out.ptr, out.pitch, src.dtype, src.ny, src.nx,
+                                            int(self.window_size), dev.stream_ptr()),
+                   window_size=self.window_size, shape=raster.shape)
+        return out
+
+
+class GrovesCorrection(DeviceFilter):
+    """One groves-correction pass (custom_filters.py:664-732): QuadraticFilter(15) -> dem - smooth ->
+    > 1.5 -> x groves_class -> 1 - . -> x (dem - smooth) -> + smooth, fused into ONE kernel.
+    Returns float64 like the reference.  ``partial_results`` is not materialised."""
+
+    window_size = 15
+    threshold = 1.5
+
+    def __init__(self, groves_class):
+        self.partial_results = []
+        self.groves_class = groves_class
+        self._groves_dev = None
+
+    def _groves(self, shape):
+        if self._groves_dev is None:
+            g = self.groves_class
+            if isinstance(g, dev.DeviceRaster):
+                self._groves_dev = dev.convert(g, _lib.U8)
+            else:
+                g = np.asarray(g)
+                if g.dtype != np.bool_ and not np.isin(g, (0, 1)).all():
+                    raise dev.DeviceError("GrovesCorrection: groves_class must be a 0/1 mask on the device path")
+                self._groves_dev = dev.upload(np.ascontiguousarray(g != 0))
+        if self._groves_dev.shape != tuple(shape):
+            raise ValueError(f"groves_class shape {self._groves_dev.shape} does not match the DEM {tuple(shape)}")
+        return self._groves_dev
+
+    def run_device(self, raster, out_dtype=None):
+        check_window(raster.shape, self.window_size)
+        src = raster if raster.dtype in (_lib.F32, _lib.F64) else dev.convert(raster, _lib.F64)
+        if out_dtype is None:
+            out_dtype = _lib.F64
+        groves = self._groves(raster.shape)
+        out = dev.empty(raster.ny, raster.nx, out_dtype, np.float64)
+        _lib.check(_lib.load().hd_groves_correction(src.ptr, src.dtype, src.pitch, groves.ptr, groves.pitch, out.ptr,
+                                                    out.dtype, out.pitch, src.ny, src.nx, self.window_size,
+                                                    self.threshold, dev.stream_ptr()),
+                   window_size=self.window_size, shape=raster.shape)
+        return out
+
+    def apply(self, image_to_filter):
+        if not isinstance(image_to_filter, np.ndarray):
+            raise NumpyArrayExpectedError(image_to_filter)
+        check_window(image_to_filter.shape, self.window_size)
+        return dev.download(self.run_device(dev.upload(image_to_filter)))
+
+
+class GrovesCorrectionsIter(ComposedFilter):
+    """``iterations`` GrovesCorrection passes (custom_filters.py:735-767)."""
+
+    def __init__(self, groves_class, iterations=3):
+        super().__init__()
+        shared = groves_class
+        if not isinstance(groves_class, dev.DeviceRaster) and isinstance(groves_class, np.ndarray):
+            first = GrovesCorrection(groves_class)
+            self.filters = [first]
+            for _ in range(iterations - 1):
+                nxt = GrovesCorrection(groves_class)
+                nxt._share = first                      # upload the mask once
+                self.filters.append(nxt)
+        else:
+            self.filters = [GrovesCorrection(shared) for _ in range(iterations)]
+
+    def run_device(self, raster):
+        content = raster
+        first = self.filters[0] if self.filters else None
+        for f in self.filters:
+            if isinstance(f, GrovesCorrection) and f is not first and getattr(f, "_share", None) is first:
+                f._groves_dev = first._groves(content.shape)
+            content = run_stage(f, content)
+        return content
+
+    def apply(self, image_to_filter):
+        Filter.apply(self, image_to_filter)
+        check_window(image_to_filter.shape, 15)
+        return dev.download(self.run_device(dev.upload(image_to_filter)))
+
+
 class MaskNegatives(ComposedFilter):
     """(image < 0) * 1 (custom_filters.py:465-486)."""
 
@@ -202,6 +301,199 @@ class PostProcessingFinal(ComposedFilter):
         if type(conv) is Convolve and type(rnd) is Around:
             return conv.run_device(raster, do_round=True)
         return super().run_device(raster)
+
+    def apply(self, image_to_filter):
+        Filter.apply(self, image_to_filter)
+        return dev.download(self.run_device(dev.upload(image_to_filter)))
+
+
+# ---- Fourier stripe removal --------------------------------------------------------------------------------
+from .extension_filters import FourierIShift, FourierITransform, FourierShift, FourierTransform  # noqa: E402,F401
+import ctypes  # noqa: E402
+
+FOURIER_MARGIN = 10            # FourierProcessQuarters._margin (custom_filters.py:911)
+BLANKS_WINDOW = 55             # DetectBlanksFourier (custom_filters.py:457)
+BLANKS_INNER = 5               # BlanksFourier (custom_filters.py:419)
+BLANKS_FACTOR = 4.0            # centre > 4 * mean (custom_filters.py:424)
+
+
+def _hollow_pass(src_f32, prev_mask, window_size):
+    """One BlanksFourier pass on the device -> (accumulated mask U8, modified image F32)."""
+    mask = dev.empty(src_f32.ny, src_f32.nx, _lib.U8, np.float64)
+    mod = dev.empty(src_f32.ny, src_f32.nx, _lib.F32, np.float64)
+    pp, ppitch = (prev_mask.ptr, prev_mask.pitch) if prev_mask is not None else (None, 0)
+    _lib.check(_lib.load().hd_hollow_mean_detect(src_f32.ptr, src_f32.pitch, pp, ppitch, mask.ptr, mask.pitch, mod.ptr,
+                                                 mod.pitch, src_f32.ny, src_f32.nx, int(window_size), BLANKS_INNER,
+                                                 BLANKS_FACTOR, dev.stream_ptr()),
+               window_size=window_size, shape=src_f32.shape)
+    return mask, mod
+
+
+class BlanksFourier(Filter):
+    """Peak detector on a spectrum quarter (custom_filters.py:369-427): returns the TUPLE
+    (mask float64, image * (1 - mask))."""
+
+    def __init__(self, *, window_size):
+        self.window_size = window_size
+
+    def run_device(self, raster):
+        check_window(raster.shape, self.window_size)
+        return _hollow_pass(as_f32(raster), None, self.window_size)
+
+    def apply(self, image_to_filter):
+        if not isinstance(image_to_filter, np.ndarray):
+            raise NumpyArrayExpectedError(image_to_filter)
+        check_window(image_to_filter.shape, self.window_size)
+        mask, mod = self.run_device(dev.upload(image_to_filter))
+        return dev.download(mask), dev.download(mod)
+
+
+class DetectBlanksFourier(WindowFilter):
+    """Two BlanksFourier(55) passes, masks added (custom_filters.py:430-462)."""
+
+    window_size = BLANKS_WINDOW
+
+    def run_device(self, raster):
+        check_window(raster.shape, BLANKS_WINDOW)
+        src = as_f32(raster)
+        mask, mod = _hollow_pass(src, None, BLANKS_WINDOW)
+        mask, _ = _hollow_pass(mod, mask, BLANKS_WINDOW)
+        return mask
+
+
+class MaskFourier(ComposedFilter):
+    """DetectBlanksFourier -> IsolatedPoints(3) -> ExpandFilter(13) (custom_filters.py:537-561)."""
+
+    def __init__(self):
+        super().__init__()
+        self.filters = [DetectBlanksFourier(), IsolatedPoints(window_size=3), ExpandFilter(window_size=13)]
+
+    def run_device(self, raster):
+        mask = self.filters[0].run_device(raster)
+        mask = self.filters[1].run_device(dev.convert(mask, _lib.F32))
+        return self.filters[2].run_device(mask)
+
+    def apply(self, image_to_filter):
+        Filter.apply(self, image_to_filter)
+        check_window(image_to_filter.shape, BLANKS_WINDOW)
+        return dev.download(self.run_device(dev.upload(image_to_filter)))
+
+
+class FourierInitial(ComposedFilterResults):
+    """fft2 -> fftshift -> abs, keeping the shifted spectrum (custom_filters.py:834-877).
+    One fused launch group: the shift and |.| are folded into the transform's last pass."""
+
+    def __init__(self):
+        super().__init__()
+        self.filters = [FourierTransform(), FourierShift(), AbsoluteValues()]
+        self._fshift_dev = None
+
+    @property
+    def fourier_shift(self):
+        return self.results["FourierShift"] if "FourierShift" in self.results else None
+
+    @fourier_shift.setter
+    def fourier_shift(self, value):
+        self.results["FourierShift"] = value
+
+    def run_device(self, raster):
+        lib = _lib.load()
+        ref = np.dtype(raster.ref_dtype)
+        src = as_f32(raster)
+        cref = np.complex64 if ref == np.float32 else np.complex128
+        fshift = dev.empty(raster.ny, raster.nx, _lib.C64, cref)
+        fabs = dev.empty(raster.ny, raster.nx, _lib.F32, np.float32 if ref == np.float32 else np.float64)
+        plan = dev.fft_plan(raster.ny, raster.nx)
+        nbytes = lib.hd_fft2_workspace_bytes(raster.ny, raster.nx)
+        work = dev.scratch(nbytes)
+        _lib.check(lib.hd_fft2_forward_shift_abs(plan, src.ptr, src.pitch, fshift.ptr, fshift.pitch, fabs.ptr, fabs.pitch,
+                                                 ctypes.c_void_p(work.data_ptr()), nbytes, dev.stream_ptr()))
+        self._fshift_dev = fshift
+        self.results["FourierShift"] = fshift
+        self.results["AbsoluteValues"] = fabs
+        return fabs
+
+    def apply(self, image_to_filter):
+        Filter.apply(self, image_to_filter)
+        return dev.download(self.run_device(dev.upload(image_to_filter)))
+
+
+class FourierProcessQuarters(Filter):
+    """Quarter extraction, MaskFourier per quarter and point-symmetric mask assembly
+    (custom_filters.py:880-1050).  ``apply`` ignores its argument like the reference."""
+
+    def __init__(self, fft_transform_abs):
+        self.fft_transform_abs = fft_transform_abs
+        shape = fft_transform_abs.shape
+        self._ny, self._nx = shape
+        self._mid_y, self._y_odd = divmod(self._ny, 2)
+        self._mid_x, self._x_odd = divmod(self._nx, 2)
+        self.pair_mid = self._mid_y, self._mid_x
+        self._margin = FOURIER_MARGIN
+
+    def run_device(self, fabs=None, invert=False, out_dtype=None):
+        fabs = fabs if fabs is not None else self.fft_transform_abs
+        if isinstance(fabs, np.ndarray):
+            fabs = dev.upload(fabs)
+        fabs = as_f32(fabs)
+        m = self._margin
+        qh, qw = self._mid_y - m, self._mid_x - m
+        if qh < 1 or qw < 1:
+            raise WindowSizeHighError(BLANKS_WINDOW, (qh, qw))
+        check_window((qh, qw), BLANKS_WINDOW)
+        q1 = fabs.sub(0, qh, 0, qw)                                          # [:my-m, :mx-m]          (:942-943)
+        x0 = self._mid_x + m + self._x_odd
+        q2 = dev.empty(qh, qw, _lib.F32)                                     # [:my-m, mx+m+x_odd:nx]  (:945-947)
+        dev.elementwise(_lib.OP_COPY, fabs.sub(0, qh, x0, self._nx), None, 0.0, q2)
+        mf = MaskFourier()
+        m1 = mf.run_device(q1)
+        m2 = mf.run_device(q2)
+        out_dtype = _lib.U8 if out_dtype is None else out_dtype
+        out = dev.empty(self._ny, self._nx, out_dtype, np.float64)
+        _lib.check(_lib.load().hd_fourier_mask_assemble(m1.ptr, m1.pitch, m2.ptr, m2.pitch, out.ptr, out.dtype, out.pitch,
+                                                        self._ny, self._nx, m, int(invert), dev.stream_ptr()))
+        return out
+
+    def apply(self, image_to_filter=None):
+        return dev.download(self.run_device())
+
+
+class DetectApplyFourier(ComposedFilter):
+    """The whole stripe-removal stage (custom_filters.py:1053-1101): FourierInitial ->
+    FourierProcessQuarters -> (1 - mask) * F_shift -> ifftshift -> ifft2 -> abs.  float64 result."""
+
+    def __init__(self):
+        super().__init__()
+        self.initial = FourierInitial()
+        self._fabs_dev = None
+        self._mask_dev = None
+
+    @property
+    def fft_transform_abs(self):
+        return dev.download(self._fabs_dev) if self._fabs_dev is not None else None
+
+    @property
+    def mask(self):
+        """The assembled blanking mask (float64 0/1), for inspection and the parity tests."""
+        return dev.download(self._mask_dev) if self._mask_dev is not None else None
+
+    def run_device(self, raster, out_dtype=None):
+        lib = _lib.load()
+        fabs = self.initial.run_device(raster)
+        fshift = self.initial._fshift_dev
+        self._fabs_dev = fabs
+        quarters = FourierProcessQuarters(fabs)
+        mask = quarters.run_device(fabs)
+        self._mask_dev = mask
+        self.filters = [quarters, SubtractionFilter(minuend=1), ProductFilter(factor=fshift), FourierIShift(),
+                        FourierITransform(), AbsoluteValues()]
+        out = dev.empty(raster.ny, raster.nx, _lib.F32 if out_dtype is None else out_dtype, np.float64)
+        plan = dev.fft_plan(raster.ny, raster.nx)
+        nbytes = lib.hd_fft2_workspace_bytes(raster.ny, raster.nx)
+        work = dev.scratch(nbytes)
+        _lib.check(lib.hd_fft2_masked_inverse_abs(plan, fshift.ptr, fshift.pitch, mask.ptr, mask.pitch, out.ptr, out.dtype,
+                                                  out.pitch, ctypes.c_void_p(work.data_ptr()), nbytes, dev.stream_ptr()))
+        return out
 
     def apply(self, image_to_filter):
         Filter.apply(self, image_to_filter)

@@ -145,3 +145,65 @@ class GreyDilation(DeviceFilter):
         _lib.check(_lib.load().hd_max_filter(src.ptr, src.pitch, out.ptr, out.pitch, src.dtype, src.ny, src.nx,
                                              int(size[0]), dev.stream_ptr()))
         return out
+
+
+def _complex_ref(ref_dtype):
+    """Result dtype of scipy.fftpack.fft2 / ifft2: single precision stays single, everything else complex128."""
+    return np.dtype(np.complex64) if np.dtype(ref_dtype) in (np.float32, np.complex64) else np.dtype(np.complex128)
+
+
+def _fft2(raster, inverse):
+    ref = np.dtype(raster.ref_dtype)
+    if ref.kind == "c":
+        src = dev.convert(raster, _lib.C64)
+    else:
+        src = dev.convert(raster, _lib.F32)
+    out = dev.empty(raster.ny, raster.nx, _lib.C64, _complex_ref(ref))
+    lib = _lib.load()
+    plan = dev.fft_plan(raster.ny, raster.nx)
+    nbytes = lib.hd_fft2_workspace_bytes(raster.ny, raster.nx)
+    work = dev.scratch(nbytes)
+    _lib.check(lib.hd_fft2_c2c(plan, src.ptr, src.dtype, src.pitch, out.ptr, out.pitch, int(inverse),
+                               ctypes.c_void_p(work.data_ptr()), nbytes, dev.stream_ptr()))
+    return out
+
+
+class FourierTransform(DeviceFilter):
+    """``scipy.fftpack.fft2(image)`` (extension_filters.py:348-379).  Computed in complex64 on the
+    device (float32 input gives complex64 exactly like scipy; wider inputs are returned as
+    complex128 but carry single-precision accuracy -- tolerance class)."""
+
+    def run_device(self, raster):
+        return _fft2(raster, inverse=False)
+
+
+class FourierITransform(DeviceFilter):
+    """``scipy.fftpack.ifft2(image)`` (extension_filters.py:382-414); see FourierTransform."""
+
+    def run_device(self, raster):
+        return _fft2(raster, inverse=True)
+
+
+def _shift(raster, inverse):
+    out = dev.empty(raster.ny, raster.nx, raster.dtype, raster.ref_dtype)
+    src = raster
+    if raster.itemsize not in (4, 8, 16):
+        src = dev.convert(raster, _lib.F32)
+        out = dev.empty(raster.ny, raster.nx, _lib.F32, raster.ref_dtype)
+    _lib.check(_lib.load().hd_fftshift2(src.ptr, src.pitch, out.ptr, out.pitch, src.dtype, src.ny, src.nx, int(inverse),
+                                        dev.stream_ptr()))
+    return out
+
+
+class FourierShift(DeviceFilter):
+    """``scipy.fftpack.fftshift(image)`` (extension_filters.py:417-447)."""
+
+    def run_device(self, raster):
+        return _shift(raster, inverse=False)
+
+
+class FourierIShift(DeviceFilter):
+    """``scipy.fftpack.ifftshift(image)`` (extension_filters.py:450-480)."""
+
+    def run_device(self, raster):
+        return _shift(raster, inverse=True)

@@ -1,0 +1,74 @@
+"""Stages named by the conditioning chain that the reference does not contain
+(SURVEY.md section 0.3): median filter, sink-fill and D8 flow direction.
+
+They follow the reference's filter idiom (keyword-only constructors,
+``apply(ndarray) -> ndarray``).  Their parity oracle is this repository's own
+definition (oracle/stencils.py:median, oracle/hydrology.py) -- "parity
+unpinned" with respect to the reference.
+"""
+import ctypes
+
+import numpy as np
+
+from . import DeviceFilter
+from .. import _lib, device as dev
+from .custom_filters import WindowFilter, as_f32, check_window
+
+
+class MedianFilter(WindowFilter):
+    """np.nanmedian over a ws*ws (or corner-less "circular") window, ws in {3, 5};
+    result in the input's dtype with the ws//2 border unchanged."""
+
+    def __init__(self, *, window_size, circular=False):
+        self.window_size = window_size
+        self.circular = circular
+
+    def run_device(self, raster):
+        check_window(raster.shape, self.window_size)
+        src = as_f32(raster)
+        out = dev.empty(raster.ny, raster.nx, _lib.F32, raster.ref_dtype)
+        _lib.check(_lib.load().hd_median(src.ptr, src.pitch, out.ptr, out.pitch, src.ny, src.nx, int(self.window_size),
+                                         int(bool(self.circular)), dev.stream_ptr()),
+                   window_size=self.window_size, shape=raster.shape)
+        if raster.dtype != _lib.F32:
+            # the border keeps the caller's exact values (dem.copy() convention)
+            wide = dev.convert(out, raster.dtype, raster.ref_dtype)
+            h = int(self.window_size) // 2
+            ny, nx = raster.shape
+            for (y0, y1, x0, x1) in ((0, h, 0, nx), (ny - h, ny, 0, nx), (h, ny - h, 0, h), (h, ny - h, nx - h, nx)):
+                if y1 > y0 and x1 > x0:
+                    dev.elementwise(_lib.OP_COPY, raster.sub(y0, y1, x0, x1), None, 0.0, wide.sub(y0, y1, x0, x1))
+            return wide
+        return out
+
+
+class SinkFill(DeviceFilter):
+    """Depression filling: the Planchon-Darboux fixed point with eps = 0 and
+    8-connectivity; frame cells and NaN cells are outlets.  float32 result.
+    ``sweeps`` holds the number of global tile sweeps of the last call."""
+
+    def __init__(self, *, max_sweeps=0):
+        self.max_sweeps = max_sweeps
+        self.sweeps = None
+
+    def run_device(self, raster):
+        lib = _lib.load()
+        src = as_f32(raster)
+        out = dev.empty(raster.ny, raster.nx, _lib.F32, np.float32)
+        nbytes = lib.hd_pdfill_workspace_bytes(raster.ny, raster.nx)
+        work = dev.scratch(nbytes)
+        sweeps = ctypes.c_int(0)
+        _lib.check(lib.hd_pdfill(src.ptr, src.pitch, out.ptr, out.pitch, src.ny, src.nx, ctypes.c_void_p(work.data_ptr()),
+                                 nbytes, int(self.max_sweeps), ctypes.byref(sweeps), dev.stream_ptr()))
+        self.sweeps = sweeps.value
+        return out
+
+
+class D8FlowDirection(DeviceFilter):
+    """D8 flow direction (ESRI codes, uint8) of a filled surface."""
+
+    def run_device(self, raster):
+        src = as_f32(raster)
+        out = dev.empty(raster.ny, raster.nx, _lib.U8, np.uint8)
+        _lib.check(_lib.load().hd_d8(src.ptr, src.pitch, out.ptr, out.pitch, src.ny, src.nx, dev.stream_ptr()))
+        return out

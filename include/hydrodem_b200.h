@@ -102,6 +102,56 @@ int hd_nanfix(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, in
 int hd_isolated(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
                 void* stream);
 
+/* QuadraticFilter.apply, custom_filters.py:226-257 ("isotropic" least-squares quadratic smoother, ws <= 15).
+ * dtype F32 or F64 (in and out alike): interior cells = ((s2+s3) r1 - s1 (r2+r3)) / (2 r1^2 - r0 (r2+r3)) over the
+ * float32-cast window with the reference's half-pixel offsets; the ws/2 border is copied.  Tolerance class. */
+int hd_quadratic(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx, int ws,
+                 void* stream);
+/* GrovesCorrection.apply, custom_filters.py:704-732, one iteration fused into the quadratic kernel:
+ * smooth = Quadratic(dem); hi = dem - smooth; keep = 1 - groves * (hi > threshold); out = keep * hi + smooth.
+ * in: F32 or F64; groves: U8 (0/1 class mask); out: F64 (the reference's dtype), or F32 for F32 input. */
+int hd_groves_correction(const void* in, int in_dtype, int64_t in_pitch, const void* groves, int64_t groves_pitch, void* out,
+                         int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx, int ws, double threshold, void* stream);
+
+/* NEW stage (not in the reference): median filter.  F32 -> F32; interior cells =
+ * np.nanmedian of the float32 ws*ws window (ws 3 or 5; corner-less if `circular`), ws/2 border copied. */
+int hd_median(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx, int ws, int circular,
+              void* stream);
+
+/* ---- Fourier stripe removal (filters/custom_filters.py:369-462, :834-1101) ------------------------ */
+/* BlanksFourier.apply, custom_filters.py:395-427 (ws = 55, inner = 5 as hard-coded there, :417-419, :457).
+ * in: F32 spectrum quarter.  mask_out (U8) = mask_prev (U8, may be NULL) + (centre > factor * hollow mean);
+ * modified (F32) = in * (1 - hit).  The window is clipped to the raster; the centre 5x5 block is excluded. */
+int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch, void* mask_out,
+                          int64_t mask_pitch, void* modified, int64_t mod_pitch, int64_t ny, int64_t nx, int ws, int inner,
+                          double factor, void* stream);
+/* FourierProcessQuarters._fill_complete_quarters / _getting_reversed_masks / _fill_complete_mask,
+ * custom_filters.py:968-1050.  q1, q2: U8 masks of the two upper quarters, each (ny/2 - margin, nx/2 - margin);
+ * out (U8 / F32 / F64, ny x nx) = assembled point-symmetric mask, or 1 - mask when `invert`. */
+int hd_fourier_mask_assemble(const void* q1, int64_t q1_pitch, const void* q2, int64_t q2_pitch, void* out, int out_dtype,
+                             int64_t out_pitch, int64_t ny, int64_t nx, int margin, int invert, void* stream);
+/* FFT plans hold the twiddle / chirp tables of one (ny, nx) shape in device memory (allocated here). Row
+ * lengths up to 8192 (any factorisation, Bluestein) or 16384 (powers of two); longer -> HD_ERR_UNSUPPORTED. */
+int hd_fft2_plan_create(int64_t ny, int64_t nx, void** plan);
+int hd_fft2_plan_destroy(void* plan);
+int64_t hd_fft2_workspace_bytes(int64_t ny, int64_t nx);
+/* FourierInitial.apply, custom_filters.py:859-877: fft2 (complex64) -> fftshift -> abs.  in: F32 (ny x nx);
+ * fshift: C64 out (may be NULL); fabs_out: F32 |F| in shifted layout. */
+int hd_fft2_forward_shift_abs(void* plan, const void* in, int64_t in_pitch, void* fshift, int64_t fshift_pitch, void* fabs_out,
+                              int64_t fabs_pitch, void* workspace, int64_t workspace_bytes, void* stream);
+/* DetectApplyFourier tail, custom_filters.py:1097-1100: (1 - mask) * F_shift -> ifftshift -> ifft2 -> abs.
+ * fshift: C64; mask: U8 (1 = blanked); out: F32 or F64.  Computed in complex64 (tolerance class). */
+int hd_fft2_masked_inverse_abs(void* plan, const void* fshift, int64_t fshift_pitch, const void* mask, int64_t mask_pitch,
+                               void* out, int out_dtype, int64_t out_pitch, void* workspace, int64_t workspace_bytes,
+                               void* stream);
+/* FourierTransform / FourierITransform.apply, extension_filters.py:363-379, :398-414 (scipy.fftpack.fft2 /
+ * ifft2).  in: F32 or C64; out: C64 (may alias nothing). */
+int hd_fft2_c2c(void* plan, const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int inverse,
+                void* workspace, int64_t workspace_bytes, void* stream);
+/* FourierShift / FourierIShift.apply, extension_filters.py:432-447, :465-480.  Any 4 / 8 / 16-byte dtype. */
+int hd_fftshift2(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
+                 int inverse, void* stream);
+
 /* ---- morphology (filters/extension_filters.py, scipy.ndimage) ------------------------------------ */
 typedef enum { HD_MORPH_ERODE = 0, HD_MORPH_DILATE = 1, HD_MORPH_CLOSE = 2, HD_MORPH_OPEN = 3 } hd_morph_op;
 /* BinaryErosion.apply, extension_filters.py:218-235 (scipy.ndimage.binary_erosion(iterations=n)) and
@@ -121,6 +171,17 @@ int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_t out_pitch
  * dtype: F32 or F64 (in and out alike). */
 int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
                  const double* weights, double divisor, int do_round, void* stream);
+
+/* ---- NEW hydrology stages (not in the reference) ----------------------------------- */
+/* Sink-fill: Planchon-Darboux fixed point with eps = 0, 8-connectivity; frame cells and NaN cells are outlets.
+ * z, w: F32.  Iterates tile sweeps until a sweep changes nothing; SYNCHRONISES the stream every few sweeps to
+ * read the convergence counter.  *sweeps_out = global sweeps executed.  max_sweeps <= 0: unlimited. */
+int64_t hd_pdfill_workspace_bytes(int64_t ny, int64_t nx);
+int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
+              int64_t workspace_bytes, int max_sweeps, int* sweeps_out, void* stream);
+/* D8 flow direction on a (filled) F32 surface -> U8 ESRI codes (E=1, SE=2, S=4, SW=8, W=16, NW=32, N=64, NE=128);
+ * steepest positive drop, diagonals scaled by 0.70710678f, ties -> first in that order, frame / NaN / flat -> 0. */
+int hd_d8(const void* w, int64_t w_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx, void* stream);
 
 #ifdef __cplusplus
 }

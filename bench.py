@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- Mcells/s of the full HydroDEM conditioning chain on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): the full conditioning chain on one synthetic 3601 x 3601 SRTM 1-arcsec
+tile per GPU -- Fourier stripe removal, groves correction x3, lagoon detection, recombination, 3x3 mean + round,
+sink-fill, D8.  A "step" is one pass of the chain over one tile.  At N > 1 every rank conditions its own tile
+(seed 1002 + rank): tiles are independent, there is no data-path collective, scaling is weak.
+
+Numbers on the JSON line
+  value     whole-job Mcells/s with the inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e       the same through the public API with HOST buffers: ConditioningChain.apply(ndarrays) -> host arrays,
+            pinned H2D of the three input rasters and D2H of final DEM / filled DEM / D8 inside the timed region
+  roofline  dominant kernel of the step: algorithmic bytes per launch / average launch time, measured live with a
+            CUDA event pair around every launch (hd_profile_*), against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle port (oracle/chain.py) timed on rank 0, one core, on a bounded sample tile
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+TILE = 3601
+SEED = 1002
+METRIC = "Mcells/s, full conditioning chain"
+UNIT = "Mcells/s"
+
+# Algorithmic HBM bytes per cell and per launch of each kernel in this workload.
+# fft_rows: the four row passes of one forward + one masked inverse 2-D transform are
+#   real->c64 (4+8), c64->c64 (8+8), masked c64->c64 (8+1+8), c64->|.| (8+4)  = 57 B/cell over 4 launches.
+ALGO_BYTES_PER_CELL = {
+    "fft_rows_kernel": 57.0 / 4.0,
+    "transpose_kernel": 16.0,
+    "transpose_real_kernel": 8.0,
+    "quadratic_kernel": 9.0,
+    "majority_kernel": 8.0,
+    "fill_sweep_kernel": 12.0,
+    "hollow_kernel": 9.0 * 0.25,        # runs on a spectrum quarter
+    "expand_kernel": 2.0,
+    "morph_kernel": 2.0,
+    "maxfilter_kernel": 8.0,
+    "fix3_kernel": 8.0,
+    "conv3_kernel": 16.0,
+    "final_terms_kernel": 20.0,
+    "elementwise_kernel": 9.0,
+    "d8_kernel": 5.0,
+}
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback"          # /opt/skills/guides/B200_PROFILING.md
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_chain_sample(size, seed):
+    """One pass of the CPU oracle chain over a size x size sample tile -> seconds."""
+    from hydrodem_b200.synth import SynthScene
+    from oracle import chain
+    sc = SynthScene(size, size, seed)
+    a, g, h = sc.srtm(), sc.groves(), sc.hsheds()
+    t0 = time.perf_counter()
+    with np.errstate(all="ignore"):
+        chain.conditioning_chain(a, g, h)
+    return time.perf_counter() - t0
+
+
+def _cpu_worker(args):
+    return cpu_chain_sample(*args)
+
+
+def run_reference(args):
+    """The reference arm: the CPU implementation of the path (the oracle port of the reference's NumPy/SciPy
+    filters -- the reference itself is Python + GDAL and cannot be installed here) on all host cores."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import clib
+    clib.build()
+    cores = os.cpu_count() or 1
+    size = args.cpu_sample
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup if args.warmup < 1 else 1):
+            pool.map(_cpu_worker, [(256, SEED + i) for i in range(cores)])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_worker, [(size, SEED + i) for i in range(cores)])     # one sample tile per core per step
+        dt = time.perf_counter() - t0
+    cells = size * size * cores * args.steps
+    value = cells / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"full conditioning chain, synthetic {TILE}x{TILE} SRTM tile per GPU",
+                   "sample": f"{cores} x {size}x{size} tiles per step (cost is linear in cells)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"oracle/chain.py on {cores} processes x {size}x{size} synthetic tiles per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from hydrodem_b200 import _lib, device as dev
+    from hydrodem_b200.pipeline import ConditioningChain
+    from hydrodem_b200.synth import SynthScene
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the conditioning path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    ny = nx = args.size
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # synthetic inputs of this rank's tile, in pinned host memory
+    scene = SynthScene(ny, nx, SEED + rank)
+    host = {}
+    for name, arr in (("srtm", scene.srtm()), ("groves", scene.groves()), ("hsheds", scene.hsheds())):
+        pin = dev.pinned_empty(arr.shape, arr.dtype)
+        pin[...] = arr
+        host[name] = pin
+    chain = ConditioningChain()
+    d_in = chain.upload_inputs(host["srtm"], host["groves"], host["hsheds"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+
+    def step_resident():
+        return chain.run_device(*d_in)
+
+    # ---- resident-input timing ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    if rank == 0:
+        sampler.start()
+    lib.hd_reset_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sweeps = []
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)                                              # evict L2 between timed steps (untimed)
+        ev[k][0].record()
+        res = step_resident()
+        ev[k][1].record()
+        sweeps.append(res.info.get("fill_sweeps"))
+    barrier()
+    launches = int(lib.hd_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    cells = ny * nx
+    value = world * cells / (ms_per_step * 1e-3) / 1e6
+
+    # ---- per-kernel profile of one more step (event pair around every launch) -----------------------------
+    lib.hd_profile_enable(1)
+    flush.fill_(1)
+    step_resident()
+    import ctypes
+    cbuf = ctypes.create_string_buffer(1 << 16)
+    lib.hd_profile_report(cbuf, 1 << 16)
+    lib.hd_profile_enable(0)
+    kernels = {}
+    for line in cbuf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        kernels[name] = {"launches": int(cnt), "total_ms": float(ms)}
+    prof_total = sum(k["total_ms"] for k in kernels.values()) or 1.0
+    top = max(kernels, key=lambda n: kernels[n]["total_ms"])
+    peak, peak_kind = measured_peak()
+    top_avg_ms = kernels[top]["total_ms"] / kernels[top]["launches"]
+    algo_bytes = ALGO_BYTES_PER_CELL.get(top, 8.0) * cells
+    achieved = algo_bytes / (top_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "launches_per_step": kernels[top]["launches"],
+                "avg_launch_ms": top_avg_ms, "share_of_step": kernels[top]["total_ms"] / prof_total,
+                "algorithmic_bytes_per_launch": algo_bytes}
+    breakdown = {n: round(k["total_ms"], 4) for n, k in sorted(kernels.items(), key=lambda kv: -kv[1]["total_ms"])}
+
+    # ---- end to end through the public API, host buffers ---------------------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h2d = sum(host[n].nbytes for n in host)
+    d2h = 0
+    for k in range(min(2, args.warmup)):
+        r = chain.apply(host["srtm"], host["groves"], host["hsheds"])
+        _ = (r.final, r.filled, r.d8)
+    barrier()
+    t_e2e = 0.0
+    for k in range(e2e_steps):
+        flush.fill_(k & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = chain.apply(host["srtm"], host["groves"], host["hsheds"])
+        outs = (r.final, r.filled, r.d8)                                   # D2H into pinned buffers, synchronous
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+        d2h = sum(o.nbytes for o in outs)
+    barrier()
+    e2e_ms = max_over_ranks(t_e2e / e2e_steps * 1e3)
+    e2e_value = world * cells / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"full conditioning chain, synthetic {ny}x{nx} SRTM 1-arcsec tile per GPU "
+                                   "(BASELINE.json configs[1])",
+                       "stages": "fft2+peak mask+ifft2, groves x3 (quadratic 15), nanfix, majority 11, erode2, expand 7, "
+                                 "max 7x7, combine, mean3+round, sink-fill, D8",
+                       "tile": [ny, nx], "seed": SEED, "parallelism": f"tile-parallel x{world}, no collective",
+                       "l2": "256 MB flush buffer written between timed steps (untimed)",
+                       "fill_sweeps": sweeps[-1] if sweeps else None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "hydrodem_b200.pipeline.ConditioningChain.apply(srtm, groves, hsheds) -> final, filled, d8"},
+            "gpu_launches": launches, "launches_per_step": launches / args.steps,
+            "roofline": roofline, "kernel_ms": breakdown, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import clib
+            clib.build()
+            dt = cpu_chain_sample(args.cpu_sample, SEED)
+            line["cpu_baseline"] = {"value": args.cpu_sample ** 2 / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "seconds": dt,
+                                    "sample": f"oracle/chain.py (NumPy/SciPy restatement of the reference filters) on "
+                                              f"one {args.cpu_sample}x{args.cpu_sample} synthetic tile, 1 process"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=TILE, help="tile edge (default 3601 = BASELINE.json configs[1])")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="edge of the CPU baseline sample tile")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,11 +30,14 @@ SIGNATURES = {
     "hd_device_count": (_i, []),
     "hd_launch_count": (_i64, []),
     "hd_reset_launch_count": (None, []),
+    "hd_profile_enable": (_i, [_i]),
+    "hd_profile_report": (_i64, [ctypes.c_char_p, _i64]),
     "hd_pitch_elems": (_i64, [_i64, _i]),
     "hd_memcpy2d_h2d": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_memcpy2d_d2h": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_stream_synchronize": (_i, [_p]),
     "hd_elementwise": (_i, [_i, _p, _i, _i64, _p, _i, _i64, _d, _p, _i, _i64, _i64, _i64, _p]),
+    "hd_final_terms": (_i, [_p, _i, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _p]),
     "hd_expand": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i64, _i, _p]),
     "hd_majority": (_i, [_p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),
     "hd_nanfix": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),

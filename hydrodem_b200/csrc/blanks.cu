@@ -157,6 +157,7 @@ extern "C" int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const voi
     const int tiles_x = hd_cdiv(nx, BT), tiles_y = hd_cdiv(ny, BT), ntiles = tiles_x * tiles_y;
     HD_CUDA_OK(cudaFuncSetAttribute(hollow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const int grid = ntiles < hd_num_sms() ? ntiles : hd_num_sms();
+    hd_prof_begin("hollow_kernel", (cudaStream_t)stream);
     hollow_kernel<<<grid, BNT, SMEM, (cudaStream_t)stream>>>(tm, (const uint8_t*)mask_prev, prev_pitch, (uint8_t*)mask_out,
                                                            mask_pitch, (float*)modified, mod_pitch, ny, nx, (float)factor,
                                                            tiles_x, ntiles);
@@ -178,6 +179,7 @@ extern "C" int hd_fourier_mask_assemble(const void* q1, int64_t q1_pitch, const 
     cudaStream_t s = (cudaStream_t)stream;
 #define HD_ASM(T, TAG)                                                                                              \
     if (out_dtype == TAG) {                                                                                         \
+        hd_prof_begin("assemble_kernel", s);                                                                           \
         assemble_kernel<T><<<blocks, 256, 0, s>>>((const uint8_t*)q1, q1_pitch, (const uint8_t*)q2, q2_pitch, (T*)out, \
                                                   out_pitch, (int)ny, (int)nx, margin, invert);                   \
         HD_LAUNCH_CHECK();                                                                                          \

@@ -27,6 +27,8 @@
 
 void hd_set_last_cuda_error(int e);
 void hd_count_launch(int n = 1);
+// per-launch profiling hook: call right before a kernel launch; hd_count_launch() closes the record
+void hd_prof_begin(const char* name, cudaStream_t stream);
 
 // Host: encode a 2-D tiled tensor map over a pitched row-major raster.
 // elem: HD_F32 / HD_F64 / HD_U8 / HD_C64 (as 2xf32 -> encoded as f32 with doubled width is NOT done; c64 unsupported here)

@@ -97,9 +97,67 @@ extern "C" int hd_elementwise(int op, const void* a, int a_dtype, int64_t a_pitc
     if (ny == 0 || nx == 0) return HD_OK;
     const int64_t total = ny * nx;
     const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    hd_prof_begin("elementwise_kernel", (cudaStream_t)stream);
     elementwise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(op, a, a_dtype, a_pitch, b, b_dtype, b_pitch, b_scalar,
                                                                  out, out_dtype, out_pitch, ny, nx);
     HD_LAUNCH_CHECK();
     hd_count_launch();
     return HD_OK;
+}
+
+// ---- HydroDEMProcess._prepare_final_terms + the three-term sum (hydro_dem_process.py:60-91, :148) ----------
+//   mask   = lagoon_values > 0                         (LagoonsDetection.mask_lagoons, custom_filters.py:659)
+//   first  = srtm * (1 - (mask + rivers))
+//   third  = hsheds_fixed * rivers
+//   out    = (first + lagoon_values) + third           float64 arithmetic, rounded once to the output dtype
+namespace {
+template <typename SrtmT, typename OutT>
+__global__ void __launch_bounds__(256) final_terms_kernel(const SrtmT* __restrict__ srtm, int64_t srtm_pitch,
+                                                          const float* __restrict__ lagoons, int64_t lag_pitch,
+                                                          const float* __restrict__ hsheds, int64_t hs_pitch,
+                                                          const float* __restrict__ rivers, int64_t riv_pitch,
+                                                          OutT* __restrict__ out, int64_t out_pitch, int64_t ny, int64_t nx)
+{
+    const int64_t total = ny * nx;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t y = t / nx, x = t - y * nx;
+        const double s = (double)srtm[y * srtm_pitch + x];
+        const double lv = (double)lagoons[y * lag_pitch + x];
+        const double r = rivers ? (double)rivers[y * riv_pitch + x] : 0.0;
+        const double mask = lv > 0.0 ? 1.0 : 0.0;
+        const double first = __dmul_rn(s, 1.0 - (mask + r));
+        double acc = __dadd_rn(first, lv);
+        if (rivers) acc = __dadd_rn(acc, __dmul_rn((double)hsheds[y * hs_pitch + x], r));
+        else acc = __dadd_rn(acc, 0.0 * (double)hsheds[y * hs_pitch + x]);
+        out[y * out_pitch + x] = (OutT)acc;
+    }
+}
+}  // namespace
+
+extern "C" int hd_final_terms(const void* srtm, int srtm_dtype, int64_t srtm_pitch, const void* lagoon_values,
+                              int64_t lag_pitch, const void* hsheds_fixed, int64_t hs_pitch, const void* rivers,
+                              int64_t riv_pitch, void* out, int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx,
+                              void* stream)
+{
+    if (!srtm || !lagoon_values || !hsheds_fixed || !out) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || srtm_pitch < nx || lag_pitch < nx || hs_pitch < nx || out_pitch < nx || (rivers && riv_pitch < nx))
+        return HD_ERR_ARG;
+    const int64_t total = ny * nx;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+#define HD_FT(ST, STAG, OT, OTAG)                                                                                      \
+    if (srtm_dtype == STAG && out_dtype == OTAG) {                                                                     \
+        hd_prof_begin("final_terms_kernel", s);                                                                        \
+        final_terms_kernel<ST, OT><<<blocks, 256, 0, s>>>((const ST*)srtm, srtm_pitch, (const float*)lagoon_values,    \
+                                                          lag_pitch, (const float*)hsheds_fixed, hs_pitch,             \
+                                                          (const float*)rivers, riv_pitch, (OT*)out, out_pitch, ny, nx); \
+        HD_LAUNCH_CHECK();                                                                                             \
+        hd_count_launch();                                                                                             \
+        return HD_OK;                                                                                                  \
+    }
+    HD_FT(float, HD_F32, float, HD_F32)
+    HD_FT(float, HD_F32, double, HD_F64)
+    HD_FT(double, HD_F64, double, HD_F64)
+#undef HD_FT
+    return HD_ERR_UNSUPPORTED;
 }

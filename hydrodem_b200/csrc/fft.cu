@@ -324,6 +324,7 @@ int launch_rows(const Plan1D& p, const RowsArgs& a, int load, cudaStream_t s)
     {                                                                                                             \
         auto kern = fft_rows_kernel<LOADV, BLUEV>;                                                                \
         HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        hd_prof_begin("fft_rows_kernel", s);                                                                       \
         kern<<<grid, FNT, smem, s>>>(a, p.n, p.m, p.log2m, p.d_tw, p.d_w, p.d_bhat);                               \
     }
     if (p.bluestein) {
@@ -391,11 +392,13 @@ int hd_fft2_forward_shift_abs(void* plan, const void* in, int64_t in_pitch, void
     float2* At = A + (int64_t)ny * nx;              // [nx][ny]
     RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, 0, 0};
     if (int e = launch_rows(p->px, r1, LOAD_REAL, s)) return e;
+    hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
     RowsArgs r2{At, ny, At, ny, nullptr, 0, nx, 0, 0, 0, 0};
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
     // At[x][y] = F[y][x]; transpose back with fftshift folded in: F[y][x] -> Fs[(y + ny/2) % ny][(x + nx/2) % nx]
+    hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, true><<<transpose_grid(nx, ny), 256, 0, s>>>(At, ny, (float2*)fshift, fshift_pitch,
                                                                          (float*)fabs_out, fabs_pitch, nx, ny, nx / 2, ny / 2);
     HD_LAUNCH_CHECK(); hd_count_launch();
@@ -418,11 +421,13 @@ int hd_fft2_masked_inverse_abs(void* plan, const void* fshift, int64_t fshift_pi
     // ifftshift: unshifted index k reads shifted index (k + n/2) % n
     RowsArgs r1{fshift, fshift_pitch, A, nx, (const uint8_t*)mask, mask_pitch, ny, ny / 2, nx / 2, 1, 0};
     if (int e = launch_rows(p->px, r1, LOAD_MASKED_SHIFTED, s)) return e;
+    hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
     float* absT = (float*)A;                        // [nx][ny] float, reuses A
     RowsArgs r2{At, ny, (float2*)absT, ny, nullptr, 0, nx, 0, 0, 1, 1};
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
+    hd_prof_begin("transpose_real_kernel", s);
     if (out_dtype == HD_F32)
         transpose_real_kernel<float><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (float*)out, out_pitch, nx, ny);
     else
@@ -445,10 +450,12 @@ int hd_fft2_c2c(void* plan, const void* in, int in_dtype, int64_t in_pitch, void
     float2* At = A + (int64_t)ny * nx;
     RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, inverse ? 1 : 0, 0};
     if (int e = launch_rows(p->px, r1, in_dtype == HD_F32 ? LOAD_REAL : LOAD_C64, s)) return e;
+    hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
     RowsArgs r2{At, ny, At, ny, nullptr, 0, nx, 0, 0, inverse ? 1 : 0, 0};
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
+    hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, false><<<transpose_grid(nx, ny), 256, 0, s>>>(At, ny, (float2*)out, out_pitch, nullptr, 0, nx, ny,
                                                                           0, 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
@@ -466,9 +473,9 @@ int hd_fftshift2(const void* in, int64_t in_pitch, void* out, int64_t out_pitch,
     const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
     cudaStream_t s = (cudaStream_t)stream;
     switch (hd_dtype_size(dtype)) {
-        case 4: shift_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, in_pitch, (float*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
-        case 8: shift_kernel<double><<<blocks, 256, 0, s>>>((const double*)in, in_pitch, (double*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
-        case 16: shift_kernel<double2><<<blocks, 256, 0, s>>>((const double2*)in, in_pitch, (double2*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
+        case 4: hd_prof_begin("shift_kernel", s); shift_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, in_pitch, (float*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
+        case 8: hd_prof_begin("shift_kernel", s); shift_kernel<double><<<blocks, 256, 0, s>>>((const double*)in, in_pitch, (double*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
+        case 16: hd_prof_begin("shift_kernel", s); shift_kernel<double2><<<blocks, 256, 0, s>>>((const double2*)in, in_pitch, (double2*)out, out_pitch, (int)ny, (int)nx, sr, sc); break;
         default: return HD_ERR_UNSUPPORTED;
     }
     HD_LAUNCH_CHECK(); hd_count_launch();

@@ -184,6 +184,7 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
     const size_t smem = Z_BYTES + W_BYTES + (size_t)(FT + 2) * WS_STRIDE * 4;
     HD_CUDA_OK(cudaFuncSetAttribute(fill_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
+    hd_prof_begin("fill_init_kernel", s);
     fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
     HD_LAUNCH_CHECK(); hd_count_launch();
     // every tile starts active
@@ -200,6 +201,7 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
         for (int b = 0; b < batch && sweeps < max_sweeps; ++b) {
             HD_CUDA_OK(cudaMemsetAsync(fout, 0, (size_t)ntiles * sizeof(int), s));
             HD_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(FillCounters), s));
+            hd_prof_begin("fill_sweep_kernel", s);
             fill_sweep_kernel<<<ntiles, FNT, smem, s>>>(tm_z, tm_w, (float*)w, w_pitch, ny, nx, tiles_x, tiles_y, fin, fout,
                                                        counters);
             HD_LAUNCH_CHECK(); hd_count_launch();
@@ -214,6 +216,7 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
         if (*h_changed == 0) break;
         if (sweeps >= max_sweeps) { rc = HD_ERR_UNSUPPORTED; break; }        // did not converge within max_sweeps
     }
+    hd_prof_begin("fill_finish_kernel", s);
     fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
     HD_LAUNCH_CHECK(); hd_count_launch();
     if (sweeps_out) *sweeps_out = sweeps;
@@ -224,6 +227,7 @@ extern "C" int hd_d8(const void* w, int64_t w_pitch, void* out, int64_t out_pitc
 {
     if (!w || !out) return HD_ERR_NULL;
     if (ny < 1 || nx < 1 || w_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    hd_prof_begin("d8_kernel", (cudaStream_t)stream);
     d8_kernel<<<stream_grid(ny * nx), 256, 0, (cudaStream_t)stream>>>((const float*)w, w_pitch, (uint8_t*)out, out_pitch, ny,
                                                                     nx);
     HD_LAUNCH_CHECK(); hd_count_launch();

@@ -130,6 +130,7 @@ int launch(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64
     if (int e = hd_make_tmap_2d(&tm, in, HD_F32, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
     HD_CUDA_OK(cudaFuncSetAttribute(majority_kernel<H, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    hd_prof_begin("majority_kernel", stream);
     majority_kernel<H, OutT><<<grid_for(ntiles, 2), NT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, ny, nx, min_count,
                                                                         tiles_x, ntiles);
     HD_LAUNCH_CHECK();

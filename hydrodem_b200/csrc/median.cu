@@ -100,6 +100,7 @@ int launch(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, HD_F32, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    hd_prof_begin("median_kernel", stream);
     median_kernel<H, CIRC><<<grid_for(ntiles, 4), NT, 2 * STAGE, stream>>>(tm, (float*)out, out_pitch, ny, nx, tiles_x,
                                                                          ntiles);
     HD_LAUNCH_CHECK();

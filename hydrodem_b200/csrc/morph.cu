@@ -235,6 +235,7 @@ int launch_expand(const CUtensorMap& tm, void* out, int64_t out_pitch, int64_t n
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
     const size_t smem = 2 * STAGE_BYTES;
     HD_CUDA_OK(cudaFuncSetAttribute(expand_kernel<InT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hd_prof_begin("expand_kernel", stream);
     expand_kernel<InT, OutT><<<grid_for(ntiles, 3), NT, smem, stream>>>(tm, (OutT*)out, out_pitch, ny, nx, h, in_w, in_h,
                                                                         tiles_x, ntiles);
     HD_LAUNCH_CHECK();
@@ -302,10 +303,12 @@ extern "C" int hd_binary_morph(const void* in, int in_dtype, int64_t in_pitch, v
     cudaStream_t s = (cudaStream_t)stream;
     if (in_dtype == HD_F32) {
         HD_CUDA_OK(cudaFuncSetAttribute(morph_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hd_prof_begin("morph_kernel", s);
         morph_kernel<float><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (uint8_t*)out, out_pitch, ny, nx, prog, in_w, in_h,
                                                                  tiles_x, ntiles);
     } else if (in_dtype == HD_U8) {
         HD_CUDA_OK(cudaFuncSetAttribute(morph_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hd_prof_begin("morph_kernel", s);
         morph_kernel<uint8_t><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (uint8_t*)out, out_pitch, ny, nx, prog, in_w, in_h,
                                                                    tiles_x, ntiles);
     } else {
@@ -335,10 +338,12 @@ extern "C" int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == HD_F32) {
         HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hd_prof_begin("maxfilter_kernel", s);
         maxfilter_kernel<float><<<grid_for(ntiles, 2), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, h, in_w, in_h,
                                                                      tiles_x, ntiles);
     } else {
         HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hd_prof_begin("maxfilter_kernel", s);
         maxfilter_kernel<double><<<grid_for(ntiles, 1), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, h, in_w, in_h,
                                                                       tiles_x, ntiles);
     }

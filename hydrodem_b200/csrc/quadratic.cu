@@ -128,6 +128,7 @@ int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_p
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
     auto kern = quadratic_kernel<H, T, OutT, GROVES>;
     HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    hd_prof_begin("quadratic_kernel", stream);
     kern<<<grid_for(ntiles, 1), NT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, (const uint8_t*)groves, groves_pitch, ny, nx,
                                                     p, tiles_x, ntiles);
     HD_LAUNCH_CHECK();

@@ -1,6 +1,11 @@
 // hydrodem_b200 runtime: status strings, launch counter, pitched copies, TMA tensor-map encoding.
 #include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -8,7 +13,44 @@ static thread_local int g_last_cuda_error = 0;
 static std::atomic<int64_t> g_launches{0};
 
 void hd_set_last_cuda_error(int e) { g_last_cuda_error = e; }
-void hd_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-launch profiling (bench.py): an event pair around every kernel launch ------------------------
+namespace {
+struct ProfRecord { const char* name; cudaEvent_t start, stop; };
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+thread_local cudaStream_t g_prof_stream = nullptr;
+thread_local int g_prof_open = -1;
+constexpr size_t PROF_MAX_RECORDS = 200000;
+
+cudaEvent_t prof_event()
+{
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+void hd_prof_begin(const char* name, cudaStream_t stream)
+{
+    if (!g_prof_on || g_prof.size() >= PROF_MAX_RECORDS) { g_prof_open = -1; return; }
+    ProfRecord r{name, prof_event(), prof_event()};
+    cudaEventRecord(r.start, stream);
+    g_prof_stream = stream;
+    g_prof.push_back(r);
+    g_prof_open = (int)g_prof.size() - 1;
+}
+
+void hd_count_launch(int n)
+{
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    if (g_prof_open >= 0) {
+        cudaEventRecord(g_prof[g_prof_open].stop, g_prof_stream);
+        g_prof_open = -1;
+    }
+}
 
 size_t hd_dtype_size(int dtype)
 {
@@ -108,6 +150,42 @@ int hd_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int hd_profile_enable(int on)
+{
+    g_prof_on = on != 0;
+    return HD_OK;
+}
+
+// Synchronises the device, then writes one line per kernel: "<name> <launches> <total_ms>\n".  Clears the records.
+int64_t hd_profile_report(char* buf, int64_t cap)
+{
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    std::map<std::string, std::pair<int64_t, double>> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            auto& a = agg[r.name];
+            a.first += 1;
+            a.second += ms;
+        }
+        g_event_pool.push_back(r.start);
+        g_event_pool.push_back(r.stop);
+    }
+    g_prof.clear();
+    std::string out;
+    char line[256];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof line, "%s %lld %.6f\n", kv.first.c_str(), (long long)kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && cap > 0) {
+        const size_t n = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)out.size();
 }
 
 int64_t hd_launch_count(void) { return g_launches.load(); }

@@ -153,10 +153,12 @@ int launch_fix3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, 
     const size_t smem = 2 * ((in_w * IN_H3 * es + 127) / 128 * 128);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == HD_F32) {
+        hd_prof_begin("fix3_kernel", s);
         fix3_kernel<MODE, float><<<grid_for(ntiles, 4), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, in_w, tiles_x,
                                                                       ntiles);
     } else {
         HD_CUDA_OK(cudaFuncSetAttribute(fix3_kernel<MODE, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hd_prof_begin("fix3_kernel", s);
         fix3_kernel<MODE, double><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, in_w, tiles_x,
                                                                        ntiles);
     }
@@ -197,9 +199,11 @@ extern "C" int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t
     const size_t smem = 2 * ((in_w * IN_H3 * es + 127) / 128 * 128);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == HD_F32) {
+        hd_prof_begin("conv3_kernel", s);
         conv3_kernel<float><<<grid_for(ntiles, 4), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, p, in_w, tiles_x, ntiles);
     } else {
         HD_CUDA_OK(cudaFuncSetAttribute(conv3_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hd_prof_begin("conv3_kernel", s);
         conv3_kernel<double><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, p, in_w, tiles_x,
                                                                   ntiles);
     }

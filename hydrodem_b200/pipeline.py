@@ -1,0 +1,118 @@
+"""The full conditioning chain, device resident.
+
+Host-side mirror of ``HydroDEMProcess.start`` (hydro_dem_process.py:122-153)
+with the GDAL file handling removed: the four rasters that ``image_srtm.py``
+and ``image_hsheds.py`` read with ``gdal.Open(...).ReadAsArray()`` come in as
+NumPy arrays, everything in between runs as CUDA kernels on device rasters,
+and the results come back as NumPy arrays in the reference's dtypes.
+
+    SRTM branch    DetectApplyFourier                       image_srtm.py:125-126
+                   BinaryClosing(ones(3,3)) on the groves   image_srtm.py:177-178
+                   GrovesCorrectionsIter(iterations=3)      image_srtm.py:199
+    HSHEDS branch  LagoonsDetection                         image_hsheds.py:133-136
+                   (river routing is out of scope: ``rivers`` is a given 0/1 raster, default none)
+    combine        _prepare_final_terms + sum               hydro_dem_process.py:60-91, :148
+                   PostProcessingFinal                      hydro_dem_process.py:149
+    NEW            SinkFill + D8FlowDirection on the final DEM
+
+Inside the chain rasters are stored as float32 / uint8 (the reference's
+float64 intermediates hold float32-representable or tolerance-class values);
+conversion to the reference dtype happens once, on download.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib, device as dev
+from .exceptions import NumpyArrayExpectedError
+from .filters import custom_filters as cf
+from .filters import extension_filters as ef
+from .filters import new_filters as nf
+
+
+class ChainResult:
+    """Device rasters of one run; ``.host(name)`` / attribute access copies to NumPy lazily."""
+
+    def __init__(self, rasters, info):
+        self.rasters = rasters
+        self.info = info
+        self._host = {}
+
+    def host(self, name):
+        if name not in self._host:
+            self._host[name] = dev.download(self.rasters[name])
+        return self._host[name]
+
+    def __getattr__(self, name):
+        rasters = self.__dict__.get("rasters", {})
+        if name in rasters:
+            return self.host(name)
+        raise AttributeError(name)
+
+
+class ConditioningChain:
+    """Run the whole chain on the GPU.
+
+    >>> out = ConditioningChain().apply(srtm, groves_class, hsheds)
+    >>> out.final, out.filled, out.d8
+    """
+
+    def __init__(self, *, groves_iterations=3, with_hydrology=True, keep_intermediates=False):
+        self.groves_iterations = groves_iterations
+        self.with_hydrology = with_hydrology
+        self.keep_intermediates = keep_intermediates
+
+    # ---- device path --------------------------------------------------------------------------------
+    def run_device(self, srtm, groves_class, hsheds, rivers=None):
+        lib = _lib.load()
+        ny, nx = srtm.shape
+        out = {}
+        info = {}
+        # SRTM branch
+        daf = cf.DetectApplyFourier()
+        corrected = daf.run_device(srtm)                                   # F32 storage, ref float64
+        groves = ef.BinaryClosing(structure=np.ones((3, 3))).run_device(groves_class)   # U8 0/1
+        dem = corrected
+        gc = cf.GrovesCorrection(groves)
+        for _ in range(self.groves_iterations):
+            dem = gc.run_device(dem, out_dtype=_lib.F32)
+        # HSHEDS branch: LagoonsDetection (custom_filters.py:633-661) with float32 / uint8 intermediates
+        fixed = cf.CorrectNANValues().run_device(hsheds)
+        majority = cf.MajorityFilter(window_size=11).run_device(fixed)
+        eroded = ef.BinaryErosion(iterations=2).run_device(majority)
+        grown = cf.ExpandFilter(window_size=7).run_device(eroded)
+        prod = dev.empty(ny, nx, _lib.F32, np.float64)                      # majority * expand: exact in float32
+        dev.elementwise(_lib.OP_MUL, grown, majority, 0.0, prod)
+        tidy = ef.GreyDilation(size=(7, 7)).run_device(prod)                # lagoons_values
+        # combine + post-processing, float64 like the reference
+        fixed32 = dev.convert(fixed, _lib.F32)
+        riv = dev.convert(rivers, _lib.F32) if rivers is not None else None
+        complete = dev.empty(ny, nx, _lib.F64, np.float64)
+        _lib.check(lib.hd_final_terms(dem.ptr, dem.dtype, dem.pitch, tidy.ptr, tidy.pitch, fixed32.ptr, fixed32.pitch,
+                                      riv.ptr if riv is not None else None, riv.pitch if riv is not None else 0,
+                                      complete.ptr, complete.dtype, complete.pitch, ny, nx, dev.stream_ptr()))
+        final = cf.PostProcessingFinal().run_device(complete)
+        out["final"] = final
+        if self.with_hydrology:
+            fill = nf.SinkFill()
+            out["filled"] = fill.run_device(final)
+            info["fill_sweeps"] = fill.sweeps
+            out["d8"] = nf.D8FlowDirection().run_device(out["filled"])
+        if self.keep_intermediates:
+            out.update(fourier=corrected, fourier_mask=daf._mask_dev, fabs=daf._fabs_dev, groves=groves, srtm=dem,
+                       hsheds_nan_fixed=fixed, majority=majority, lagoons_values=tidy, dem_complete=complete)
+        return ChainResult(out, info)
+
+    # ---- host API ---------------------------------------------------------------------------------
+    def upload_inputs(self, srtm_raw, groves_class_raw, hsheds, rivers=None):
+        for a in (srtm_raw, groves_class_raw, hsheds) + ((rivers,) if rivers is not None else ()):
+            if not isinstance(a, np.ndarray):
+                raise NumpyArrayExpectedError(a)
+        if not (srtm_raw.shape == groves_class_raw.shape == hsheds.shape):
+            raise ValueError("srtm, groves_class and hsheds must have the same shape")
+        return (dev.upload(srtm_raw), dev.upload(groves_class_raw), dev.upload(hsheds),
+                dev.upload(rivers) if rivers is not None else None)
+
+    def apply(self, srtm_raw, groves_class_raw, hsheds, rivers=None):
+        """ndarrays in -> ChainResult (``final`` float64, ``filled`` float32, ``d8`` uint8)."""
+        return self.run_device(*self.upload_inputs(srtm_raw, groves_class_raw, hsheds, rivers))

@@ -2,9 +2,11 @@
 
 There is no network and the reference's input tiles are stripped from the
 repo, so every workload above the bundled 519x508
-tile is synthetic.  The recipe follows SURVEY.md section 8(d) with one
-addition, stated in DESIGN.md: a 0.3 m white-noise term on the SRTM surface
-(real SRTM carries ~1 m of sensor noise).  Without it the high-frequency half
+tile is synthetic.  The recipe follows SURVEY.md section 8(d) with two
+additions, stated in DESIGN.md: a 0.3 m white-noise term on the SRTM surface
+(real SRTM carries ~1 m of sensor noise) and 0.55 m of texture on the
+HydroSHEDS surface before rounding (calibrated on the bundled tile), with
+twice the lagoon density so that ~7 % of the cells are lagoon plateaus.  Without it the high-frequency half
 of the spectrum sits at the float32 FFT rounding floor and the Fourier
 peak detector (centre > 4 x hollow mean) thresholds pure rounding noise.
 
@@ -56,7 +58,7 @@ class SynthScene:
             self._groves.append((y0, x0, hgt, wid, np.float32(rg.uniform(2.0, 6.0))))
         # lagoons: discs flattened to their minimum
         rl = np.random.default_rng([self.seed, 3])
-        n_lag = max(1, cells // 50000)
+        n_lag = max(1, cells // 25000)
         self._lagoons = [(int(rl.integers(0, self.ny)), int(rl.integers(0, self.nx)),
                           float(rl.uniform(6.0, 40.0))) for _ in range(n_lag)]
         self._lagoon_level = None
@@ -136,7 +138,9 @@ class SynthScene:
     def hsheds(self, rows=None):
         """HydroSHEDS-style raster: integer metres as float32, lagoon plateaus, voids."""
         r0, r1 = self._rows(rows)
-        out = np.round(self.base(rows)).astype(np.float32)
+        # 0.55 m of texture before rounding to integer metres: the bundled HydroSHEDS tile has ~59 % equal
+        # horizontal neighbours (a perfectly smooth surface would make MajorityFilter fire everywhere)
+        out = np.round(self.base(rows) + self._white(rows, 6, 0.55)).astype(np.float32)
         for (cy, cx, rad), lev in zip(self._lagoons, self._levels()):
             r = int(np.ceil(rad))
             a, b = max(cy - r, r0), min(cy + r + 1, r1)

@@ -57,6 +57,10 @@ int hd_device_count(void);
 /* kernels launched by this library since the last reset (bench.py's gpu_launches) */
 int64_t hd_launch_count(void);
 void hd_reset_launch_count(void);
+/* per-kernel timing for bench.py: while enabled, every launch is bracketed by a CUDA event pair on its own
+ * stream; hd_profile_report synchronises the device and writes "<kernel> <launches> <total_ms>" lines. */
+int hd_profile_enable(int on);
+int64_t hd_profile_report(char* buf, int64_t cap);
 /* smallest pitch (elements) >= nx that satisfies the alignment rules for `dtype` rasters */
 int64_t hd_pitch_elems(int64_t nx, int dtype);
 /* pitched host<->device copies (cudaMemcpy2DAsync); pitches and width in BYTES */
@@ -82,6 +86,14 @@ typedef enum {
  * rounded once to out_dtype (innocuous double rounding: identical to native float32 arithmetic). */
 int hd_elementwise(int op, const void* a, int a_dtype, int64_t a_pitch, const void* b, int b_dtype, int64_t b_pitch,
                    double b_scalar, void* out, int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx, void* stream);
+
+/* HydroDEMProcess._prepare_final_terms and the three-term sum, hydro_dem_process.py:60-91, :148, fused:
+ * out = srtm * (1 - ((lagoon_values > 0) + rivers)) + lagoon_values + hsheds_fixed * rivers, in float64
+ * arithmetic.  srtm: F32 / F64; lagoon_values, hsheds_fixed, rivers (0/1, may be NULL = no rivers): F32;
+ * out: F32 or F64. */
+int hd_final_terms(const void* srtm, int srtm_dtype, int64_t srtm_pitch, const void* lagoon_values, int64_t lag_pitch,
+                   const void* hsheds_fixed, int64_t hs_pitch, const void* rivers, int64_t riv_pitch, void* out, int out_dtype,
+                   int64_t out_pitch, int64_t ny, int64_t nx, void* stream);
 
 /* ---- windowed filters (filters/custom_filters.py) ------------------------------------------------ */
 /* ExpandFilter.apply, custom_filters.py:102-125.  in: F32 or U8; out: U8 / F32 / F64, every cell written

@@ -1,0 +1,53 @@
+"""GPU: the fused device-resident chain (hydrodem_b200.pipeline) against the oracle chain."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from hydrodem_b200.pipeline import ConditioningChain
+    from hydrodem_b200.synth import SynthScene
+    from oracle import chain as ochain, hydrology
+
+
+@pytest.mark.parametrize("shape,seed", [((300, 420), 77), ((519, 508), 5)])
+def test_chain_vs_oracle(shape, seed):
+    sc = SynthScene(*shape, seed)
+    srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()
+    res = ConditioningChain(keep_intermediates=True).apply(srtm, groves, hsheds.copy())
+    with np.errstate(all="ignore"):
+        want = ochain.conditioning_chain(srtm, groves, hsheds.copy())
+    lag = want["lagoons"]
+    # bit-exact class
+    np.testing.assert_array_equal(res.hsheds_nan_fixed, lag["CorrectNANValues"])
+    np.testing.assert_array_equal(res.majority, lag["MajorityFilter"])
+    np.testing.assert_array_equal(res.lagoons_values, lag["TidyingLagoons"])
+    np.testing.assert_array_equal(res.groves.astype(bool), want["groves"])
+    assert int((res.fourier_mask != want["mask"]).sum()) == 0
+    # tolerance class: <= 1e-5 relative
+    np.testing.assert_allclose(res.fourier, want["fourier"], rtol=1e-5)
+    np.testing.assert_allclose(res.srtm, want["srtm"], rtol=1e-5)
+    np.testing.assert_allclose(res.dem_complete, want["dem_complete"], rtol=1e-5)
+    # rounding: flips only where the 3x3 mean sits within 1e-3 of a half-integer
+    assert res.final.dtype == np.float64
+    from oracle import stencils
+    mean = stencils.convolve_reflect(want["dem_complete"], np.ones((3, 3))) / 9
+    flips = res.final != want["final"]
+    frac = np.abs(mean - np.floor(mean) - 0.5)
+    assert (frac[flips] < 1e-3).all() and np.abs(res.final - want["final"])[flips].max(initial=0) <= 1
+    print("rounding flips:", int(flips.sum()), "of", flips.size)
+    # hydrology on the chain's own final DEM
+    np.testing.assert_array_equal(res.filled, hydrology.sinkfill(res.final))
+    np.testing.assert_array_equal(res.d8, hydrology.d8(res.filled))
+
+
+def test_chain_with_rivers():
+    sc = SynthScene(200, 260, 9)
+    srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()
+    rivers = np.zeros(srtm.shape, dtype=np.float32)
+    rivers[50, 20:200] = 1
+    res = ConditioningChain(with_hydrology=False, keep_intermediates=True).apply(srtm, groves, hsheds.copy(), rivers)
+    with np.errstate(all="ignore"):
+        want = ochain.conditioning_chain(srtm, groves, hsheds.copy(), rivers=rivers, with_hydrology=False)
+    np.testing.assert_allclose(res.dem_complete, want["dem_complete"], rtol=1e-5)

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libhydrodem_b200.so")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++20", "--expt-relaxed-constexpr",
          "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing", "--fmad=false"]
 
 

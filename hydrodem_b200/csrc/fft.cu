@@ -20,6 +20,7 @@
 // spectrum is never materialised separately.
 #include <cmath>
 #include <complex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -27,13 +28,14 @@
 namespace {
 
 constexpr int FNT = 512;                 // threads per FFT CTA
-constexpr int MAX_M = 16384;             // 128 KB of complex64 in shared memory
+constexpr int MAX_M = 16384;             // 136 KB of (padded) complex64 in shared memory
 constexpr double PI = 3.14159265358979323846;
 
 struct Plan1D {
     int n = 0, m = 0, log2m = 0;
     bool bluestein = false;
-    float2* d_tw = nullptr;              // [m/2]  exp(-2 pi i k / m)
+    int npass = 0, k[4] = {0, 0, 0, 0};  // radix-2^k passes (DIF order)
+    float2* d_tw = nullptr;              // [m]    exp(-2 pi i k / m), full circle
     float2* d_w = nullptr;               // [n]    chirp exp(-i pi k^2 / n)                  (Bluestein only)
     float2* d_bhat = nullptr;            // [m]    FFT_m(conj chirp) / m, bit-reversed order (Bluestein only)
 };
@@ -96,8 +98,10 @@ int build1d(Plan1D& p, int64_t n)
     p.n = (int)n; p.m = (int)m; p.bluestein = !pow2;
     p.log2m = 0;
     while ((1 << p.log2m) < m) ++p.log2m;
-    std::vector<float2> tw(m / 2 > 0 ? m / 2 : 1);
-    for (int64_t k = 0; k < m / 2; ++k) {
+    p.npass = p.log2m ? (p.log2m + 3) / 4 : 0;
+    for (int i = 0; i < p.npass; ++i) p.k[i] = p.log2m / p.npass + (i < p.log2m % p.npass ? 1 : 0);
+    std::vector<float2> tw(m);
+    for (int64_t k = 0; k < m; ++k) {
         const double ang = -2.0 * PI * (double)k / (double)m;
         tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
@@ -135,37 +139,165 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b)   // a * conj(b)
     return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
 
-// DIF, natural order in -> bit-reversed order out, kernel exp(-2 pi i / m)
-__device__ __forceinline__ void fft_dif(float2* s, int m, const float2* __restrict__ tw)
+// ---- register-blocked radix-2^K passes (prototype + proof of the index algebra: tools/proto/fft_passes.py) ------
+// A pass of radix R = 2^K on sub-transforms of length L works on groups {base + r + q * (L/R)}, q = 0..R-1, held
+// in registers by one thread:
+//   DIF: y = DFT_R(x) by K constant-twiddle radix-2 stages (bit-reversed register order), y[p] *= W_L^(r * rev(p))
+//   DIT: x[p] *= W_L^(+-r * rev(p)), then K constant-twiddle radix-2 stages (natural register order)
+// so a length-8192 transform is 4 shared-memory round trips (radices 16, 8, 8, 8) instead of 13.
+// Shared-memory index padding (one slot per 16) keeps the stride-R accesses of the last passes off the same banks.
+__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
+
+__host__ __device__ constexpr int rev_bits(int v, int bits)
 {
-    int tstep = 1;
-    for (int half = m >> 1; half >= 1; half >>= 1, tstep <<= 1) {
-        for (int t = threadIdx.x; t < (m >> 1); t += FNT) {
-            const int j = t & (half - 1);
-            const int i = ((t - j) << 1) + j;
-            const float2 a = s[i], b = s[i + half];
-            const float2 w = __ldg(&tw[j * tstep]);
-            s[i] = make_float2(a.x + b.x, a.y + b.y);
-            s[i + half] = cmul(make_float2(a.x - b.x, a.y - b.y), w);
-        }
-        __syncthreads();
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+// d * W_16^E (CONJ: conjugate twiddle), E = 0..7
+template <int E, bool CONJ>
+__device__ __forceinline__ float2 mul_w16(float2 d)
+{
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+    if constexpr (E == 0) return d;
+    else if constexpr (E == 4) return CONJ ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+    else {
+        constexpr float c = (E == 1) ? C1 : (E == 2) ? H : (E == 3) ? S1 : (E == 5) ? -S1 : (E == 6) ? -H : -C1;
+        constexpr float sn = (E == 1) ? S1 : (E == 2) ? H : (E == 3) ? C1 : (E == 5) ? C1 : (E == 6) ? H : S1;
+        // W = c - i sn  (forward);  conj: c + i sn
+        constexpr float si = CONJ ? sn : -sn;
+        return make_float2(fmaf(d.x, c, -d.y * si), fmaf(d.x, si, d.y * c));
     }
 }
-// DIT, bit-reversed order in -> natural order out; conj_tw = true gives the exp(+2 pi i / m) kernel
-__device__ __forceinline__ void fft_dit(float2* s, int m, const float2* __restrict__ tw, bool conj_tw)
+
+template <int K, int T = 0>
+__device__ __forceinline__ void dif_regs(float2 (&x)[1 << K])
 {
-    int tstep = m >> 1;
-    for (int half = 1; half < m; half <<= 1, tstep >>= 1) {
-        for (int t = threadIdx.x; t < (m >> 1); t += FNT) {
-            const int j = t & (half - 1);
-            const int i = ((t - j) << 1) + j;
-            const float2 w = __ldg(&tw[j * tstep]);
-            const float2 a = s[i];
-            const float2 b = conj_tw ? cmul_conj(s[i + half], w) : cmul(s[i + half], w);
-            s[i] = make_float2(a.x + b.x, a.y + b.y);
-            s[i + half] = make_float2(a.x - b.x, a.y - b.y);
+    if constexpr (T < K) {
+        constexpr int R = 1 << K, LT = R >> T, HALF = LT >> 1, STEP = 16 / LT;
+#pragma unroll
+        for (int blk = 0; blk < R; blk += LT) {
+            auto bf = [&](auto jc) {
+                constexpr int J = decltype(jc)::value;
+                const float2 a = x[blk + J], b = x[blk + J + HALF];
+                x[blk + J] = make_float2(a.x + b.x, a.y + b.y);
+                x[blk + J + HALF] = mul_w16<J * STEP, false>(make_float2(a.x - b.x, a.y - b.y));
+            };
+            [&]<int... J>(std::integer_sequence<int, J...>) { (bf(std::integral_constant<int, J>{}), ...); }
+            (std::make_integer_sequence<int, HALF>{});
         }
-        __syncthreads();
+        dif_regs<K, T + 1>(x);
+    }
+}
+
+template <int K, bool CONJ, int T = 0>
+__device__ __forceinline__ void dit_regs(float2 (&x)[1 << K])
+{
+    if constexpr (T < K) {
+        constexpr int R = 1 << K, HALF = 1 << T, LT = 2 * HALF, STEP = 16 / LT;
+#pragma unroll
+        for (int blk = 0; blk < R; blk += LT) {
+            auto bf = [&](auto jc) {
+                constexpr int J = decltype(jc)::value;
+                const float2 a = x[blk + J];
+                const float2 b = mul_w16<J * STEP, CONJ>(x[blk + J + HALF]);
+                x[blk + J] = make_float2(a.x + b.x, a.y + b.y);
+                x[blk + J + HALF] = make_float2(a.x - b.x, a.y - b.y);
+            };
+            [&]<int... J>(std::integer_sequence<int, J...>) { (bf(std::integral_constant<int, J>{}), ...); }
+            (std::make_integer_sequence<int, HALF>{});
+        }
+        dit_regs<K, CONJ, T + 1>(x);
+    }
+}
+
+// One DIF pass over sub-transforms of length L (log2 = lgL); tw = full-circle table exp(-2 pi i k / m).
+// MULB: multiply the outputs by bhat[position] on the way out (the Bluestein pointwise product, fused).
+template <int K, bool MULB>
+__device__ __forceinline__ void dif_pass(float2* s, int m, int lgm, int lgL, const float2* __restrict__ tw,
+                                         const float2* __restrict__ bhat)
+{
+    constexpr int R = 1 << K;
+    const int lgst = lgL - K, st = 1 << lgst, tshift = lgm - lgL;
+    for (int g = threadIdx.x; g < (m >> K); g += FNT) {
+        const int r = g & (st - 1);
+        const int base = ((g - r) << K) + r;
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = s[pad(base + (q << lgst))];
+        dif_regs<K>(x);
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+            constexpr int dummy = 0; (void)dummy;
+            const int mm = rev_bits(p, K);
+            float2 v = x[p];
+            if (p > 0) v = cmul(v, __ldg(&tw[(r * mm) << tshift]));
+            const int pos = base + (p << lgst);
+            if (MULB) v = cmul(v, __ldg(&bhat[pos]));
+            s[pad(pos)] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// One DIT pass producing sub-transforms of length L; CONJ selects exp(+2 pi i / m).
+template <int K, bool CONJ>
+__device__ __forceinline__ void dit_pass(float2* s, int m, int lgm, int lgL, const float2* __restrict__ tw)
+{
+    constexpr int R = 1 << K;
+    const int lgst = lgL - K, st = 1 << lgst, tshift = lgm - lgL;
+    for (int g = threadIdx.x; g < (m >> K); g += FNT) {
+        const int r = g & (st - 1);
+        const int base = ((g - r) << K) + r;
+        float2 x[R];
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+            const int mm = rev_bits(p, K);
+            float2 v = s[pad(base + (p << lgst))];
+            if (p > 0) {
+                const float2 w = __ldg(&tw[(r * mm) << tshift]);
+                v = CONJ ? cmul_conj(v, w) : cmul(v, w);
+            }
+            x[p] = v;
+        }
+        dit_regs<K, CONJ>(x);
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[pad(base + (q << lgst))] = x[q];
+    }
+    __syncthreads();
+}
+
+struct PassPlan { int npass; int k[4]; };
+
+template <bool MULB_LAST>
+__device__ __forceinline__ void fft_dif_all(float2* s, int m, int lgm, const PassPlan& pl, const float2* tw, const float2* bhat)
+{
+    int lgL = lgm;
+    for (int i = 0; i < pl.npass; ++i) {
+        const bool last = MULB_LAST && i == pl.npass - 1;
+        switch (pl.k[i]) {
+            case 1: last ? dif_pass<1, true>(s, m, lgm, lgL, tw, bhat) : dif_pass<1, false>(s, m, lgm, lgL, tw, bhat); break;
+            case 2: last ? dif_pass<2, true>(s, m, lgm, lgL, tw, bhat) : dif_pass<2, false>(s, m, lgm, lgL, tw, bhat); break;
+            case 3: last ? dif_pass<3, true>(s, m, lgm, lgL, tw, bhat) : dif_pass<3, false>(s, m, lgm, lgL, tw, bhat); break;
+            default: last ? dif_pass<4, true>(s, m, lgm, lgL, tw, bhat) : dif_pass<4, false>(s, m, lgm, lgL, tw, bhat); break;
+        }
+        lgL -= pl.k[i];
+    }
+}
+
+template <bool CONJ>
+__device__ __forceinline__ void fft_dit_all(float2* s, int m, int lgm, const PassPlan& pl, const float2* tw)
+{
+    int lgL = 0;
+    for (int i = pl.npass - 1; i >= 0; --i) {
+        lgL += pl.k[i];
+        switch (pl.k[i]) {
+            case 1: dit_pass<1, CONJ>(s, m, lgm, lgL, tw); break;
+            case 2: dit_pass<2, CONJ>(s, m, lgm, lgL, tw); break;
+            case 3: dit_pass<3, CONJ>(s, m, lgm, lgL, tw); break;
+            default: dit_pass<4, CONJ>(s, m, lgm, lgL, tw); break;
+        }
     }
 }
 
@@ -185,8 +317,9 @@ struct RowsArgs {
 };
 
 template <int LOAD, bool BLUE>
-__global__ void __launch_bounds__(FNT) fft_rows_kernel(RowsArgs a, int n, int m, int log2m, const float2* __restrict__ tw,
-                                                       const float2* __restrict__ chirp, const float2* __restrict__ bhat)
+__global__ void __launch_bounds__(FNT) fft_rows_kernel(RowsArgs a, int n, int m, int log2m, PassPlan plan,
+                                                       const float2* __restrict__ tw, const float2* __restrict__ chirp,
+                                                       const float2* __restrict__ bhat)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
@@ -210,21 +343,19 @@ __global__ void __launch_bounds__(FNT) fft_rows_kernel(RowsArgs a, int n, int m,
                 if (a.inverse) v.y = -v.y;
                 if (BLUE) v = cmul(v, __ldg(&chirp[k]));
             }
-            if (BLUE) s[k] = v;
-            else s[log2m ? (__brev((unsigned)k) >> (32 - log2m)) : 0u] = v;   // DIT wants bit-reversed input
+            if (BLUE) s[pad(k)] = v;
+            else s[pad(log2m ? (int)(__brev((unsigned)k) >> (32 - log2m)) : 0)] = v;   // DIT wants bit-reversed input
         }
         __syncthreads();
         if (BLUE) {
-            fft_dif(s, m, tw);
-            for (int k = threadIdx.x; k < m; k += FNT) s[k] = cmul(s[k], __ldg(&bhat[k]));
-            __syncthreads();
-            fft_dit(s, m, tw, true);
+            fft_dif_all<true>(s, m, log2m, plan, tw, bhat);       // ... * FFT(conj chirp) / m fused into the last pass
+            fft_dit_all<true>(s, m, log2m, plan, tw);
         } else if (m > 1) {
-            fft_dit(s, m, tw, false);
+            fft_dit_all<false>(s, m, log2m, plan, tw);
         }
         // ---- store -------------------------------------------------------------------------------------------
         for (int k = threadIdx.x; k < n; k += FNT) {
-            float2 v = s[k];
+            float2 v = s[pad(k)];
             if (BLUE) v = cmul(v, __ldg(&chirp[k]));
             if (a.inverse) v.y = -v.y;
             v.x *= scale; v.y *= scale;
@@ -315,17 +446,19 @@ __global__ void __launch_bounds__(256) shift_kernel(const T* __restrict__ in, in
 // ---- host launch helpers -----------------------------------------------------------------------------------------
 int launch_rows(const Plan1D& p, const RowsArgs& a, int load, cudaStream_t s)
 {
-    const size_t smem = (size_t)p.m * sizeof(float2);
-    const int per_sm = smem > 0 ? (int)(200 * 1024 / (smem + 1024)) : 1;
-    int grid = hd_num_sms() * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
-    if (grid > a.nrows) grid = a.nrows;
-    if (grid < 1) return HD_OK;
-#define HD_ROWS(LOADV, BLUEV)                                                                                     \
-    {                                                                                                             \
-        auto kern = fft_rows_kernel<LOADV, BLUEV>;                                                                \
-        HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-        hd_prof_begin("fft_rows_kernel", s);                                                                       \
-        kern<<<grid, FNT, smem, s>>>(a, p.n, p.m, p.log2m, p.d_tw, p.d_w, p.d_bhat);                               \
+    const size_t smem = (size_t)(p.m + (p.m >> 4) + 1) * sizeof(float2);
+    PassPlan plan{p.npass, {p.k[0], p.k[1], p.k[2], p.k[3]}};
+    if (a.nrows < 1) return HD_OK;
+#define HD_ROWS(LOADV, BLUEV)                                                                          \
+    {                                                                                                  \
+        auto kern = fft_rows_kernel<LOADV, BLUEV>;                                                     \
+        HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int per_sm = 1;                                                                                \
+        HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FNT, smem));            \
+        int grid = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);                                           \
+        if (grid > a.nrows) grid = a.nrows;                                                            \
+        hd_prof_begin("fft_rows_kernel", s);                                                           \
+        kern<<<grid, FNT, smem, s>>>(a, p.n, p.m, p.log2m, plan, p.d_tw, p.d_w, p.d_bhat);              \
     }
     if (p.bluestein) {
         if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, true)

@@ -16,6 +16,9 @@
 // vote per thread group, one atomic per changed tile.
 //
 // Algorithmic HBM traffic: 4 B (z) + 4 B (W) read + 4 B (W) written per cell of an active tile per sweep.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -126,6 +129,207 @@ __global__ void __launch_bounds__(FNT) fill_sweep_kernel(const __grid_constant__
     }
 }
 
+// ---- asynchronous worklist variant (default on one GPU) --------------------------------------------------------------
+// The sweep kernel above needs one launch per "ring" of tiles the fill wave crosses (39 sweeps on a 3601^2 tile) and
+// visits every active tile once per sweep.  Here a persistent grid of co-resident CTAs pulls tiles from a device-side
+// FIFO: a tile that changed pushes exactly the neighbours whose halo it changed, so the wave advances as fast as single
+// tiles finish and nothing waits for a grid-wide barrier.  Because the fixed point is unique, the (racy) order in which
+// tiles are processed cannot change the result.
+//   queue  : ring of tile ids; producers reserve a slot with atomicAdd(tail), consumers take tickets with
+//            atomicAdd(head) and wait for "their" slot; `queued[tile]` de-duplicates; `pending` = tiles queued or in
+//            flight, 0 means the global fixed point is reached.
+//   memory : W is read with ld.global.cg (L2, never a stale L1 line) and written with plain stores followed by
+//            __threadfence() before the neighbour is published.
+struct FillCtl {
+    int head, tail, pending, error;
+    unsigned long long visits, changed_visits;
+    int qcap, pad_[5];
+};
+constexpr int SLOT_EMPTY = -1;
+constexpr int SPIN_LIMIT = 1 << 22;
+// per-tile state: a tile is never processed by two CTAs at once (a second writer could overwrite a lower W with a
+// higher one); a tile that is poked while running is marked dirty and re-queued by its own worker when it finishes
+enum { T_IDLE = 0, T_QUEUED = 1, T_RUNNING = 2, T_DIRTY = 3 };
+
+__device__ __forceinline__ void fill_push(FillCtl* ctl, int* slots, int qcap, int tile)
+{
+    atomicAdd(&ctl->pending, 1);
+    const int t = atomicAdd(&ctl->tail, 1);
+    *(volatile int*)(slots + (t % qcap)) = tile;
+}
+__device__ __forceinline__ void fill_poke(FillCtl* ctl, int* slots, int qcap, int* state, int tile)
+{
+    for (;;) {
+        const int st = atomicCAS(&state[tile], T_IDLE, T_QUEUED);
+        if (st == T_IDLE) { fill_push(ctl, slots, qcap, tile); return; }
+        if (st == T_QUEUED || st == T_DIRTY) return;
+        if (atomicCAS(&state[tile], T_RUNNING, T_DIRTY) == T_RUNNING) return;     // else the state moved: retry
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_seed_kernel(const float* __restrict__ z, int64_t z_pitch, int64_t ny, int64_t nx,
+                                                        int tiles_x, int tiles_y, FillCtl* ctl, int* __restrict__ slots,
+                                                        int* __restrict__ queued)
+{
+    // one warp per tile: a tile is seeded when it touches the raster frame or contains a NaN cell (an outlet)
+    const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = tiles_x * tiles_y;
+    for (int tile = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tile < ntiles; tile += gridDim.x * warps_per_block) {
+        const int ty = tile / tiles_x, tx = tile % tiles_x;
+        const int64_t y0 = (int64_t)ty * FT, x0 = (int64_t)tx * FT;
+        const int64_t y1 = y0 + FT < ny ? y0 + FT : ny, x1 = x0 + FT < nx ? x0 + FT : nx;
+        bool seed = (ty == 0 || tx == 0 || ty == tiles_y - 1 || tx == tiles_x - 1);
+        if (!seed) {
+            bool nan = false;
+            for (int64_t y = y0; y < y1 && !nan; ++y)
+                for (int64_t x = x0 + lane; x < x1; x += 32) {
+                    const float v = z[y * z_pitch + x];
+                    nan |= (v != v);
+                }
+            seed = __any_sync(0xffffffffu, nan);
+        }
+        if (seed && lane == 0) {
+            queued[tile] = T_QUEUED;
+            fill_push(ctl, slots, ctl->qcap, tile);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FNT) fill_async_kernel(const __grid_constant__ CUtensorMap tm_z, float* __restrict__ w,
+                                                         int64_t w_pitch, int64_t ny, int64_t nx, int tiles_x, int tiles_y,
+                                                         FillCtl* ctl, int* slots, int* queued)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ int s_tile;
+    __shared__ unsigned s_edges;
+    float* zs = reinterpret_cast<float*>(smem);                           // [FT][FT]
+    float* wold = reinterpret_cast<float*>(smem + Z_BYTES);               // [(FT+2)][WS_STRIDE] as loaded
+    float* ws = wold + (FT + 2) * WS_STRIDE;                              // [(FT+2)][WS_STRIDE] working copy
+    const int qcap = ctl->qcap;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    const int group = threadIdx.x >> 6, lane64 = threadIdx.x & 63;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (unsigned it = 0;; ++it) {
+        // ---- take a ticket and wait for its slot --------------------------------------------------------------------
+        if (threadIdx.x == 0) {
+            int tile = -1;
+            const int my = atomicAdd(&ctl->head, 1);
+            volatile int* slot = slots + (my % qcap);
+            for (int spin = 0;; ++spin) {
+                const int v = *slot;
+                if (v != SLOT_EMPTY) { *slot = SLOT_EMPTY; tile = v; break; }
+                if (*(volatile int*)&ctl->pending <= 0 || *(volatile int*)&ctl->error) break;
+                if (spin > SPIN_LIMIT) { atomicExch(&ctl->error, 1); break; }
+                __nanosleep(200);
+            }
+            if (tile >= 0) { atomicExch(&queued[tile], T_RUNNING); __threadfence(); }
+            s_tile = tile;
+            s_edges = 0u;
+        }
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile < 0) return;
+        const int ty0 = (tile / tiles_x) * FT, tx0 = (tile % tiles_x) * FT;
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&bar, Z_BYTES);
+            tma_load_2d(zs, &tm_z, tx0, ty0, &bar);
+        }
+        // W with a one-cell halo straight from L2; outside the raster = NaN (ignored by fminf)
+        const bool vec_ok = ((w_pitch & 3) == 0) && ((((uintptr_t)w) & 15) == 0);
+#pragma unroll 2
+        for (int t = threadIdx.x; t < (FT + 2) * 18; t += FNT) {
+            // per row of the box: 16 aligned float4 (the 64 tile columns) + the two halo columns
+            const int r = t / 18, k = t - r * 18;
+            const int64_t y = (int64_t)ty0 - 1 + r;
+            const bool yin = y >= 0 && y < ny;
+            float* po = wold + r * WS_STRIDE;
+            float* pw = ws + r * WS_STRIDE;
+            if (k < 16) {
+                const int64_t x = (int64_t)tx0 + 4 * k;
+                float4 v = make_float4(qnan, qnan, qnan, qnan);
+                if (yin && vec_ok && x + 3 < nx) {
+                    v = __ldcg(reinterpret_cast<const float4*>(w + y * w_pitch + x));
+                } else if (yin) {
+                    if (x < nx) v.x = __ldcg(w + y * w_pitch + x);
+                    if (x + 1 < nx) v.y = __ldcg(w + y * w_pitch + x + 1);
+                    if (x + 2 < nx) v.z = __ldcg(w + y * w_pitch + x + 2);
+                    if (x + 3 < nx) v.w = __ldcg(w + y * w_pitch + x + 3);
+                }
+                const int c = 1 + 4 * k;
+                po[c] = v.x; po[c + 1] = v.y; po[c + 2] = v.z; po[c + 3] = v.w;
+                pw[c] = v.x; pw[c + 1] = v.y; pw[c + 2] = v.z; pw[c + 3] = v.w;
+            } else {
+                const int c = (k == 16) ? 0 : FT + 1;
+                const int64_t x = (int64_t)tx0 - 1 + c;
+                float v = qnan;
+                if (yin && x >= 0 && x < nx) v = __ldcg(w + y * w_pitch + x);
+                po[c] = v;
+                pw[c] = v;
+            }
+        }
+        mbar_wait(&bar, it & 1);
+        __syncthreads();
+        bool tile_changed = false;
+        for (int iter = 0; iter < 4096; ++iter) {
+            bool changed = false;
+            for (int step = 0; step < FT; ++step) {
+                int r, c;
+                if (group == 0) { r = step; c = lane64; }
+                else if (group == 1) { r = FT - 1 - step; c = lane64; }
+                else if (group == 2) { r = lane64; c = step; }
+                else { r = lane64; c = FT - 1 - step; }
+                float* cell = ws + (r + 1) * WS_STRIDE + (c + 1);
+                const float cand = relax(ws, zs, r, c);
+                if (cand < *cell) { *cell = cand; changed = true; }
+            }
+            if (!__syncthreads_or(changed)) break;
+            tile_changed = true;
+        }
+        if (tile_changed) {
+            unsigned edges = 0u;
+            for (int t = threadIdx.x; t < FT * FT; t += FNT) {
+                const int r = t >> 6, c = t & 63;
+                const int64_t y = ty0 + r, x = tx0 + c;
+                const float nv = ws[(r + 1) * WS_STRIDE + c + 1], ov = wold[(r + 1) * WS_STRIDE + c + 1];
+                if (y < ny && x < nx && nv != ov && !(nv != nv)) {
+                    w[y * w_pitch + x] = nv;
+                    // which neighbours read this cell as halo: bit = (dy+1)*3 + (dx+1)
+                    const int dy0 = (r == 0) ? -1 : 0, dy1 = (r == FT - 1 || y == ny - 1) ? 1 : 0;
+                    const int dx0 = (c == 0) ? -1 : 0, dx1 = (c == FT - 1 || x == nx - 1) ? 1 : 0;
+                    for (int dy = dy0; dy <= dy1; ++dy)
+                        for (int dx = dx0; dx <= dx1; ++dx)
+                            if (dy | dx) edges |= 1u << ((dy + 1) * 3 + (dx + 1));
+                }
+            }
+            if (edges) atomicOr(&s_edges, edges);
+            __threadfence();                                   // W stores visible device-wide before neighbours are published
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned edges = s_edges;
+            const int ty = tile / tiles_x, tx = tile % tiles_x;
+            for (int k = 0; k < 9; ++k) {
+                if (!((edges >> k) & 1u)) continue;
+                const int tyy = ty + k / 3 - 1, txx = tx + k % 3 - 1;
+                if (tyy < 0 || tyy >= tiles_y || txx < 0 || txx >= tiles_x) continue;
+                fill_poke(ctl, slots, qcap, queued, tyy * tiles_x + txx);
+            }
+            atomicAdd(&ctl->visits, 1ull);
+            if (tile_changed) atomicAdd(&ctl->changed_visits, 1ull);
+            __threadfence();
+            if (atomicCAS(&queued[tile], T_RUNNING, T_IDLE) != T_RUNNING) {     // poked while running: go again
+                atomicExch(&queued[tile], T_QUEUED);
+                fill_push(ctl, slots, qcap, tile);
+            }
+            __threadfence();
+            atomicSub(&ctl->pending, 1);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- D8 ------------------------------------------------------------------------------------------------------
 // ESRI codes E=1 SE=2 S=4 SW=8 W=16 NW=32 N=64 NE=128; steepest positive drop, diagonal drops scaled by
 // 0.70710678f in float32; ties keep the first in that order; frame cells, NaN centres, no drop -> 0.
@@ -161,10 +365,58 @@ int stream_grid(int64_t total)
 
 }  // namespace
 
+
+static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
+                        int* visits_out, cudaStream_t s)
+{
+    const int tiles_x = hd_cdiv(nx, FT), tiles_y = hd_cdiv(ny, FT), ntiles = tiles_x * tiles_y;
+    FillCtl* ctl = (FillCtl*)workspace;
+    const int qcap = ntiles + 8192;
+    int* slots = (int*)((char*)workspace + 256);
+    int* queued = slots + qcap;
+    CUtensorMap tm_z;
+    if (int e = hd_make_tmap_2d(&tm_z, z, HD_F32, ny, nx, z_pitch, FT, FT, false)) return e;
+    const size_t smem = Z_BYTES + 2 * (size_t)(FT + 2) * WS_STRIDE * 4;
+    HD_CUDA_OK(cudaFuncSetAttribute(fill_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel, FNT, smem));
+    int grid = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);       // every CTA must be co-resident: they wait on each other
+    if (grid > ntiles) grid = ntiles;
+    FillCtl h{};
+    h.qcap = qcap;
+    HD_CUDA_OK(cudaMemsetAsync(slots, 0xff, (size_t)qcap * sizeof(int), s));        // SLOT_EMPTY = -1
+    HD_CUDA_OK(cudaMemsetAsync(queued, 0, (size_t)ntiles * sizeof(int), s));
+    HD_CUDA_OK(cudaMemcpyAsync(ctl, &h, sizeof h, cudaMemcpyHostToDevice, s));
+    hd_prof_begin("fill_init_kernel", s);
+    fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    hd_prof_begin("fill_seed_kernel", s);
+    fill_seed_kernel<<<hd_cdiv(ntiles, 8) < 1184 ? hd_cdiv(ntiles, 8) : 1184, 256, 0, s>>>(
+        (const float*)z, z_pitch, ny, nx, tiles_x, tiles_y, ctl, slots, queued);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    hd_prof_begin("fill_async_kernel", s);
+    fill_async_kernel<<<grid, FNT, smem, s>>>(tm_z, (float*)w, w_pitch, ny, nx, tiles_x, tiles_y, ctl, slots, queued);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    hd_prof_begin("fill_finish_kernel", s);
+    fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    static FillCtl* h_ctl = nullptr;
+    if (!h_ctl) HD_CUDA_OK(cudaHostAlloc((void**)&h_ctl, sizeof(FillCtl), cudaHostAllocDefault));
+    HD_CUDA_OK(cudaMemcpyAsync(h_ctl, ctl, sizeof(FillCtl), cudaMemcpyDeviceToHost, s));
+    HD_CUDA_OK(cudaStreamSynchronize(s));
+    if (getenv("HD_FILL_TRACE"))
+        fprintf(stderr, "pdfill async: %llu tile visits (%llu changed) over %d tiles, grid %d\n", h_ctl->visits,
+                h_ctl->changed_visits, ntiles, grid);
+    if (visits_out) *visits_out = (int)h_ctl->visits;
+    if (h_ctl->error || h_ctl->pending != 0) return HD_ERR_UNSUPPORTED;    // worklist stalled (should not happen)
+    return HD_OK;
+}
+
 extern "C" int64_t hd_pdfill_workspace_bytes(int64_t ny, int64_t nx)
 {
     const int64_t ntiles = (int64_t)hd_cdiv(ny, FT) * hd_cdiv(nx, FT);
-    return 2 * ntiles * (int64_t)sizeof(int) + 256;
+    // control block + FIFO ring (ntiles + slack) + per-tile flags; the sweep variant uses two flag arrays
+    return 256 + (2 * ntiles + 8192) * (int64_t)sizeof(int) + 2 * ntiles * (int64_t)sizeof(int);
 }
 
 extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
@@ -175,6 +427,9 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
     if (workspace_bytes < hd_pdfill_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     const int tiles_x = hd_cdiv(nx, FT), tiles_y = hd_cdiv(ny, FT), ntiles = tiles_x * tiles_y;
+    const char* mode = getenv("HD_FILL_MODE");
+    if (!(mode && mode[0] == 's') && max_sweeps <= 0)
+        return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, sweeps_out, s);
     FillCounters* counters = (FillCounters*)workspace;
     int* flags_a = (int*)((char*)workspace + 256);
     int* flags_b = flags_a + ntiles;
@@ -195,7 +450,8 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
     int* fin = flags_a;
     int* fout = flags_b;
     if (max_sweeps <= 0) max_sweeps = 1 << 30;
-    const int batch = 4;                      // sweeps between host convergence checks
+    const bool trace = getenv("HD_FILL_TRACE") != nullptr;
+    const int batch = trace ? 1 : 4;          // sweeps between host convergence checks
     for (;;) {
         int last_changed_ptr_valid = 0;
         for (int b = 0; b < batch && sweeps < max_sweeps; ++b) {
@@ -213,6 +469,7 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
         // the counter of the LAST sweep of the batch: zero means that sweep found a global fixed point
         HD_CUDA_OK(cudaMemcpyAsync(h_changed, &counters->changed_tiles, sizeof(int), cudaMemcpyDeviceToHost, s));
         HD_CUDA_OK(cudaStreamSynchronize(s));
+        if (trace) fprintf(stderr, "pdfill sweep %d: %d of %d tiles changed\n", sweeps, *h_changed, ntiles);
         if (*h_changed == 0) break;
         if (sweeps >= max_sweeps) { rc = HD_ERR_UNSUPPORTED; break; }        // did not converge within max_sweeps
     }

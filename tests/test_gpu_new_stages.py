@@ -63,6 +63,18 @@ def test_sinkfill_d8_vs_oracle(shape):
     eq(nf.SinkFill().apply(w), w)
 
 
+@pytest.mark.parametrize("mode", ["sweep", "async"])
+def test_sinkfill_modes_agree(mode, monkeypatch):
+    """Both schedules (level-synchronous sweeps, asynchronous worklist) reach the same unique fixed point."""
+    if mode == "sweep":
+        monkeypatch.setenv("HD_FILL_MODE", "sweep")
+    else:
+        monkeypatch.delenv("HD_FILL_MODE", raising=False)
+    z = _terrain(515, 777, 12)
+    z[100:104, 200:230] = np.nan
+    eq(nf.SinkFill().apply(z), hydrology.sinkfill(z))
+
+
 def test_sinkfill_small_against_iterative_pd():
     z = _terrain(48, 50, 3)
     it, _ = hydrology.sinkfill_iterative(z)

@@ -35,7 +35,8 @@ constexpr uint32_t W_BYTES = WBOX_W * WBOX_H * 4;
 struct FillCounters { int changed_tiles; int pad[3]; };
 
 __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
-                                                        int64_t w_pitch, int64_t ny, int64_t nx)
+                                                        int64_t w_pitch, int64_t ny, int64_t nx, int top_is_halo = 0,
+                                                        int bottom_is_halo = 0)
 {
     const int64_t total = ny * nx;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict_
         const float v = z[y * z_pitch + x];
         float r = __int_as_float(0x7f800000);                                    // +inf inside
         if (v != v) r = __int_as_float(0xff800000);                              // nodata: outlet at -inf
-        else if (y == 0 || x == 0 || y == ny - 1 || x == nx - 1) r = v;          // frame: W = z
+        else if ((y == 0 && !top_is_halo) || x == 0 || (y == ny - 1 && !bottom_is_halo) || x == nx - 1)
+            r = v;                                                               // frame: W = z (a band's halo rows are not frame)
         w[y * w_pitch + x] = r;
     }
 }
@@ -169,7 +171,7 @@ __device__ __forceinline__ void fill_poke(FillCtl* ctl, int* slots, int qcap, in
 
 __global__ void __launch_bounds__(256) fill_seed_kernel(const float* __restrict__ z, int64_t z_pitch, int64_t ny, int64_t nx,
                                                         int tiles_x, int tiles_y, FillCtl* ctl, int* __restrict__ slots,
-                                                        int* __restrict__ queued)
+                                                        int* __restrict__ queued, int edge_rows_only)
 {
     // one warp per tile: a tile is seeded when it touches the raster frame or contains a NaN cell (an outlet)
     const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
@@ -179,7 +181,10 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(const float* __restrict_
         const int64_t y0 = (int64_t)ty * FT, x0 = (int64_t)tx * FT;
         const int64_t y1 = y0 + FT < ny ? y0 + FT : ny, x1 = x0 + FT < nx ? x0 + FT : nx;
         bool seed = (ty == 0 || tx == 0 || ty == tiles_y - 1 || tx == tiles_x - 1);
-        if (!seed) {
+        if (edge_rows_only) {
+            // continuing a banded fill: only the tile rows next to a refreshed halo row can change
+            seed = ((edge_rows_only & 2) && ty == 0) || ((edge_rows_only & 4) && ty == tiles_y - 1);
+        } else if (!seed) {
             bool nan = false;
             for (int64_t y = y0; y < y1 && !nan; ++y)
                 for (int64_t x = x0 + lane; x < x1; x += 32) {
@@ -366,8 +371,10 @@ int stream_grid(int64_t total)
 }  // namespace
 
 
+// flags: 1 = W already initialised (continue a banded fill), 2 / 4 = the top / bottom raster row is a halo row of a
+// neighbouring band (not frame); finish = restore NaN at nodata cells afterwards
 static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
-                        int* visits_out, cudaStream_t s)
+                        int* visits_out, cudaStream_t s, int flags = 0, bool finish = true)
 {
     const int tiles_x = hd_cdiv(nx, FT), tiles_y = hd_cdiv(ny, FT), ntiles = tiles_x * tiles_y;
     FillCtl* ctl = (FillCtl*)workspace;
@@ -387,19 +394,24 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     HD_CUDA_OK(cudaMemsetAsync(slots, 0xff, (size_t)qcap * sizeof(int), s));        // SLOT_EMPTY = -1
     HD_CUDA_OK(cudaMemsetAsync(queued, 0, (size_t)ntiles * sizeof(int), s));
     HD_CUDA_OK(cudaMemcpyAsync(ctl, &h, sizeof h, cudaMemcpyHostToDevice, s));
-    hd_prof_begin("fill_init_kernel", s);
-    fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
-    HD_LAUNCH_CHECK(); hd_count_launch();
+    if (!(flags & 1)) {
+        hd_prof_begin("fill_init_kernel", s);
+        fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, flags & 2,
+                                                             flags & 4);
+        HD_LAUNCH_CHECK(); hd_count_launch();
+    }
     hd_prof_begin("fill_seed_kernel", s);
     fill_seed_kernel<<<hd_cdiv(ntiles, 8) < 1184 ? hd_cdiv(ntiles, 8) : 1184, 256, 0, s>>>(
-        (const float*)z, z_pitch, ny, nx, tiles_x, tiles_y, ctl, slots, queued);
+        (const float*)z, z_pitch, ny, nx, tiles_x, tiles_y, ctl, slots, queued, (flags & 1) ? (flags & 6) : 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
     hd_prof_begin("fill_async_kernel", s);
     fill_async_kernel<<<grid, FNT, smem, s>>>(tm_z, (float*)w, w_pitch, ny, nx, tiles_x, tiles_y, ctl, slots, queued);
     HD_LAUNCH_CHECK(); hd_count_launch();
-    hd_prof_begin("fill_finish_kernel", s);
-    fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
-    HD_LAUNCH_CHECK(); hd_count_launch();
+    if (finish) {
+        hd_prof_begin("fill_finish_kernel", s);
+        fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
+        HD_LAUNCH_CHECK(); hd_count_launch();
+    }
     static FillCtl* h_ctl = nullptr;
     if (!h_ctl) HD_CUDA_OK(cudaHostAlloc((void**)&h_ctl, sizeof(FillCtl), cudaHostAllocDefault));
     HD_CUDA_OK(cudaMemcpyAsync(h_ctl, ctl, sizeof(FillCtl), cudaMemcpyDeviceToHost, s));
@@ -478,6 +490,27 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
     HD_LAUNCH_CHECK(); hd_count_launch();
     if (sweeps_out) *sweeps_out = sweeps;
     return rc;
+}
+
+extern "C" int hd_pdfill_band(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx,
+                              void* workspace, int64_t workspace_bytes, int flags, int* visits_out, void* stream)
+{
+    if (!z || !w || !workspace) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || z_pitch < nx || w_pitch < nx || (flags & ~7)) return HD_ERR_ARG;
+    if (workspace_bytes < hd_pdfill_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
+    return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, (cudaStream_t)stream, flags, false);
+}
+
+extern "C" int hd_pdfill_finish(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx,
+                                void* stream)
+{
+    if (!z || !w) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || z_pitch < nx || w_pitch < nx) return HD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    hd_prof_begin("fill_finish_kernel", s);
+    fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
 }
 
 extern "C" int hd_d8(const void* w, int64_t w_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx, void* stream)

@@ -191,6 +191,13 @@ int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch,
 int64_t hd_pdfill_workspace_bytes(int64_t ny, int64_t nx);
 int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
               int64_t workspace_bytes, int max_sweeps, int* sweeps_out, void* stream);
+/* Row-band variant for one band of a sharded mosaic (hydrodem_b200/sharding.py): the raster passed in is
+ * [halo row | band | halo row].  flags: 1 = W is already initialised (continue after a halo exchange; only the
+ * tile rows next to the halo rows are re-seeded), 2 / 4 = the top / bottom row is a neighbour's halo row, not
+ * raster frame.  Nodata cells stay at -inf until hd_pdfill_finish restores NaN.  *visits_out = tile visits. */
+int hd_pdfill_band(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
+                   int64_t workspace_bytes, int flags, int* visits_out, void* stream);
+int hd_pdfill_finish(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* stream);
 /* D8 flow direction on a (filled) F32 surface -> U8 ESRI codes (E=1, SE=2, S=4, SW=8, W=16, NW=32, N=64, NE=128);
  * steepest positive drop, diagonals scaled by 0.70710678f, ties -> first in that order, frame / NaN / flat -> 0. */
 int hd_d8(const void* w, int64_t w_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx, void* stream);

@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(const float* __restrict_
         const int64_t y1 = y0 + FT < ny ? y0 + FT : ny, x1 = x0 + FT < nx ? x0 + FT : nx;
         bool seed = (ty == 0 || tx == 0 || ty == tiles_y - 1 || tx == tiles_x - 1);
         if (edge_rows_only) {
-            // continuing a banded fill: only the tile rows next to a refreshed halo row can change
-            seed = ((edge_rows_only & 2) && ty == 0) || ((edge_rows_only & 4) && ty == tiles_y - 1);
+            // continuing a banded fill: only tiles that hold a refreshed halo row, or read it as their own halo
+            // (the row next to it), can change
+            seed = ((edge_rows_only & 2) && ty == 0) || ((edge_rows_only & 4) && ty >= (int)((ny - 2) / FT));
         } else if (!seed) {
             bool nan = false;
             for (int64_t y = y0; y < y1 && !nan; ++y)

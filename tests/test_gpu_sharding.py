@@ -34,9 +34,10 @@ def test_banded_stencils_match_single_gpu(world):
     np.testing.assert_array_equal(np.concatenate([r[2] for r in res]), want_er)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_banded_sinkfill_matches_oracle(world):
-    sc = SynthScene(400, 390, 52)
+@pytest.mark.parametrize("world,ny", [(2, 400), (4, 400), (2, 512), (3, 386)])
+def test_banded_sinkfill_matches_oracle(world, ny):
+    # ny = 512 / world 2: the extended band has 257 rows, so the halo row sits alone in its tile row
+    sc = SynthScene(ny, 390, 52)
     z = np.round(sc.srtm())
     z[100:103, 50:60] = np.nan
     z[200:260, 100:180] -= 9                                   # a pan that spans band boundaries

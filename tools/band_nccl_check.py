@@ -28,7 +28,7 @@ for _ in range(2):                                                    # warm-up 
     maj = band.apply(cf.MajorityFilter(window_size=11), d_hs, 5)
     w, d8 = band.sinkfill(d_z)
     torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
-got = [dev.download(maj), dev.download(w), dev.download(d8)]
+got = [dev.download(maj), dev.download(w), dev.download(d8), hs, z]
 gathered = [None] * world
 dist.all_gather_object(gathered, got)
 if rank == 0:
@@ -36,9 +36,12 @@ if rank == 0:
     ref_maj = cf.MajorityFilter(window_size=11).apply(full_hs)
     ref_w = nf.SinkFill().apply(full_z)
     ref_d8 = nf.D8FlowDirection().apply(ref_w)
-    ok = (np.array_equal(np.concatenate([g[0] for g in gathered]), ref_maj)
-          and np.array_equal(np.concatenate([g[1] for g in gathered]), ref_w, equal_nan=True)
-          and np.array_equal(np.concatenate([g[2] for g in gathered]), ref_d8))
+    cat = [np.concatenate([g[k] for g in gathered]) for k in range(5)]
+    parts = dict(majority=np.array_equal(cat[0], ref_maj), fill=np.array_equal(cat[1], ref_w, equal_nan=True),
+                 d8=np.array_equal(cat[2], ref_d8), hs_input=np.array_equal(cat[3], full_hs),
+                 z_input=np.array_equal(cat[4], full_z))
+    print(parts, "fill diff cells", int((cat[1] != ref_w).sum()), "maj diff", int((cat[0] != ref_maj).sum()), flush=True)
+    ok = all(parts.values())
     print(f"band check world={world} n={n}: {'OK' if ok else 'MISMATCH'}  rounds={band.fill_rounds}  "
           f"majority+fill+d8 {dt * 1e3:.1f} ms  ({n * n / dt / 1e6:.0f} Mcells/s)", flush=True)
     if not ok:

@@ -212,6 +212,22 @@ __device__ __forceinline__ void dit_regs(float2 (&x)[1 << K])
     }
 }
 
+// W_L^(r * mm), mm = 1 .. R-1: the powers of two are loaded from the table (correctly rounded), the others are products
+// of at most three of them -- 4 loads instead of 15 for radix 16; the loads were the kernel's long-scoreboard stalls.
+template <int K>
+__device__ __forceinline__ void pass_twiddles(float2 (&w)[1 << K], const float2* __restrict__ tw, int r, int tshift)
+{
+    constexpr int R = 1 << K;
+#pragma unroll
+    for (int b = 1; b < R; b <<= 1) w[b] = __ldg(&tw[(r * b) << tshift]);
+#pragma unroll
+    for (int mm = 3; mm < R; ++mm) {
+        constexpr int dummy = 0; (void)dummy;
+        const int hi = 1 << (31 - __builtin_clz(mm));       // highest set bit (compile-time after unrolling)
+        if (mm != hi) w[mm] = cmul(w[hi], w[mm - hi]);
+    }
+}
+
 // One DIF pass over sub-transforms of length L (log2 = lgL); tw = full-circle table exp(-2 pi i k / m).
 // MULB: multiply the outputs by bhat[position] on the way out (the Bluestein pointwise product, fused).
 template <int K, bool MULB>
@@ -227,12 +243,13 @@ __device__ __forceinline__ void dif_pass(float2* s, int m, int lgm, int lgL, con
 #pragma unroll
         for (int q = 0; q < R; ++q) x[q] = s[pad(base + (q << lgst))];
         dif_regs<K>(x);
+        float2 w[R];
+        pass_twiddles<K>(w, tw, r, tshift);
 #pragma unroll
         for (int p = 0; p < R; ++p) {
-            constexpr int dummy = 0; (void)dummy;
             const int mm = rev_bits(p, K);
             float2 v = x[p];
-            if (p > 0) v = cmul(v, __ldg(&tw[(r * mm) << tshift]));
+            if (p > 0) v = cmul(v, w[mm]);
             const int pos = base + (p << lgst);
             if (MULB) v = cmul(v, __ldg(&bhat[pos]));
             s[pad(pos)] = v;
@@ -250,15 +267,13 @@ __device__ __forceinline__ void dit_pass(float2* s, int m, int lgm, int lgL, con
     for (int g = threadIdx.x; g < (m >> K); g += FNT) {
         const int r = g & (st - 1);
         const int base = ((g - r) << K) + r;
-        float2 x[R];
+        float2 x[R], w[R];
+        pass_twiddles<K>(w, tw, r, tshift);
 #pragma unroll
         for (int p = 0; p < R; ++p) {
             const int mm = rev_bits(p, K);
             float2 v = s[pad(base + (p << lgst))];
-            if (p > 0) {
-                const float2 w = __ldg(&tw[(r * mm) << tshift]);
-                v = CONJ ? cmul_conj(v, w) : cmul(v, w);
-            }
+            if (p > 0) v = CONJ ? cmul_conj(v, w[mm]) : cmul(v, w[mm]);
             x[p] = v;
         }
         dit_regs<K, CONJ>(x);
@@ -324,13 +339,20 @@ __global__ void __launch_bounds__(FNT) fft_rows_kernel(RowsArgs a, int n, int m,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
     const float scale = a.inverse ? 1.0f / (float)n : 1.0f;
-    for (int row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+    // LOAD_REAL packs TWO real rows into one complex transform (x = row_a + i row_b) and separates the two
+    // spectra afterwards: A[k] = (X[k] + conj X[n-k]) / 2, B[k] = (X[k] - conj X[n-k]) / 2i.
+    const int nwork = (LOAD == LOAD_REAL) ? (a.nrows + 1) / 2 : a.nrows;
+    for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
+        const int row = (LOAD == LOAD_REAL) ? 2 * item : item;
+        const bool has_b = (LOAD == LOAD_REAL) && (row + 1 < a.nrows);
         // ---- load (+ conj for the inverse, + chirp for Bluestein) ---------------------------------------
         for (int k = threadIdx.x; k < m; k += FNT) {
             float2 v = make_float2(0.f, 0.f);
             if (k < n) {
                 if (LOAD == LOAD_REAL) {
-                    v.x = reinterpret_cast<const float*>(a.in)[(int64_t)row * a.in_pitch + k];
+                    const float* src = reinterpret_cast<const float*>(a.in) + (int64_t)row * a.in_pitch + k;
+                    v.x = src[0];
+                    if (has_b) v.y = src[a.in_pitch];
                 } else if (LOAD == LOAD_C64) {
                     v = reinterpret_cast<const float2*>(a.in)[(int64_t)row * a.in_pitch + k];
                 } else {
@@ -340,7 +362,7 @@ __global__ void __launch_bounds__(FNT) fft_rows_kernel(RowsArgs a, int n, int m,
                     const float keep = 1.0f - (float)a.mask[(int64_t)sr * a.mask_pitch + sc];   // SubtractionFilter(minuend=1)
                     v.x *= keep; v.y *= keep;                                                     // ProductFilter(factor=F_shift)
                 }
-                if (a.inverse) v.y = -v.y;
+                if (LOAD != LOAD_REAL && a.inverse) v.y = -v.y;      // real rows: conj is applied after the split
                 if (BLUE) v = cmul(v, __ldg(&chirp[k]));
             }
             if (BLUE) s[pad(k)] = v;
@@ -357,10 +379,29 @@ __global__ void __launch_bounds__(FNT) fft_rows_kernel(RowsArgs a, int n, int m,
         for (int k = threadIdx.x; k < n; k += FNT) {
             float2 v = s[pad(k)];
             if (BLUE) v = cmul(v, __ldg(&chirp[k]));
-            if (a.inverse) v.y = -v.y;
-            v.x *= scale; v.y *= scale;
-            if (a.store_abs) reinterpret_cast<float*>(a.out)[(int64_t)row * a.out_pitch + k] = hypotf(v.x, v.y);
-            else a.out[(int64_t)row * a.out_pitch + k] = v;
+            if (LOAD == LOAD_REAL) {
+                const int kn = k ? n - k : 0;
+                float2 u = s[pad(kn)];
+                if (BLUE) u = cmul(u, __ldg(&chirp[kn]));
+                float2 fa = make_float2(0.5f * (v.x + u.x), 0.5f * (v.y - u.y));
+                float2 fb = make_float2(0.5f * (v.y + u.y), 0.5f * (u.x - v.x));
+                if (a.inverse) { fa.y = -fa.y; fb.y = -fb.y; }
+                fa.x *= scale; fa.y *= scale; fb.x *= scale; fb.y *= scale;
+                if (a.store_abs) {
+                    float* dst = reinterpret_cast<float*>(a.out) + (int64_t)row * a.out_pitch + k;
+                    dst[0] = hypotf(fa.x, fa.y);
+                    if (has_b) dst[a.out_pitch] = hypotf(fb.x, fb.y);
+                } else {
+                    float2* dst = a.out + (int64_t)row * a.out_pitch + k;
+                    dst[0] = fa;
+                    if (has_b) dst[a.out_pitch] = fb;
+                }
+            } else {
+                if (a.inverse) v.y = -v.y;
+                v.x *= scale; v.y *= scale;
+                if (a.store_abs) reinterpret_cast<float*>(a.out)[(int64_t)row * a.out_pitch + k] = hypotf(v.x, v.y);
+                else a.out[(int64_t)row * a.out_pitch + k] = v;
+            }
         }
         __syncthreads();
     }
@@ -456,7 +497,8 @@ int launch_rows(const Plan1D& p, const RowsArgs& a, int load, cudaStream_t s)
         int per_sm = 1;                                                                                \
         HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FNT, smem));            \
         int grid = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);                                           \
-        if (grid > a.nrows) grid = a.nrows;                                                            \
+        const int nwork = (LOADV == LOAD_REAL) ? (a.nrows + 1) / 2 : a.nrows;                          \
+        if (grid > nwork) grid = nwork;                                                                \
         hd_prof_begin("fft_rows_kernel", s);                                                           \
         kern<<<grid, FNT, smem, s>>>(a, p.n, p.m, p.log2m, plan, p.d_tw, p.d_w, p.d_bhat);              \
     }

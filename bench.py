@@ -241,6 +241,8 @@ def run_gpu(args):
     cells = ny * nx
     value = world * cells / (ms_per_step * 1e-3) / 1e6
 
+    stats = ConditioningChain(fill_stats=True).run_device(*d_in)          # untimed: tile visits of the fill worklist
+    sweeps = [stats.info.get("fill_sweeps")]
     # ---- per-kernel profile of one more step (event pair around every launch) -----------------------------
     lib.hd_profile_enable(1)
     flush.fill_(1)
@@ -300,7 +302,7 @@ def run_gpu(args):
                                  "max 7x7, combine, mean3+round, sink-fill, D8",
                        "tile": [ny, nx], "seed": SEED, "parallelism": f"tile-parallel x{world}, no collective",
                        "l2": "256 MB flush buffer written between timed steps (untimed)",
-                       "fill_sweeps": sweeps[-1] if sweeps else None},
+                       "fill_tile_visits": sweeps[-1] if sweeps else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "hydrodem_b200.pipeline.ConditioningChain.apply(srtm, groves, hsheds) -> final, filled, d8"},

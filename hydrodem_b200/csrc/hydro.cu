@@ -61,13 +61,14 @@ __global__ void __launch_bounds__(256) fill_finish_kernel(const float* __restric
     }
 }
 
+template <int ZSTRIDE = FT>
 __device__ __forceinline__ float relax(const float* ws, const float* zs, int r, int c)
 {
     // ws is the padded (FT+2) x WS_STRIDE array, cell (r, c) of the tile lives at ws[(r+1)*WS_STRIDE + c+1]
     const float* p = ws + (r + 1) * WS_STRIDE + (c + 1);
     float m = fminf(fminf(p[-WS_STRIDE - 1], p[-WS_STRIDE]), fminf(p[-WS_STRIDE + 1], p[-1]));
     m = fminf(m, fminf(fminf(p[1], p[WS_STRIDE - 1]), fminf(p[WS_STRIDE], p[WS_STRIDE + 1])));
-    return fmaxf(zs[r * FT + c], m);            // fminf / fmaxf skip NaN operands
+    return fmaxf(zs[r * ZSTRIDE + c], m);       // fminf / fmaxf skip NaN operands
 }
 
 __global__ void __launch_bounds__(FNT) fill_sweep_kernel(const __grid_constant__ CUtensorMap tm_z,
@@ -144,8 +145,8 @@ __global__ void __launch_bounds__(FNT) fill_sweep_kernel(const __grid_constant__
 //            __threadfence() before the neighbour is published.
 struct FillCtl {
     int head, tail, pending, error;
-    unsigned long long visits, changed_visits;
-    int qcap, pad_[5];
+    unsigned long long visits, changed_visits, iterations;
+    int qcap, pad_[3];
 };
 constexpr int SLOT_EMPTY = -1;
 constexpr int SPIN_LIMIT = 1 << 22;
@@ -201,23 +202,24 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(FNT) fill_async_kernel(const __grid_constant__ CUtensorMap tm_z, float* __restrict__ w,
+constexpr int ZS_STRIDE = FT + 1;         // 65: odd stride, the row-marching groups read z down a column
+
+__global__ void __launch_bounds__(FNT) fill_async_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
                                                          int64_t w_pitch, int64_t ny, int64_t nx, int tiles_x, int tiles_y,
                                                          FillCtl* ctl, int* slots, int* queued)
 {
+    // This kernel does not use TMA: W must be read L2-coherently (ld.global.cg) while other CTAs update it, and z
+    // has to land in a padded (conflict-free) layout that a dense TMA box cannot produce.
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
     __shared__ int s_tile;
     __shared__ unsigned s_edges;
-    float* zs = reinterpret_cast<float*>(smem);                           // [FT][FT]
-    float* wold = reinterpret_cast<float*>(smem + Z_BYTES);               // [(FT+2)][WS_STRIDE] as loaded
+    float* zs = reinterpret_cast<float*>(smem);                           // [FT][ZS_STRIDE]
+    float* wold = zs + FT * ZS_STRIDE;                                    // [(FT+2)][WS_STRIDE] as loaded
     float* ws = wold + (FT + 2) * WS_STRIDE;                              // [(FT+2)][WS_STRIDE] working copy
     const int qcap = ctl->qcap;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    __syncthreads();
     const int group = threadIdx.x >> 6, lane64 = threadIdx.x & 63;
     const float qnan = __int_as_float(0x7fc00000);
-    for (unsigned it = 0;; ++it) {
+    for (;;) {
         // ---- take a ticket and wait for its slot --------------------------------------------------------------------
         if (threadIdx.x == 0) {
             int tile = -1;
@@ -238,9 +240,25 @@ __global__ void __launch_bounds__(FNT) fill_async_kernel(const __grid_constant__
         const int tile = s_tile;
         if (tile < 0) return;
         const int ty0 = (tile / tiles_x) * FT, tx0 = (tile % tiles_x) * FT;
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(&bar, Z_BYTES);
-            tma_load_2d(zs, &tm_z, tx0, ty0, &bar);
+        // z tile (read-only path), zero outside the raster like a TMA box
+        const bool zvec_ok = ((z_pitch & 3) == 0) && ((((uintptr_t)z) & 15) == 0);
+#pragma unroll 2
+        for (int t = threadIdx.x; t < FT * 16; t += FNT) {
+            const int r = t >> 4, k = t & 15;
+            const int64_t y = (int64_t)ty0 + r, x = (int64_t)tx0 + 4 * k;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y < ny) {
+                if (zvec_ok && x + 3 < nx) {
+                    v = __ldg(reinterpret_cast<const float4*>(z + y * z_pitch + x));
+                } else {
+                    if (x < nx) v.x = __ldg(z + y * z_pitch + x);
+                    if (x + 1 < nx) v.y = __ldg(z + y * z_pitch + x + 1);
+                    if (x + 2 < nx) v.z = __ldg(z + y * z_pitch + x + 2);
+                    if (x + 3 < nx) v.w = __ldg(z + y * z_pitch + x + 3);
+                }
+            }
+            float* pz = zs + r * ZS_STRIDE + 4 * k;
+            pz[0] = v.x; pz[1] = v.y; pz[2] = v.z; pz[3] = v.w;
         }
         // W with a one-cell halo straight from L2; outside the raster = NaN (ignored by fminf)
         const bool vec_ok = ((w_pitch & 3) == 0) && ((((uintptr_t)w) & 15) == 0);
@@ -275,9 +293,9 @@ __global__ void __launch_bounds__(FNT) fill_async_kernel(const __grid_constant__
                 pw[c] = v;
             }
         }
-        mbar_wait(&bar, it & 1);
         __syncthreads();
         bool tile_changed = false;
+        int iters = 0;
         for (int iter = 0; iter < 4096; ++iter) {
             bool changed = false;
             for (int step = 0; step < FT; ++step) {
@@ -287,12 +305,14 @@ __global__ void __launch_bounds__(FNT) fill_async_kernel(const __grid_constant__
                 else if (group == 2) { r = lane64; c = step; }
                 else { r = lane64; c = FT - 1 - step; }
                 float* cell = ws + (r + 1) * WS_STRIDE + (c + 1);
-                const float cand = relax(ws, zs, r, c);
+                const float cand = relax<ZS_STRIDE>(ws, zs, r, c);
                 if (cand < *cell) { *cell = cand; changed = true; }
             }
+            ++iters;
             if (!__syncthreads_or(changed)) break;
             tile_changed = true;
         }
+        if (threadIdx.x == 0) atomicAdd(&ctl->iterations, (unsigned long long)iters);
         if (tile_changed) {
             unsigned edges = 0u;
             for (int t = threadIdx.x; t < FT * FT; t += FNT) {
@@ -382,9 +402,7 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     const int qcap = ntiles + 8192;
     int* slots = (int*)((char*)workspace + 256);
     int* queued = slots + qcap;
-    CUtensorMap tm_z;
-    if (int e = hd_make_tmap_2d(&tm_z, z, HD_F32, ny, nx, z_pitch, FT, FT, false)) return e;
-    const size_t smem = Z_BYTES + 2 * (size_t)(FT + 2) * WS_STRIDE * 4;
+    const size_t smem = (size_t)FT * ZS_STRIDE * 4 + 2 * (size_t)(FT + 2) * WS_STRIDE * 4;
     HD_CUDA_OK(cudaFuncSetAttribute(fill_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel, FNT, smem));
@@ -406,20 +424,22 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
         (const float*)z, z_pitch, ny, nx, tiles_x, tiles_y, ctl, slots, queued, (flags & 1) ? (flags & 6) : 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
     hd_prof_begin("fill_async_kernel", s);
-    fill_async_kernel<<<grid, FNT, smem, s>>>(tm_z, (float*)w, w_pitch, ny, nx, tiles_x, tiles_y, ctl, slots, queued);
+    fill_async_kernel<<<grid, FNT, smem, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, tiles_x, tiles_y, ctl,
+                                              slots, queued);
     HD_LAUNCH_CHECK(); hd_count_launch();
     if (finish) {
         hd_prof_begin("fill_finish_kernel", s);
         fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
+    if (!visits_out && !getenv("HD_FILL_TRACE")) return HD_OK;      // fully asynchronous when nobody asks for statistics
     static FillCtl* h_ctl = nullptr;
     if (!h_ctl) HD_CUDA_OK(cudaHostAlloc((void**)&h_ctl, sizeof(FillCtl), cudaHostAllocDefault));
     HD_CUDA_OK(cudaMemcpyAsync(h_ctl, ctl, sizeof(FillCtl), cudaMemcpyDeviceToHost, s));
     HD_CUDA_OK(cudaStreamSynchronize(s));
     if (getenv("HD_FILL_TRACE"))
-        fprintf(stderr, "pdfill async: %llu tile visits (%llu changed) over %d tiles, grid %d\n", h_ctl->visits,
-                h_ctl->changed_visits, ntiles, grid);
+        fprintf(stderr, "pdfill async: %llu tile visits (%llu changed, %llu in-tile iterations) over %d tiles, grid %d\n",
+                h_ctl->visits, h_ctl->changed_visits, h_ctl->iterations, ntiles, grid);
     if (visits_out) *visits_out = (int)h_ctl->visits;
     if (h_ctl->error || h_ctl->pending != 0) return HD_ERR_UNSUPPORTED;    // worklist stalled (should not happen)
     return HD_OK;

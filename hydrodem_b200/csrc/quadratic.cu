@@ -6,9 +6,10 @@
 // with x, y = linspace(-ws/2 + 1, ws/2, ws) (half-pixel asymmetric offsets).  All three sums are separable:
 //     column pass : V1[y][x] = sum_dy w,  Vyy[y][x] = sum_dy y^2 w        (one pass down each tile column)
 //     row pass    : s1 = sum_dx V1,  s3 = sum_dx Vyy,  s2 = sum_dx x^2 V1
-// i.e. 2*ws taps instead of ws^2 per sum.  Accumulation is in double (the reference's s2, s3 are float64 and
-// the final expression cancels two ~1e9 terms), so agreement with the reference is ~1e-7 relative -- inside
-// the 1e-5 tolerance class of this stage.
+// i.e. 2*ws taps instead of ws^2 per sum.  The kernel weights sum to 1, so the sums are taken over (w - ref) with a
+// per-tile reference elevation: float32 partial sums then carry terrain relief, not absolute elevation, and the
+// final expression (evaluated in double) agrees with the reference to ~5e-7 relative -- inside the 1e-5
+// tolerance class of this stage.
 //
 // Groves tail (one GrovesCorrection iteration, fused -- the six elementwise filters never touch HBM):
 //     hi = dem - smooth;  tall = hi > 1.5;  keep = 1 - groves * tall;  out = keep * hi + smooth
@@ -43,26 +44,38 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
     constexpr uint32_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
-    double* v1 = reinterpret_cast<double*>(smem + 2 * STAGE);   // [TH][CW]  sum_dy w
-    double* vyy = v1 + TH * CW;                                  // [TH][CW]  sum_dy y^2 w
+    __shared__ float s_ref;
+    float* v1 = reinterpret_cast<float*>(smem + 2 * STAGE);     // [TH][CW]  sum_dy (w - ref)
+    float* vyy = v1 + TH * CW;                                   // [TH][CW]  sum_dy y^2 (w - ref)
+    float c2f[WS];
+#pragma unroll
+    for (int k = 0; k < WS; ++k) c2f[k] = (float)p.c2[k];        // squared half-integers: exact in float32
 
     const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * sizeof(T)), HX, H}};
     tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const T* tile = reinterpret_cast<const T*>(st);
+        // The kernel sums to 1, so smoothed = ref + K * (w - ref) for any constant ref.  Taking ref from the tile
+        // keeps the float32 partial sums small (terrain relief instead of absolute elevation): ~5e-7 relative.
+        if (threadIdx.x == 0) {
+            const float r = (float)tile[H * IN_W + HX];
+            s_ref = (r - r == 0.f) ? r : 0.f;                    // finite, else 0
+        }
+        __syncthreads();
+        const float ref = s_ref;
         // ---- column pass ----------------------------------------------------------------------------
         for (int item = threadIdx.x; item < CW * (TH / STRIP); item += NT) {
             const int c = item % CW, s = item / CW;
-            double v[STRIP + 2 * H];
+            float v[STRIP + 2 * H];
 #pragma unroll
             for (int r = 0; r < STRIP + 2 * H; ++r)
-                v[r] = (double)(float)tile[(s * STRIP + r) * IN_W + c + XOFF];      // window cast to float32
+                v[r] = (float)tile[(s * STRIP + r) * IN_W + c + XOFF] - ref;          // window cast to float32
 #pragma unroll
             for (int o = 0; o < STRIP; ++o) {
-                double a = 0.0, b = 0.0;
+                float a = 0.f, b = 0.f;
 #pragma unroll
                 for (int r = 0; r < WS; ++r) {
                     a += v[o + r];
-                    b = fma(p.c2[r], v[o + r], b);
+                    b = fmaf(c2f[r], v[o + r], b);
                 }
                 v1[(s * STRIP + o) * CW + c] = a;
                 vyy[(s * STRIP + o) * CW + c] = b;
@@ -76,12 +89,12 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
             const int ro = idx >> 5, c4 = idx & 31;
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
-            double a[WS + 3], b[WS + 3];
-            const double2* pa = reinterpret_cast<const double2*>(v1 + ro * CW + 4 * c4);
-            const double2* pb = reinterpret_cast<const double2*>(vyy + ro * CW + 4 * c4);
+            float a[WS + 3], b[WS + 3];
+            const float2* pa = reinterpret_cast<const float2*>(v1 + ro * CW + 4 * c4);
+            const float2* pb = reinterpret_cast<const float2*>(vyy + ro * CW + 4 * c4);
 #pragma unroll
             for (int k = 0; k < (WS + 3) / 2; ++k) {
-                const double2 qa = pa[k], qb = pb[k];
+                const float2 qa = pa[k], qb = pb[k];
                 a[2 * k] = qa.x; a[2 * k + 1] = qa.y;
                 b[2 * k] = qb.x; b[2 * k + 1] = qb.y;
             }
@@ -92,14 +105,15 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
                 const bool interior = y >= H && y < ny - H && x + j >= H && x + j < nx - H;
                 T smooth = ctr;                                    // smoothed = dem.copy()  (:249)
                 if (interior) {
-                    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                     for (int d = 0; d < WS; ++d) {
                         s1 += a[j + d];
-                        s2 = fma(p.c2[d], a[j + d], s2);
+                        s2 = fmaf(c2f[d], a[j + d], s2);
                         s3 += b[j + d];
                     }
-                    smooth = (T)(((s2 + s3) * p.r1 - s1 * p.r23) / p.den);   // (:255-256), stored in dem's dtype
+                    // (:255-256) on the re-centred sums, in double; stored in dem's dtype
+                    smooth = (T)((double)ref + (((double)s2 + (double)s3) * p.r1 - (double)s1 * p.r23) / p.den);
                 }
                 if (GROVES) {
                     const double g = (x + j < nx) ? (double)groves[y * groves_pitch + x + j] : 0.0;
@@ -122,14 +136,14 @@ int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_p
 {
     constexpr int CW = TW + 2 * H, IN_W = TW + 2 * hd_halo_x(H, sizeof(T)), IN_H = TH + 2 * H;
     constexpr size_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128;
-    constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * sizeof(double);
+    constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * sizeof(float);
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
     auto kern = quadratic_kernel<H, T, OutT, GROVES>;
     HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     hd_prof_begin("quadratic_kernel", stream);
-    kern<<<grid_for(ntiles, 1), NT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, (const uint8_t*)groves, groves_pitch, ny, nx,
+    kern<<<grid_for(ntiles, 2), NT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, (const uint8_t*)groves, groves_pitch, ny, nx,
                                                     p, tiles_x, ntiles);
     HD_LAUNCH_CHECK();
     hd_count_launch();

@@ -47,8 +47,9 @@ class SinkFill(DeviceFilter):
     8-connectivity; frame cells and NaN cells are outlets.  float32 result.
     ``sweeps`` holds the number of global tile sweeps of the last call."""
 
-    def __init__(self, *, max_sweeps=0):
+    def __init__(self, *, max_sweeps=0, want_stats=True):
         self.max_sweeps = max_sweeps
+        self.want_stats = want_stats      # False: no host synchronisation inside the call
         self.sweeps = None
 
     def run_device(self, raster):
@@ -57,10 +58,11 @@ class SinkFill(DeviceFilter):
         out = dev.empty(raster.ny, raster.nx, _lib.F32, np.float32)
         nbytes = lib.hd_pdfill_workspace_bytes(raster.ny, raster.nx)
         work = dev.scratch(nbytes)
-        sweeps = ctypes.c_int(0)
+        sweeps = ctypes.c_int(-1)
         _lib.check(lib.hd_pdfill(src.ptr, src.pitch, out.ptr, out.pitch, src.ny, src.nx, ctypes.c_void_p(work.data_ptr()),
-                                 nbytes, int(self.max_sweeps), ctypes.byref(sweeps), dev.stream_ptr()))
-        self.sweeps = sweeps.value
+                                 nbytes, int(self.max_sweeps), ctypes.byref(sweeps) if self.want_stats else None,
+                                 dev.stream_ptr()))
+        self.sweeps = sweeps.value if self.want_stats else None
         return out
 
 

@@ -57,7 +57,8 @@ class ConditioningChain:
     >>> out.final, out.filled, out.d8
     """
 
-    def __init__(self, *, groves_iterations=3, with_hydrology=True, keep_intermediates=False):
+    def __init__(self, *, groves_iterations=3, with_hydrology=True, keep_intermediates=False, fill_stats=False):
+        self.fill_stats = fill_stats          # True: SinkFill synchronises once to report its tile-visit count
         self.groves_iterations = groves_iterations
         self.with_hydrology = with_hydrology
         self.keep_intermediates = keep_intermediates
@@ -94,7 +95,7 @@ class ConditioningChain:
         final = cf.PostProcessingFinal().run_device(complete)
         out["final"] = final
         if self.with_hydrology:
-            fill = nf.SinkFill()
+            fill = nf.SinkFill(want_stats=self.fill_stats)
             out["filled"] = fill.run_device(final)
             info["fill_sweeps"] = fill.sweeps
             out["d8"] = nf.D8FlowDirection().run_device(out["filled"])

@@ -30,7 +30,9 @@ def test_banded_stencils_match_single_gpu(world):
 
     res = sharding.ThreadComm.run(world, fn)
     np.testing.assert_array_equal(np.concatenate([r[0] for r in res]), want_maj)
-    np.testing.assert_array_equal(np.concatenate([r[1] for r in res]), want_quad)
+    # tolerance-class stage: float32 partial sums are re-centred per tile, and band tiles are not aligned with the
+    # single-GPU tiles -> agreement to rounding, not to the bit
+    np.testing.assert_allclose(np.concatenate([r[1] for r in res]), want_quad, rtol=1e-6)
     np.testing.assert_array_equal(np.concatenate([r[2] for r in res]), want_er)
 
 

@@ -27,7 +27,7 @@
 
 namespace {
 
-constexpr int FNT = 512;                 // threads per FFT CTA
+constexpr int FNT = 256;                 // threads per FFT CTA; two CTAs per SM overlap each other's barriers and global phases
 constexpr int MAX_M = 16384;             // 136 KB of (padded) complex64 in shared memory
 constexpr double PI = 3.14159265358979323846;
 
@@ -332,7 +332,7 @@ struct RowsArgs {
 };
 
 template <int LOAD, bool BLUE>
-__global__ void __launch_bounds__(FNT) fft_rows_kernel(RowsArgs a, int n, int m, int log2m, PassPlan plan,
+__global__ void __launch_bounds__(FNT, 2) fft_rows_kernel(RowsArgs a, int n, int m, int log2m, PassPlan plan,
                                                        const float2* __restrict__ tw, const float2* __restrict__ chirp,
                                                        const float2* __restrict__ bhat)
 {

@@ -272,8 +272,8 @@ def run_gpu(args):
     h2d = sum(host[n].nbytes for n in host)
     d2h = 0
     for k in range(min(2, args.warmup)):
-        r = chain.apply(host["srtm"], host["groves"], host["hsheds"])
-        outs = (r.final, r.filled, r.d8)
+        r = chain.apply_to_host(host["srtm"], host["groves"], host["hsheds"])
+        outs = (r["final"], r["filled"], r["d8"])
         del r, outs                                                        # pinned result buffers go back to the cache
     barrier()
     t_e2e = 0.0
@@ -281,8 +281,8 @@ def run_gpu(args):
         flush.fill_(k & 0xff)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        r = chain.apply(host["srtm"], host["groves"], host["hsheds"])
-        outs = (r.final, r.filled, r.d8)                                   # D2H into pinned buffers, synchronous
+        r = chain.apply_to_host(host["srtm"], host["groves"], host["hsheds"])
+        outs = (r["final"], r["filled"], r["d8"])                          # host arrays (pinned), all copies complete
         torch.cuda.synchronize()
         t_e2e += time.perf_counter() - t0
         d2h = sum(o.nbytes for o in outs)
@@ -305,7 +305,7 @@ def run_gpu(args):
                        "fill_tile_visits": sweeps[-1] if sweeps else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "hydrodem_b200.pipeline.ConditioningChain.apply(srtm, groves, hsheds) -> final, filled, d8"},
+                    "api": "hydrodem_b200.pipeline.ConditioningChain.apply_to_host(srtm, groves, hsheds) -> final, filled, d8 (ndarrays)"},
             "gpu_launches": launches, "launches_per_step": launches / args.steps,
             "roofline": roofline, "kernel_ms": breakdown, "clocks": clocks,
         }

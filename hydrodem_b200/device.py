@@ -178,6 +178,39 @@ def download(raster, out=None):
     return host
 
 
+def upload_async(array, stream):
+    """Pinned host ndarray -> device raster on ``stream`` (a torch.cuda.Stream); no host synchronisation.
+    Returns (raster, event).  The caller keeps ``array`` alive until the event has completed."""
+    if not isinstance(array, np.ndarray):
+        raise NumpyArrayExpectedError(array)
+    require_cuda()
+    host = np.ascontiguousarray(array)
+    dt = hd_dtype_of(host.dtype)
+    ny, nx = host.shape
+    r = empty(ny, nx, dt, array.dtype)
+    es = host.dtype.itemsize
+    _lib.check(_lib.load().hd_memcpy2d_h2d(r.ptr, r.pitch * es, ctypes.c_void_p(host.ctypes.data), nx * es, nx * es, ny,
+                                           ctypes.c_void_p(stream.cuda_stream)))
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    return r, ev
+
+
+def download_async(raster, stream):
+    """Device raster (already in its reference dtype) -> pinned host array on ``stream``; returns (array, event)."""
+    ref = raster.ref_dtype
+    if hd_dtype_of(ref) != raster.dtype:
+        raise DeviceError("download_async needs a raster stored in its reference dtype")
+    host = pinned_empty(raster.shape, ref)
+    es = ref.itemsize
+    _lib.check(_lib.load().hd_memcpy2d_d2h(ctypes.c_void_p(host.ctypes.data), raster.nx * es, raster.ptr, raster.pitch * es,
+                                           raster.nx * es, raster.ny, ctypes.c_void_p(stream.cuda_stream)))
+    raster.buf.record_stream(stream)
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    return host, ev
+
+
 # ---- FFT plans and scratch --------------------------------------------------------------------------
 _FFT_PLANS = {}
 

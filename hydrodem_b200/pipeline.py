@@ -64,20 +64,37 @@ class ConditioningChain:
         self.keep_intermediates = keep_intermediates
 
     # ---- device path --------------------------------------------------------------------------------
-    def run_device(self, srtm, groves_class, hsheds, rivers=None):
+    def run_device(self, srtm, groves_class, hsheds, rivers=None, ready=None, on_ready=None):
+        """``ready``: optional {name: torch.cuda.Event} -- the compute stream waits for an input's upload only where
+        that input is first used.  ``on_ready(name, raster)`` is called as soon as an output raster is enqueued."""
+        import torch
         lib = _lib.load()
         ny, nx = srtm.shape
         out = {}
         info = {}
+        cur = torch.cuda.current_stream()
+
+        def need(name):
+            if ready and ready.get(name) is not None:
+                cur.wait_event(ready[name])
+
+        def emit(name, raster):
+            out[name] = raster
+            if on_ready:
+                on_ready(name, raster)
+
         # SRTM branch
+        need("srtm")
         daf = cf.DetectApplyFourier()
         corrected = daf.run_device(srtm)                                   # F32 storage, ref float64
+        need("groves")
         groves = ef.BinaryClosing(structure=np.ones((3, 3))).run_device(groves_class)   # U8 0/1
         dem = corrected
         gc = cf.GrovesCorrection(groves)
         for _ in range(self.groves_iterations):
             dem = gc.run_device(dem, out_dtype=_lib.F32)
         # HSHEDS branch: LagoonsDetection (custom_filters.py:633-661) with float32 / uint8 intermediates
+        need("hsheds")
         fixed = cf.CorrectNANValues().run_device(hsheds)
         majority = cf.MajorityFilter(window_size=11).run_device(fixed)
         eroded = ef.BinaryErosion(iterations=2).run_device(majority)
@@ -87,18 +104,20 @@ class ConditioningChain:
         tidy = ef.GreyDilation(size=(7, 7)).run_device(prod)                # lagoons_values
         # combine + post-processing, float64 like the reference
         fixed32 = dev.convert(fixed, _lib.F32)
+        if rivers is not None:
+            need("rivers")
         riv = dev.convert(rivers, _lib.F32) if rivers is not None else None
         complete = dev.empty(ny, nx, _lib.F64, np.float64)
         _lib.check(lib.hd_final_terms(dem.ptr, dem.dtype, dem.pitch, tidy.ptr, tidy.pitch, fixed32.ptr, fixed32.pitch,
                                       riv.ptr if riv is not None else None, riv.pitch if riv is not None else 0,
                                       complete.ptr, complete.dtype, complete.pitch, ny, nx, dev.stream_ptr()))
         final = cf.PostProcessingFinal().run_device(complete)
-        out["final"] = final
+        emit("final", final)
         if self.with_hydrology:
             fill = nf.SinkFill(want_stats=self.fill_stats)
-            out["filled"] = fill.run_device(final)
+            emit("filled", fill.run_device(final))
             info["fill_sweeps"] = fill.sweeps
-            out["d8"] = nf.D8FlowDirection().run_device(out["filled"])
+            emit("d8", nf.D8FlowDirection().run_device(out["filled"]))
         if self.keep_intermediates:
             out.update(fourier=corrected, fourier_mask=daf._mask_dev, fabs=daf._fabs_dev, groves=groves, srtm=dem,
                        hsheds_nan_fixed=fixed, majority=majority, lagoons_values=tidy, dem_complete=complete)
@@ -115,5 +134,58 @@ class ConditioningChain:
                 dev.upload(rivers) if rivers is not None else None)
 
     def apply(self, srtm_raw, groves_class_raw, hsheds, rivers=None):
-        """ndarrays in -> ChainResult (``final`` float64, ``filled`` float32, ``d8`` uint8)."""
+        """ndarrays in -> ChainResult (``final`` float64, ``filled`` float32, ``d8`` uint8); results are copied to
+        the host lazily, on first access."""
         return self.run_device(*self.upload_inputs(srtm_raw, groves_class_raw, hsheds, rivers))
+
+    def apply_to_host(self, srtm_raw, groves_class_raw, hsheds, rivers=None):
+        """ndarrays in -> dict of ndarrays (``final``, ``filled``, ``d8``) with the PCIe traffic overlapped with the
+        kernels: inputs go up on a copy stream (the Fourier stage starts as soon as the SRTM raster has landed,
+        HydroSHEDS and groves follow underneath it), and each result starts its way down on a second copy stream
+        the moment its last kernel is enqueued (the final DEM travels while the sink-fill runs).  Pageable inputs
+        are staged through pinned buffers first."""
+        import torch
+        arrays = dict(srtm=srtm_raw, groves=groves_class_raw, hsheds=hsheds)
+        if rivers is not None:
+            arrays["rivers"] = rivers
+        for a in arrays.values():
+            if not isinstance(a, np.ndarray):
+                raise NumpyArrayExpectedError(a)
+        if not (srtm_raw.shape == groves_class_raw.shape == hsheds.shape):
+            raise ValueError("srtm, groves_class and hsheds must have the same shape")
+        dev.require_cuda()
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_streams"):
+            self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        up, down = self._streams
+        up.wait_stream(cur)
+        down.wait_stream(cur)
+        rasters, ready, keep = {}, {}, []
+        for name in ("srtm", "hsheds", "groves", "rivers"):
+            if name not in arrays:
+                continue
+            host = np.ascontiguousarray(arrays[name])
+            if not dev._is_pinned(host):
+                pin = dev.pinned_empty(host.shape, host.dtype)
+                pin[...] = host
+                host = pin
+            keep.append(host)
+            rasters[name], ready[name] = dev.upload_async(host, up)
+            rasters[name].buf.record_stream(cur)
+        pending = {}
+
+        def on_ready(name, raster):
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            down.wait_event(ev)
+            pending[name] = dev.download_async(raster, down)
+
+        self.run_device(rasters["srtm"], rasters["groves"], rasters["hsheds"], rasters.get("rivers"), ready=ready,
+                        on_ready=on_ready)
+        result = {}
+        for name, (host, ev) in pending.items():
+            ev.synchronize()
+            result[name] = host
+        cur.wait_stream(down)
+        del keep
+        return result

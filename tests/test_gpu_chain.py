@@ -51,3 +51,17 @@ def test_chain_with_rivers():
     with np.errstate(all="ignore"):
         want = ochain.conditioning_chain(srtm, groves, hsheds.copy(), rivers=rivers, with_hydrology=False)
     np.testing.assert_allclose(res.dem_complete, want["dem_complete"], rtol=1e-5)
+
+
+def test_apply_to_host_matches_lazy_path():
+    """The overlapped host API returns exactly what the lazy ChainResult path returns."""
+    sc = SynthScene(333, 401, 3)
+    srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()
+    chain = ConditioningChain()
+    a = chain.apply(srtm, groves, hsheds.copy())
+    for _ in range(2):
+        b = chain.apply_to_host(srtm, groves, hsheds.copy())
+        assert b["final"].dtype == np.float64 and b["filled"].dtype == np.float32 and b["d8"].dtype == np.uint8
+        np.testing.assert_array_equal(b["final"], a.final)
+        np.testing.assert_array_equal(b["filled"], a.filled)
+        np.testing.assert_array_equal(b["d8"], a.d8)

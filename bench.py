@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -85,6 +85,10 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark(self):
+        """Drop what was sampled so far (warm-up); keep sampling."""
+        self.first = len(self.lines)
 
     def stop(self):
         if not self.proc:
@@ -96,7 +100,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.lines:
+        for line in self.lines[getattr(self, "first", 0):]:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -216,12 +220,14 @@ def run_gpu(args):
         return chain.run_device(*d_in)
 
     # ---- resident-input timing ------------------------------------------------------------------------
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    if rank == 0:
+        sampler.start()                    # nvidia-smi needs ~0.5 s to start streaming: launch it before the warm-up
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()                     # only samples taken from here on (the timed region) are reported
     lib.hd_reset_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sweeps = []
@@ -325,7 +331,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=TILE, help="tile edge (default 3601 = BASELINE.json configs[1])")

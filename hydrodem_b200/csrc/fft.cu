@@ -332,7 +332,7 @@ struct RowsArgs {
 };
 
 template <int LOAD, bool BLUE>
-__global__ void __launch_bounds__(FNT, 2) fft_rows_kernel(RowsArgs a, int n, int m, int log2m, PassPlan plan,
+__global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int m, int log2m, PassPlan plan,
                                                        const float2* __restrict__ tw, const float2* __restrict__ chirp,
                                                        const float2* __restrict__ bhat)
 {

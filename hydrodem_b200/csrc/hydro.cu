@@ -296,17 +296,30 @@ __global__ void __launch_bounds__(FNT) fill_async_kernel(const float* __restrict
         __syncthreads();
         bool tile_changed = false;
         int iters = 0;
+        // marching geometry of this thread group: f = step along the march, l = step to the neighbouring thread
+        const int f = (group == 0) ? WS_STRIDE : (group == 1) ? -WS_STRIDE : (group == 2) ? 1 : -1;
+        const int l = (group < 2) ? 1 : WS_STRIDE;
+        const int zf = (group == 0) ? ZS_STRIDE : (group == 1) ? -ZS_STRIDE : (group == 2) ? 1 : -1;
+        const int p0 = (group == 0) ? (1 * WS_STRIDE + lane64 + 1) : (group == 1) ? (FT * WS_STRIDE + lane64 + 1)
+                     : (group == 2) ? ((lane64 + 1) * WS_STRIDE + 1) : ((lane64 + 1) * WS_STRIDE + FT);
+        const int z0 = (group == 0) ? lane64 : (group == 1) ? ((FT - 1) * ZS_STRIDE + lane64)
+                     : (group == 2) ? (lane64 * ZS_STRIDE) : (lane64 * ZS_STRIDE + FT - 1);
         for (int iter = 0; iter < 4096; ++iter) {
             bool changed = false;
+            int p = p0, zp = z0;
+            // the row behind (b*), the current row's lateral neighbours (cm, cp) and the row ahead (f*): the row
+            // ahead of step k is the current row of step k+1 and this thread's own result is the next "behind"
+            // centre, so 7 shared-memory reads per cell instead of 10
+            float b0 = ws[p - f], cm = ws[p - l], cp = ws[p + l];
             for (int step = 0; step < FT; ++step) {
-                int r, c;
-                if (group == 0) { r = step; c = lane64; }
-                else if (group == 1) { r = FT - 1 - step; c = lane64; }
-                else if (group == 2) { r = lane64; c = step; }
-                else { r = lane64; c = FT - 1 - step; }
-                float* cell = ws + (r + 1) * WS_STRIDE + (c + 1);
-                const float cand = relax<ZS_STRIDE>(ws, zs, r, c);
-                if (cand < *cell) { *cell = cand; changed = true; }
+                const float bm = ws[p - f - l], bp = ws[p - f + l];
+                const float fm = ws[p + f - l], f0 = ws[p + f], fp = ws[p + f + l];
+                float m = fminf(fminf(fminf(bm, b0), fminf(bp, cm)), fminf(fminf(cp, fm), fminf(f0, fp)));
+                const float cand = fmaxf(zs[zp], m);                       // fminf / fmaxf skip NaN operands
+                float own = ws[p];
+                if (cand < own) { ws[p] = cand; own = cand; changed = true; }   // only ever lowers W
+                b0 = own; cm = fm; cp = fp;
+                p += f; zp += zf;
             }
             ++iters;
             if (!__syncthreads_or(changed)) break;

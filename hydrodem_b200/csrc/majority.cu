@@ -19,6 +19,7 @@
 namespace {
 
 constexpr int STRIP = 8;   // output rows per column-summary work item
+constexpr int MNT = 512;   // threads per CTA: 2 CTAs x 16 warps per SM (the kernel is latency / ALU bound)
 
 struct BM { float c; int n; };
 
@@ -36,7 +37,7 @@ __device__ __forceinline__ void bm_merge(BM& s, float c2, int n2)
 }
 
 template <int H, typename OutT>
-__global__ void __launch_bounds__(NT) majority_kernel(const __grid_constant__ CUtensorMap tm_in, OutT* __restrict__ out,
+__global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ CUtensorMap tm_in, OutT* __restrict__ out,
                                                       int64_t out_pitch, int64_t ny, int64_t nx, int min_count,
                                                       int tiles_x, int ntiles)
 {
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(NT) majority_kernel(const __grid_constant__ CU
     tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const float* tile = reinterpret_cast<const float*>(st);
         // ---- 1. column summaries ---------------------------------------------------------------
-        for (int item = threadIdx.x; item < CW * (TH / STRIP); item += NT) {
+        for (int item = threadIdx.x; item < CW * (TH / STRIP); item += MNT) {
             const int c = item % CW, s = item / CW;
             float v[STRIP + 2 * H];
 #pragma unroll
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(NT) majority_kernel(const __grid_constant__ CU
         __syncthreads();
         // ---- 2. merge + 3. verify -------------------------------------------------------------------
 #pragma unroll 1
-        for (int rep = 0; rep < TH * TW / NT; ++rep) {
-            const int idx = rep * NT + threadIdx.x;
+        for (int rep = 0; rep < TH * TW / MNT; ++rep) {
+            const int idx = rep * MNT + threadIdx.x;
             const int ro = idx / TW, xo = idx % TW;
             const int64_t y = ty0 + ro, x = tx0 + xo;
             if (y >= ny || x >= nx) continue;
@@ -131,7 +132,7 @@ int launch(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
     HD_CUDA_OK(cudaFuncSetAttribute(majority_kernel<H, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     hd_prof_begin("majority_kernel", stream);
-    majority_kernel<H, OutT><<<grid_for(ntiles, 2), NT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, ny, nx, min_count,
+    majority_kernel<H, OutT><<<grid_for(ntiles, 2), MNT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, ny, nx, min_count,
                                                                         tiles_x, ntiles);
     HD_LAUNCH_CHECK();
     hd_count_launch();

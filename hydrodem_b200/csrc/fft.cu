@@ -31,7 +31,15 @@ constexpr int FNT = 256;                 // threads per FFT CTA; two CTAs per SM
 constexpr int MAX_M = 16384;             // 136 KB of (padded) complex64 in shared memory
 constexpr double PI = 3.14159265358979323846;
 
+// Rows longer than one shared-memory transform are split once, Cooley-Tukey style: N = n1 * n2 with a SMALL n1
+// (3, 5, 7 ...) and n2 <= 8192.  For each k1 < n1 one CTA transforms the length-n2 sequence
+//     y_k1[j] = W_N^(j k1) * sum_a x[a n2 + j] W_n1^(a k1)          (n1-point DFT + twiddle, done while loading)
+// and X[k1 + n1 k2] = FFT_n2(y_k1)[k2].  The result is STORED as [k1][k2] (contiguous writes); the transposes
+// that follow every row pass undo this permutation in their index arithmetic, so it costs no extra pass.
 struct Plan1D {
+    int n_total = 0, n1 = 1;             // n_total = n1 * n   (n = length transformed in shared memory)
+    float2* d_w1 = nullptr;              // [n1 * n1]  exp(-2 pi i a b / n1)
+    float2* d_wn = nullptr;              // [n_total]  exp(-2 pi i j / n_total)
     int n = 0, m = 0, log2m = 0;
     bool bluestein = false;
     int npass = 0, k[4] = {0, 0, 0, 0};  // radix-2^k passes (DIF order)
@@ -83,13 +91,40 @@ int upload(float2** dst, const std::vector<float2>& src)
 
 void destroy1d(Plan1D& p)
 {
-    cudaFree(p.d_tw); cudaFree(p.d_w); cudaFree(p.d_bhat);
+    cudaFree(p.d_tw); cudaFree(p.d_w); cudaFree(p.d_bhat); cudaFree(p.d_w1); cudaFree(p.d_wn);
     p = Plan1D{};
 }
 
-int build1d(Plan1D& p, int64_t n)
+constexpr int MAX_N1 = 16;
+constexpr int MAX_INNER = 8192;
+
+int build1d(Plan1D& p, int64_t n_total)
 {
-    if (n < 1) return HD_ERR_ARG;
+    if (n_total < 1) return HD_ERR_ARG;
+    int64_t n = n_total;
+    p.n_total = (int)n_total;
+    p.n1 = 1;
+    const bool total_pow2 = (n_total & (n_total - 1)) == 0;
+    if (n_total > MAX_INNER && !(total_pow2 && n_total <= MAX_M)) {
+        int n1 = 0;
+        for (int f = 2; f <= MAX_N1; ++f)
+            if (n_total % f == 0 && n_total / f <= MAX_INNER) { n1 = f; break; }
+        if (!n1) return HD_ERR_UNSUPPORTED;          // e.g. a prime length above 8192
+        p.n1 = n1;
+        n = n_total / n1;
+        std::vector<float2> w1((size_t)n1 * n1), wn((size_t)n_total);
+        for (int a = 0; a < n1; ++a)
+            for (int b = 0; b < n1; ++b) {
+                const double ang = -2.0 * PI * (double)((a * b) % n1) / (double)n1;
+                w1[(size_t)a * n1 + b] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+            }
+        for (int64_t j = 0; j < n_total; ++j) {
+            const double ang = -2.0 * PI * (double)j / (double)n_total;
+            wn[j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        if (int e = upload(&p.d_w1, w1)) return e;
+        if (int e = upload(&p.d_wn, wn)) return e;
+    }
     const bool pow2 = (n & (n - 1)) == 0;
     int64_t m = 1;
     if (pow2) m = n;
@@ -329,6 +364,10 @@ struct RowsArgs {
     int shift_rows, shift_cols;   // LOAD_MASKED_SHIFTED: source = ((row + shift_rows) % nrows, (col + shift_cols) % n)
     int inverse;             // conj in, conj out, scale 1/n
     int store_abs;           // write |z| as float instead of z
+    int n1;                  // outer factor of a long row (1 = the whole row fits one transform)
+    int n_total;             // n1 * n
+    const float2* w1;        // [n1 * n1]
+    const float2* wn;        // [n_total]
 };
 
 template <int LOAD, bool BLUE>
@@ -338,31 +377,51 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
-    const float scale = a.inverse ? 1.0f / (float)n : 1.0f;
-    // LOAD_REAL packs TWO real rows into one complex transform (x = row_a + i row_b) and separates the two
-    // spectra afterwards: A[k] = (X[k] + conj X[n-k]) / 2, B[k] = (X[k] - conj X[n-k]) / 2i.
-    const int nwork = (LOAD == LOAD_REAL) ? (a.nrows + 1) / 2 : a.nrows;
+    const float scale = a.inverse ? 1.0f / (float)a.n_total : 1.0f;
+    const int n1 = a.n1;
+    // LOAD_REAL with n1 == 1 packs TWO real rows into one complex transform (x = row_a + i row_b) and separates the
+    // two spectra afterwards: A[k] = (X[k] + conj X[n-k]) / 2, B[k] = (X[k] - conj X[n-k]) / 2i.
+    const bool pair = (LOAD == LOAD_REAL) && n1 == 1;
+    const int nwork = pair ? (a.nrows + 1) / 2 : a.nrows * n1;
+    // one element of the (virtual) input row, natural column index `col`
+    auto elem = [&](int row, int col) -> float2 {
+        float2 v = make_float2(0.f, 0.f);
+        if (LOAD == LOAD_REAL) {
+            v.x = reinterpret_cast<const float*>(a.in)[(int64_t)row * a.in_pitch + col];
+        } else if (LOAD == LOAD_C64) {
+            v = reinterpret_cast<const float2*>(a.in)[(int64_t)row * a.in_pitch + col];
+        } else {
+            int sr = row + a.shift_rows; if (sr >= a.nrows) sr -= a.nrows;
+            int sc = col + a.shift_cols; if (sc >= a.n_total) sc -= a.n_total;
+            v = reinterpret_cast<const float2*>(a.in)[(int64_t)sr * a.in_pitch + sc];
+            const float keep = 1.0f - (float)a.mask[(int64_t)sr * a.mask_pitch + sc];   // SubtractionFilter(minuend=1)
+            v.x *= keep; v.y *= keep;                                                     // ProductFilter(factor=F_shift)
+        }
+        if (a.inverse) v.y = -v.y;          // ifft(x) = conj(fft(conj x)) / N
+        return v;
+    };
     for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
-        const int row = (LOAD == LOAD_REAL) ? 2 * item : item;
-        const bool has_b = (LOAD == LOAD_REAL) && (row + 1 < a.nrows);
-        // ---- load (+ conj for the inverse, + chirp for Bluestein) ---------------------------------------
+        const int row = pair ? 2 * item : item / n1;
+        const int k1 = pair ? 0 : item - row * n1;
+        const bool has_b = pair && (row + 1 < a.nrows);
+        // ---- load (+ n1-point DFT and twiddle for long rows, + chirp for Bluestein) --------------------------
         for (int k = threadIdx.x; k < m; k += FNT) {
             float2 v = make_float2(0.f, 0.f);
             if (k < n) {
-                if (LOAD == LOAD_REAL) {
+                if (pair) {
                     const float* src = reinterpret_cast<const float*>(a.in) + (int64_t)row * a.in_pitch + k;
                     v.x = src[0];
-                    if (has_b) v.y = src[a.in_pitch];
-                } else if (LOAD == LOAD_C64) {
-                    v = reinterpret_cast<const float2*>(a.in)[(int64_t)row * a.in_pitch + k];
+                    if (has_b) v.y = src[a.in_pitch];        // real rows: the inverse conj is applied after the split
+                } else if (n1 == 1) {
+                    v = elem(row, k);
                 } else {
-                    int sr = row + a.shift_rows; if (sr >= a.nrows) sr -= a.nrows;
-                    int sc = k + a.shift_cols;   if (sc >= n) sc -= n;
-                    v = reinterpret_cast<const float2*>(a.in)[(int64_t)sr * a.in_pitch + sc];
-                    const float keep = 1.0f - (float)a.mask[(int64_t)sr * a.mask_pitch + sc];   // SubtractionFilter(minuend=1)
-                    v.x *= keep; v.y *= keep;                                                     // ProductFilter(factor=F_shift)
+                    for (int aa = 0; aa < n1; ++aa) {
+                        const float2 x = elem(row, aa * n + k), w = __ldg(&a.w1[aa * n1 + k1]);
+                        v.x = fmaf(x.x, w.x, fmaf(-x.y, w.y, v.x));
+                        v.y = fmaf(x.x, w.y, fmaf(x.y, w.x, v.y));
+                    }
+                    v = cmul(v, __ldg(&a.wn[k * k1]));
                 }
-                if (LOAD != LOAD_REAL && a.inverse) v.y = -v.y;      // real rows: conj is applied after the split
                 if (BLUE) v = cmul(v, __ldg(&chirp[k]));
             }
             if (BLUE) s[pad(k)] = v;
@@ -375,11 +434,12 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
         } else if (m > 1) {
             fft_dit_all<false>(s, m, log2m, plan, tw);
         }
-        // ---- store -------------------------------------------------------------------------------------------
+        // ---- store: X[k1 + n1 * k] goes to position k1 * n + k (see Plan1D) ------------------------------------
+        const int64_t obase = (int64_t)row * a.out_pitch + (int64_t)k1 * n;
         for (int k = threadIdx.x; k < n; k += FNT) {
             float2 v = s[pad(k)];
             if (BLUE) v = cmul(v, __ldg(&chirp[k]));
-            if (LOAD == LOAD_REAL) {
+            if (pair) {
                 const int kn = k ? n - k : 0;
                 float2 u = s[pad(kn)];
                 if (BLUE) u = cmul(u, __ldg(&chirp[kn]));
@@ -388,19 +448,19 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
                 if (a.inverse) { fa.y = -fa.y; fb.y = -fb.y; }
                 fa.x *= scale; fa.y *= scale; fb.x *= scale; fb.y *= scale;
                 if (a.store_abs) {
-                    float* dst = reinterpret_cast<float*>(a.out) + (int64_t)row * a.out_pitch + k;
+                    float* dst = reinterpret_cast<float*>(a.out) + obase + k;
                     dst[0] = hypotf(fa.x, fa.y);
                     if (has_b) dst[a.out_pitch] = hypotf(fb.x, fb.y);
                 } else {
-                    float2* dst = a.out + (int64_t)row * a.out_pitch + k;
+                    float2* dst = a.out + obase + k;
                     dst[0] = fa;
                     if (has_b) dst[a.out_pitch] = fb;
                 }
             } else {
                 if (a.inverse) v.y = -v.y;
                 v.x *= scale; v.y *= scale;
-                if (a.store_abs) reinterpret_cast<float*>(a.out)[(int64_t)row * a.out_pitch + k] = hypotf(v.x, v.y);
-                else a.out[(int64_t)row * a.out_pitch + k] = v;
+                if (a.store_abs) reinterpret_cast<float*>(a.out)[obase + k] = hypotf(v.x, v.y);
+                else a.out[obase + k] = v;
             }
         }
         __syncthreads();
@@ -410,10 +470,13 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
 // ---- tiled transposes ---------------------------------------------------------------------------------------------
 // out[(x + sx) % nx_out_rows ...]: generic "transpose + cyclic shift" of a (rows x cols) array into (cols x rows).
 // Element in[r][c] lands at out[(c + shift_c) % cols][(r + shift_r) % rows].
+// pn1 > 1: the input columns are stored permuted by a long-row pass -- position c holds index c / pn2 + pn1 * (c % pn2)
+__device__ __forceinline__ int unpermute(int c, int pn1, int pn2) { return pn1 > 1 ? c / pn2 + pn1 * (c % pn2) : c; }
+
 template <typename T, bool WITH_ABS>
 __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int64_t in_pitch, T* __restrict__ out,
                                                         int64_t out_pitch, float* __restrict__ out_abs, int64_t abs_pitch,
-                                                        int rows, int cols, int shift_r, int shift_c)
+                                                        int rows, int cols, int shift_r, int shift_c, int pn1, int pn2)
 {
     __shared__ T tile[32][33];
     const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
@@ -431,7 +494,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k, r = r0 + tx;            // out row = c, out col = r
             if (r < rows && c < cols) {
-                int orow = c + shift_c; if (orow >= cols) orow -= cols;
+                int orow = unpermute(c, pn1, pn2) + shift_c; if (orow >= cols) orow -= cols;
                 int ocol = r + shift_r; if (ocol >= rows) ocol -= rows;
                 const T v = tile[tx][ty + 8 * k];
                 if (out) out[(int64_t)orow * out_pitch + ocol] = v;
@@ -447,7 +510,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) transpose_real_kernel(const float* __restrict__ in, int64_t in_pitch,
-                                                             OutT* __restrict__ out, int64_t out_pitch, int rows, int cols)
+                                                             OutT* __restrict__ out, int64_t out_pitch, int rows, int cols,
+                                                             int pn1, int pn2)
 {
     __shared__ float tile[32][33];
     const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
@@ -464,7 +528,7 @@ __global__ void __launch_bounds__(256) transpose_real_kernel(const float* __rest
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k, r = r0 + tx;
-            if (r < rows && c < cols) out[(int64_t)c * out_pitch + r] = (OutT)tile[tx][ty + 8 * k];
+            if (r < rows && c < cols) out[(int64_t)unpermute(c, pn1, pn2) * out_pitch + r] = (OutT)tile[tx][ty + 8 * k];
         }
         __syncthreads();
     }
@@ -485,8 +549,13 @@ __global__ void __launch_bounds__(256) shift_kernel(const T* __restrict__ in, in
 }
 
 // ---- host launch helpers -----------------------------------------------------------------------------------------
-int launch_rows(const Plan1D& p, const RowsArgs& a, int load, cudaStream_t s)
+int launch_rows(const Plan1D& p, const RowsArgs& a_in, int load, cudaStream_t s)
 {
+    RowsArgs a = a_in;
+    a.n1 = p.n1;
+    a.n_total = p.n_total;
+    a.w1 = p.d_w1;
+    a.wn = p.d_wn;
     const size_t smem = (size_t)(p.m + (p.m >> 4) + 1) * sizeof(float2);
     PassPlan plan{p.npass, {p.k[0], p.k[1], p.k[2], p.k[3]}};
     if (a.nrows < 1) return HD_OK;
@@ -497,7 +566,7 @@ int launch_rows(const Plan1D& p, const RowsArgs& a, int load, cudaStream_t s)
         int per_sm = 1;                                                                                \
         HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FNT, smem));            \
         int grid = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);                                           \
-        const int nwork = (LOADV == LOAD_REAL) ? (a.nrows + 1) / 2 : a.nrows;                          \
+        const int nwork = (LOADV == LOAD_REAL && p.n1 == 1) ? (a.nrows + 1) / 2 : a.nrows * p.n1;      \
         if (grid > nwork) grid = nwork;                                                                \
         hd_prof_begin("fft_rows_kernel", s);                                                           \
         kern<<<grid, FNT, smem, s>>>(a, p.n, p.m, p.log2m, plan, p.d_tw, p.d_w, p.d_bhat);              \
@@ -568,14 +637,16 @@ int hd_fft2_forward_shift_abs(void* plan, const void* in, int64_t in_pitch, void
     RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, 0, 0};
     if (int e = launch_rows(p->px, r1, LOAD_REAL, s)) return e;
     hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
+    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0, p->px.n1,
+                                                                          p->px.n);
     HD_LAUNCH_CHECK(); hd_count_launch();
-    RowsArgs r2{At, ny, At, ny, nullptr, 0, nx, 0, 0, 0, 0};
+    RowsArgs r2{At, ny, A, ny, nullptr, 0, nx, 0, 0, 0, 0};              // out of place: long rows read the whole row
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
     // At[x][y] = F[y][x]; transpose back with fftshift folded in: F[y][x] -> Fs[(y + ny/2) % ny][(x + nx/2) % nx]
     hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, true><<<transpose_grid(nx, ny), 256, 0, s>>>(At, ny, (float2*)fshift, fshift_pitch,
-                                                                         (float*)fabs_out, fabs_pitch, nx, ny, nx / 2, ny / 2);
+    transpose_kernel<float2, true><<<transpose_grid(nx, ny), 256, 0, s>>>(A, ny, (float2*)fshift, fshift_pitch,
+                                                                         (float*)fabs_out, fabs_pitch, nx, ny, nx / 2, ny / 2,
+                                                                         p->py.n1, p->py.n);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }
@@ -597,16 +668,19 @@ int hd_fft2_masked_inverse_abs(void* plan, const void* fshift, int64_t fshift_pi
     RowsArgs r1{fshift, fshift_pitch, A, nx, (const uint8_t*)mask, mask_pitch, ny, ny / 2, nx / 2, 1, 0};
     if (int e = launch_rows(p->px, r1, LOAD_MASKED_SHIFTED, s)) return e;
     hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
+    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0, p->px.n1,
+                                                                          p->px.n);
     HD_LAUNCH_CHECK(); hd_count_launch();
     float* absT = (float*)A;                        // [nx][ny] float, reuses A
     RowsArgs r2{At, ny, (float2*)absT, ny, nullptr, 0, nx, 0, 0, 1, 1};
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
     hd_prof_begin("transpose_real_kernel", s);
     if (out_dtype == HD_F32)
-        transpose_real_kernel<float><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (float*)out, out_pitch, nx, ny);
+        transpose_real_kernel<float><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (float*)out, out_pitch, nx, ny,
+                                                                           p->py.n1, p->py.n);
     else
-        transpose_real_kernel<double><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (double*)out, out_pitch, nx, ny);
+        transpose_real_kernel<double><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (double*)out, out_pitch, nx, ny,
+                                                                            p->py.n1, p->py.n);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }
@@ -626,13 +700,14 @@ int hd_fft2_c2c(void* plan, const void* in, int in_dtype, int64_t in_pitch, void
     RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, inverse ? 1 : 0, 0};
     if (int e = launch_rows(p->px, r1, in_dtype == HD_F32 ? LOAD_REAL : LOAD_C64, s)) return e;
     hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0);
+    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0, p->px.n1,
+                                                                          p->px.n);
     HD_LAUNCH_CHECK(); hd_count_launch();
-    RowsArgs r2{At, ny, At, ny, nullptr, 0, nx, 0, 0, inverse ? 1 : 0, 0};
+    RowsArgs r2{At, ny, A, ny, nullptr, 0, nx, 0, 0, inverse ? 1 : 0, 0};
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
     hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, false><<<transpose_grid(nx, ny), 256, 0, s>>>(At, ny, (float2*)out, out_pitch, nullptr, 0, nx, ny,
-                                                                          0, 0);
+    transpose_kernel<float2, false><<<transpose_grid(nx, ny), 256, 0, s>>>(A, ny, (float2*)out, out_pitch, nullptr, 0, nx, ny,
+                                                                          0, 0, p->py.n1, p->py.n);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }

@@ -142,8 +142,10 @@ int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const void* mask_pre
  * out (U8 / F32 / F64, ny x nx) = assembled point-symmetric mask, or 1 - mask when `invert`. */
 int hd_fourier_mask_assemble(const void* q1, int64_t q1_pitch, const void* q2, int64_t q2_pitch, void* out, int out_dtype,
                              int64_t out_pitch, int64_t ny, int64_t nx, int margin, int invert, void* stream);
-/* FFT plans hold the twiddle / chirp tables of one (ny, nx) shape in device memory (allocated here). Row
- * lengths up to 8192 (any factorisation, Bluestein) or 16384 (powers of two); longer -> HD_ERR_UNSUPPORTED. */
+/* FFT plans hold the twiddle / chirp tables of one (ny, nx) shape in device memory (allocated here).  Row
+ * lengths up to 8192 (any factorisation: Bluestein in shared memory) or 16384 (powers of two) are one transform;
+ * longer rows are split once as n = n1 * n2 with n1 <= 16, n2 <= 8192 (36000 = 5 * 7200, 10801 = 7 * 1543);
+ * a length with no such factor (a prime above 8192) -> HD_ERR_UNSUPPORTED. */
 int hd_fft2_plan_create(int64_t ny, int64_t nx, void** plan);
 int hd_fft2_plan_destroy(void* plan);
 int64_t hd_fft2_workspace_bytes(int64_t ny, int64_t nx);

@@ -145,6 +145,32 @@ def test_stripe_removal_bundled_tile():
 
 
 def test_fft_size_limit_fails_loudly():
+    """Rows above 8192 need a small factor (n = n1 * n2, n1 <= 16, n2 <= 8192): a large prime has none."""
     from hydrodem_b200.exceptions import DeviceError
     with pytest.raises(DeviceError):
-        ef.FourierTransform().apply(np.zeros((16, 9000), dtype=np.float32))
+        ef.FourierTransform().apply(np.zeros((16, 10007), dtype=np.float32))
+
+
+@pytest.mark.parametrize("shape", [(40, 9000), (10801, 48), (33, 16384), (18000, 20), (150, 36000)])
+def test_fft_long_rows_vs_scipy(shape):
+    """Rows longer than one shared-memory transform: n = n1 * n2 split (9000 = 2 * 4500, 10801 = 7 * 1543,
+    18000 = 3 * 6000, 36000 = 5 * 7200) and the 16384 power of two."""
+    from scipy import fftpack
+    rng = np.random.default_rng(shape[0])
+    a = (rng.normal(100, 10, shape)).astype(np.float32)
+    f = ef.FourierTransform().apply(a)
+    want = fftpack.fft2(a)
+    spectrum_close(f, want)
+    back = ef.FourierITransform().apply(want)
+    np.testing.assert_allclose(back.real, a, rtol=RTOL)
+
+
+def test_stripe_removal_long_rows():
+    """The fused forward / masked inverse passes on a raster whose rows need the n1 * n2 split."""
+    sc = SynthScene(200, 9000, 17)
+    a = sc.srtm()
+    want, mask, _ = fourier.detect_apply_fourier(a)
+    daf = cf.DetectApplyFourier()
+    got = daf.apply(a)
+    assert int((daf.mask != mask).sum()) == 0
+    np.testing.assert_allclose(got, want, rtol=RTOL)

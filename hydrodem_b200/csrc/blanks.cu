@@ -8,8 +8,8 @@
 // takes np.nanmean of what is left and flags the cell when centre > 4 * mean.
 //
 // Kernel: a 64x64 tile with a 27-cell halo is staged by TMA (zero fill outside the quarter = "not counted"),
-// a float64 integral image of the 118x120 box is built in shared memory with warp scans (rows, then
-// columns), and each output needs 8 integral-image reads: big box minus inner box.  The number of valid
+// a float64 integral image of the 118x120 box is built in shared memory (one serial pass down the columns, one
+// along the rows -- both conflict free), and each output needs 8 integral-image reads: big box minus inner box.  The number of valid
 // cells is analytic (clipped 55x55 minus clipped 5x5).  float64 sums of float32 data are exact to ~1e-16, the
 // reference's float32 pairwise nanmean to ~1e-7: the stage is tolerance class, the mask is expected to be
 // identical (mismatch count reported by the tests).  NaN cells INSIDE the quarter are not skipped (they
@@ -31,16 +31,6 @@ constexpr int IS = IN_W + 1;                        // integral-image row stride
 constexpr uint32_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
 constexpr size_t SMEM = STAGE + (size_t)(IN_H + 1) * IS * sizeof(double);
 
-__device__ __forceinline__ double warp_inclusive_scan(double v, int lane)
-{
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
 __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                         const uint8_t* __restrict__ mask_prev, int64_t prev_pitch,
                                                         uint8_t* __restrict__ mask_out, int64_t mask_pitch,
@@ -50,35 +40,33 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
     double* I = reinterpret_cast<double*>(smem + STAGE);       // [(IN_H + 1)][IS], I[r][c] = sum tile[<r][<c]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * 4), HX, H}};
     for (int t = threadIdx.x; t < IS; t += BNT) I[t] = 0.0;                    // row 0
     for (int t = threadIdx.x; t <= IN_H; t += BNT) I[t * IS] = 0.0;            // column 0
     tile_loop<1, 1>(smem, STAGE, bars, planes, BT, BT, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const float* tile = reinterpret_cast<const float*>(st);
-        // ---- row prefix sums: I[r+1][c+1] = sum_{c' <= c} tile[r][c'] ----------------------------------
-        for (int r = warp; r < IN_H; r += BNT / 32) {
-            double carry = 0.0;
-#pragma unroll
-            for (int j = 0; j < (IN_W + 31) / 32; ++j) {
-                const int c = 32 * j + lane;
-                const double v = (c < IN_W) ? (double)tile[r * IN_W + c] : 0.0;
-                const double s = warp_inclusive_scan(v, lane) + carry;
-                if (c < IN_W) I[(r + 1) * IS + c + 1] = s;
-                carry = __shfl_sync(0xffffffffu, s, 31);
+        // ---- integral image, two serial passes with conflict-free access patterns ---------------------------------
+        // pass 1: one thread per tile COLUMN runs down the rows (lanes = consecutive columns);
+        //         I[r+1][c+1] = sum_{r' <= r} tile[r'][c]
+        if (threadIdx.x < IN_W) {
+            const int c = threadIdx.x;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < IN_H; ++r) {
+                acc += (double)tile[r * IN_W + c];
+                I[(r + 1) * IS + c + 1] = acc;
             }
         }
         __syncthreads();
-        // ---- column prefix sums over the row prefixes -------------------------------------------------------
-        for (int c = warp + 1; c <= IN_W; c += BNT / 32) {
-            double carry = 0.0;
-#pragma unroll
-            for (int j = 0; j < (IN_H + 31) / 32; ++j) {
-                const int r = 32 * j + lane + 1;
-                const double v = (r <= IN_H) ? I[r * IS + c] : 0.0;
-                const double s = warp_inclusive_scan(v, lane) + carry;
-                if (r <= IN_H) I[r * IS + c] = s;
-                carry = __shfl_sync(0xffffffffu, s, 31);
+        // pass 2: one thread per ROW runs along the columns (lanes = consecutive rows; the odd stride IS keeps the
+        //         64-bit accesses on distinct banks)
+        if (threadIdx.x < IN_H) {
+            double* row = I + (threadIdx.x + 1) * IS + 1;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < IN_W; ++c) {
+                acc += row[c];
+                row[c] = acc;
             }
         }
         __syncthreads();

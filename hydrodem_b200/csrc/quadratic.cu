@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
                                                        int tiles_x, int ntiles)
 {
     constexpr int WS = 2 * H + 1;
-    constexpr int CW = TW + 2 * H;
+    constexpr int CWU = TW + 2 * H;                 // window columns touched by a tile
+    constexpr int CW = (CWU + 3) / 4 * 4 + 4;       // row stride of the partial-sum arrays: 16-byte aligned rows, room for
+                                                    // whole float4 reads past the last used column
     constexpr int HX = hd_halo_x(H, sizeof(T));
     constexpr int XOFF = HX - H;
     constexpr int IN_W = TW + 2 * HX;
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
         __syncthreads();
         const float ref = s_ref;
         // ---- column pass ----------------------------------------------------------------------------
-        for (int item = threadIdx.x; item < CW * (TH / STRIP); item += NT) {
-            const int c = item % CW, s = item / CW;
+        for (int item = threadIdx.x; item < CWU * (TH / STRIP); item += NT) {
+            const int c = item % CWU, s = item / CWU;
             float v[STRIP + 2 * H];
 #pragma unroll
             for (int r = 0; r < STRIP + 2 * H; ++r)
@@ -89,14 +91,15 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
             const int ro = idx >> 5, c4 = idx & 31;
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
-            float a[WS + 3], b[WS + 3];
-            const float2* pa = reinterpret_cast<const float2*>(v1 + ro * CW + 4 * c4);
-            const float2* pb = reinterpret_cast<const float2*>(vyy + ro * CW + 4 * c4);
+            constexpr int NQ = (WS + 3 + 3) / 4;        // float4 loads covering the WS + 3 columns of 4 windows
+            float a[4 * NQ], b[4 * NQ];
+            const float4* pa = reinterpret_cast<const float4*>(v1 + ro * CW + 4 * c4);    // lanes 16 B apart: conflict free
+            const float4* pb = reinterpret_cast<const float4*>(vyy + ro * CW + 4 * c4);
 #pragma unroll
-            for (int k = 0; k < (WS + 3) / 2; ++k) {
-                const float2 qa = pa[k], qb = pb[k];
-                a[2 * k] = qa.x; a[2 * k + 1] = qa.y;
-                b[2 * k] = qb.x; b[2 * k + 1] = qb.y;
+            for (int k = 0; k < NQ; ++k) {
+                const float4 qa = pa[k], qb = pb[k];
+                a[4 * k] = qa.x; a[4 * k + 1] = qa.y; a[4 * k + 2] = qa.z; a[4 * k + 3] = qa.w;
+                b[4 * k] = qb.x; b[4 * k + 1] = qb.y; b[4 * k + 2] = qb.z; b[4 * k + 3] = qb.w;
             }
             OutT res[4];
 #pragma unroll
@@ -134,7 +137,7 @@ template <int H, typename T, typename OutT, bool GROVES>
 int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_pitch, const void* groves,
            int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t stream)
 {
-    constexpr int CW = TW + 2 * H, IN_W = TW + 2 * hd_halo_x(H, sizeof(T)), IN_H = TH + 2 * H;
+    constexpr int CW = (TW + 2 * H + 3) / 4 * 4 + 4, IN_W = TW + 2 * hd_halo_x(H, sizeof(T)), IN_H = TH + 2 * H;
     constexpr size_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128;
     constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * sizeof(float);
     CUtensorMap tm;

@@ -37,6 +37,21 @@ __device__ __forceinline__ float nanfix_mean(const float (&v)[8])
     return __fdiv_rn(s, (float)n);                                     // float32 sum / count  (:316)
 }
 
+// Four consecutive tile cells starting at a 16-byte aligned position, as ONE shared-memory access per lane
+// (LDS.128 / 2 x LDS.128): lanes sit 16 (32) bytes apart, so a quarter-warp reads one contiguous 128-byte
+// segment -- conflict free, where four scalar reads at a 4-cell lane stride are 4-way bank conflicts.
+template <typename T> __device__ __forceinline__ void load_quad(const T* p, T (&q)[4]);
+template <> __device__ __forceinline__ void load_quad<float>(const float* p, float (&q)[4])
+{
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+}
+template <> __device__ __forceinline__ void load_quad<double>(const double* p, double (&q)[4])
+{
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+}
+
 template <int MODE, typename T>   // MODE 0 = nanfix, 1 = isolated; T = raster dtype (windows are cast to float32)
 __global__ void __launch_bounds__(NT) fix3_kernel(const __grid_constant__ CUtensorMap tm_in, T* __restrict__ out,
                                                   int64_t out_pitch, int64_t ny, int64_t nx, int in_w, int tiles_x,
@@ -56,11 +71,12 @@ __global__ void __launch_bounds__(NT) fix3_kernel(const __grid_constant__ CUtens
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
             const T* c = tile + (ro + 1) * in_w + 4 * c4 + HX;
-            T v[4];
+            T v[4], own[4];
+            load_quad<T>(c, own);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float ctr = (float)c[j];                 // grid.astype('float32'), sliding_window.py:132
-                T r = c[j];
+                const float ctr = (float)own[j];               // grid.astype('float32'), sliding_window.py:132
+                T r = own[j];
                 const bool interior = y >= 1 && y < ny - 1 && x + j >= 1 && x + j < nx - 1;
                 // iter_over_ones gate: int(v) == 1  (sliding_window.py:192)
                 const bool gate = MODE == 0 ? (ctr < 0.f) : (ctr >= 1.f && ctr < 2.f);
@@ -118,7 +134,16 @@ __global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUten
             const int ro = idx >> 5, c4 = idx & 31;
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
-            const T* c = tile + ro * in_w + 4 * c4 + HX - 1;  // top-left of the first window
+            const T* c = tile + ro * in_w + 4 * c4 + HX;      // first of the 4 centre columns, top window row
+            T win[3][6];                                      // 3 window rows x (4 centres + left and right neighbour)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                T q[4];
+                load_quad<T>(c + dy * in_w, q);
+                win[dy][0] = c[dy * in_w - 1];
+                win[dy][1] = q[0]; win[dy][2] = q[1]; win[dy][3] = q[2]; win[dy][4] = q[3];
+                win[dy][5] = c[dy * in_w + 4];
+            }
             T v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -128,7 +153,7 @@ __global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUten
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
                         const double w = p.w[dy * 3 + dx];
-                        if (w != 0.0) acc = __dadd_rn(acc, __dmul_rn((double)c[dy * in_w + dx + j], w));
+                        if (w != 0.0) acc = __dadd_rn(acc, __dmul_rn((double)win[dy][j + dx], w));
                     }
                 v[j] = div_round<T>((T)acc, p.divisor, p.do_round);
             }

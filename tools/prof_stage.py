@@ -26,5 +26,22 @@ elif stage == "majority":
     r = dev.upload(sc.hsheds())
     for _ in range(3):
         cf.MajorityFilter(window_size=11).run_device(r)
+elif stage == "stencils":
+    from hydrodem_b200.filters import extension_filters as ef
+    from hydrodem_b200 import _lib
+    srtm = dev.upload(sc.srtm()); hs = dev.upload(sc.hsheds())
+    maj = cf.MajorityFilter(window_size=11).run_device(hs)
+    dem64 = dev.convert(srtm, _lib.F64)
+    for _ in range(2):
+        cf.ExpandFilter(window_size=13).run_device(maj)
+        ef.BinaryErosion(iterations=2).run_device(maj)
+        ef.GreyDilation(size=(7, 7)).run_device(maj)
+        cf.PostProcessingFinal().run_device(dem64)
+        cf.PostProcessingFinal().run_device(srtm)
+        nf.D8FlowDirection().run_device(srtm)
+        nf.MedianFilter(window_size=3).run_device(srtm)
+        cf.CorrectNANValues().run_device(hs)
+        cf.QuadraticFilter(window_size=15).run_device(srtm)
+        cf.DetectBlanksFourier().run_device(srtm.sub(0, 1790, 0, 1790))
 torch.cuda.synchronize()
 print("done", stage)

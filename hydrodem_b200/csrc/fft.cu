@@ -476,8 +476,13 @@ __device__ __forceinline__ int unpermute(int c, int pn1, int pn2) { return pn1 >
 template <typename T, bool WITH_ABS>
 __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int64_t in_pitch, T* __restrict__ out,
                                                         int64_t out_pitch, float* __restrict__ out_abs, int64_t abs_pitch,
-                                                        int rows, int cols, int shift_r, int shift_c, int pn1, int pn2)
+                                                        int rows, int cols, int shift_r, int shift_c, int pn1, int pn2,
+                                                        int keep_max = -1, int mirror_rows = 0)
 {
+    // keep_max >= 0: only input columns whose (unpermuted) index is <= keep_max are written (half spectrum of a real
+    //                transform).
+    // mirror_rows > 0: the input holds rows 0 .. rows-1 of a Hermitian spectrum whose full height is mirror_rows
+    //                (X[mirror_rows - r][cols - c] = conj X[r][c]); the missing rows are written from their mirror.
     __shared__ T tile[32][33];
     const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
     const int ntiles = tiles_c * tiles_r;
@@ -494,13 +499,30 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k, r = r0 + tx;            // out row = c, out col = r
             if (r < rows && c < cols) {
-                int orow = unpermute(c, pn1, pn2) + shift_c; if (orow >= cols) orow -= cols;
-                int ocol = r + shift_r; if (ocol >= rows) ocol -= rows;
+                const int kc = unpermute(c, pn1, pn2);
+                if (keep_max >= 0 && kc > keep_max) continue;
+                const int full_rows = mirror_rows > 0 ? mirror_rows : rows;     // extent of the output's column axis
+                int orow = kc + shift_c; if (orow >= cols) orow -= cols;
+                int ocol = r + shift_r; if (ocol >= full_rows) ocol -= full_rows;
                 const T v = tile[tx][ty + 8 * k];
                 if (out) out[(int64_t)orow * out_pitch + ocol] = v;
+                float mag = 0.f;
                 if (WITH_ABS) {
                     const float2 z = *reinterpret_cast<const float2*>(&v);
-                    out_abs[(int64_t)orow * abs_pitch + ocol] = hypotf(z.x, z.y);      // np.abs(complex64) -> float32
+                    mag = hypotf(z.x, z.y);                                     // np.abs(complex64) -> float32
+                    out_abs[(int64_t)orow * abs_pitch + ocol] = mag;
+                }
+                if (mirror_rows > 0 && r > 0 && 2 * r != mirror_rows) {
+                    // conjugate partner: (r, kc) -> (mirror_rows - r, (cols - kc) % cols)
+                    int mrow = (kc ? cols - kc : 0) + shift_c; if (mrow >= cols) mrow -= cols;
+                    int mcol = (mirror_rows - r) + shift_r; if (mcol >= full_rows) mcol -= full_rows;
+                    if (out) {
+                        T cv = v;
+                        float2* pz = reinterpret_cast<float2*>(&cv);
+                        pz->y = -pz->y;
+                        out[(int64_t)mrow * out_pitch + mcol] = cv;
+                    }
+                    if (WITH_ABS) out_abs[(int64_t)mrow * abs_pitch + mcol] = mag;
                 }
             }
         }
@@ -634,19 +656,23 @@ int hd_fft2_forward_shift_abs(void* plan, const void* in, int64_t in_pitch, void
     cudaStream_t s = (cudaStream_t)stream;
     float2* A = (float2*)workspace;                 // [ny][nx]
     float2* At = A + (int64_t)ny * nx;              // [nx][ny]
+    // The input is real, so the spectrum is Hermitian: only columns kx = 0 .. nx/2 go through the second (column) pass,
+    // the other half is written from its conjugate mirror by the last transpose.
+    const int nh = nx / 2 + 1;
     RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, 0, 0};
     if (int e = launch_rows(p->px, r1, LOAD_REAL, s)) return e;
     hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0, p->px.n1,
-                                                                          p->px.n);
+                                                                          p->px.n, nh - 1, 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
-    RowsArgs r2{At, ny, A, ny, nullptr, 0, nx, 0, 0, 0, 0};              // out of place: long rows read the whole row
+    RowsArgs r2{At, ny, A, ny, nullptr, 0, nh, 0, 0, 0, 0};              // out of place: long rows read the whole row
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
-    // At[x][y] = F[y][x]; transpose back with fftshift folded in: F[y][x] -> Fs[(y + ny/2) % ny][(x + nx/2) % nx]
+    // A[kx][ky] = F[ky][kx] for kx < nh; transpose back with fftshift folded in:
+    // F[ky][kx] -> Fs[(ky + ny/2) % ny][(kx + nx/2) % nx], plus the mirrored half
     hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, true><<<transpose_grid(nx, ny), 256, 0, s>>>(A, ny, (float2*)fshift, fshift_pitch,
-                                                                         (float*)fabs_out, fabs_pitch, nx, ny, nx / 2, ny / 2,
-                                                                         p->py.n1, p->py.n);
+    transpose_kernel<float2, true><<<transpose_grid(nh, ny), 256, 0, s>>>(A, ny, (float2*)fshift, fshift_pitch,
+                                                                         (float*)fabs_out, fabs_pitch, nh, ny, nx / 2, ny / 2,
+                                                                         p->py.n1, p->py.n, -1, nx);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }

@@ -36,14 +36,18 @@ struct FillCounters { int changed_tiles; int pad[3]; };
 
 __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
                                                         int64_t w_pitch, int64_t ny, int64_t nx, int top_is_halo = 0,
-                                                        int bottom_is_halo = 0)
+                                                        int bottom_is_halo = 0, int* __restrict__ tile_has_nodata = nullptr,
+                                                        int tiles_x = 0)
 {
     const int64_t total = ny * nx;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t y = t / nx, x = t - y * nx;
         const float v = z[y * z_pitch + x];
         float r = __int_as_float(0x7f800000);                                    // +inf inside
-        if (v != v) r = __int_as_float(0xff800000);                              // nodata: outlet at -inf
+        if (v != v) {
+            r = __int_as_float(0xff800000);                                      // nodata: outlet at -inf
+            if (tile_has_nodata) tile_has_nodata[(y / FT) * tiles_x + (x / FT)] = 1;   // benign race: every writer stores 1
+        }
         else if ((y == 0 && !top_is_halo) || x == 0 || (y == ny - 1 && !bottom_is_halo) || x == nx - 1)
             r = v;                                                               // frame: W = z (a band's halo rows are not frame)
         w[y * w_pitch + x] = r;
@@ -170,35 +174,22 @@ __device__ __forceinline__ void fill_poke(FillCtl* ctl, int* slots, int qcap, in
     }
 }
 
-__global__ void __launch_bounds__(256) fill_seed_kernel(const float* __restrict__ z, int64_t z_pitch, int64_t ny, int64_t nx,
-                                                        int tiles_x, int tiles_y, FillCtl* ctl, int* __restrict__ slots,
-                                                        int* __restrict__ queued, int edge_rows_only)
+__global__ void __launch_bounds__(256) fill_seed_kernel(int tiles_x, int tiles_y, int64_t ny, FillCtl* ctl,
+                                                        int* __restrict__ slots, int* __restrict__ queued, int edge_rows_only)
 {
-    // one warp per tile: a tile is seeded when it touches the raster frame or contains a NaN cell (an outlet)
-    const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
+    // A tile is seeded when it touches the raster frame or contains a nodata cell (fill_init_kernel left a 1 in
+    // queued[tile] for those).  Continuing a banded fill, only tiles that hold a refreshed halo row, or read it as
+    // their own halo (the row next to it), can change.
     const int ntiles = tiles_x * tiles_y;
-    for (int tile = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tile < ntiles; tile += gridDim.x * warps_per_block) {
+    for (int tile = blockIdx.x * blockDim.x + threadIdx.x; tile < ntiles; tile += gridDim.x * blockDim.x) {
         const int ty = tile / tiles_x, tx = tile % tiles_x;
-        const int64_t y0 = (int64_t)ty * FT, x0 = (int64_t)tx * FT;
-        const int64_t y1 = y0 + FT < ny ? y0 + FT : ny, x1 = x0 + FT < nx ? x0 + FT : nx;
-        bool seed = (ty == 0 || tx == 0 || ty == tiles_y - 1 || tx == tiles_x - 1);
-        if (edge_rows_only) {
-            // continuing a banded fill: only tiles that hold a refreshed halo row, or read it as their own halo
-            // (the row next to it), can change
+        bool seed;
+        if (edge_rows_only)
             seed = ((edge_rows_only & 2) && ty == 0) || ((edge_rows_only & 4) && ty >= (int)((ny - 2) / FT));
-        } else if (!seed) {
-            bool nan = false;
-            for (int64_t y = y0; y < y1 && !nan; ++y)
-                for (int64_t x = x0 + lane; x < x1; x += 32) {
-                    const float v = z[y * z_pitch + x];
-                    nan |= (v != v);
-                }
-            seed = __any_sync(0xffffffffu, nan);
-        }
-        if (seed && lane == 0) {
-            queued[tile] = T_QUEUED;
-            fill_push(ctl, slots, ctl->qcap, tile);
-        }
+        else
+            seed = ty == 0 || tx == 0 || ty == tiles_y - 1 || tx == tiles_x - 1 || queued[tile] != 0;
+        queued[tile] = seed ? T_QUEUED : T_IDLE;
+        if (seed) fill_push(ctl, slots, ctl->qcap, tile);
     }
 }
 
@@ -429,12 +420,12 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     if (!(flags & 1)) {
         hd_prof_begin("fill_init_kernel", s);
         fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, flags & 2,
-                                                             flags & 4);
+                                                             flags & 4, queued, tiles_x);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
     hd_prof_begin("fill_seed_kernel", s);
-    fill_seed_kernel<<<hd_cdiv(ntiles, 8) < 1184 ? hd_cdiv(ntiles, 8) : 1184, 256, 0, s>>>(
-        (const float*)z, z_pitch, ny, nx, tiles_x, tiles_y, ctl, slots, queued, (flags & 1) ? (flags & 6) : 0);
+    fill_seed_kernel<<<hd_cdiv(ntiles, 256) < 1184 ? hd_cdiv(ntiles, 256) : 1184, 256, 0, s>>>(
+        tiles_x, tiles_y, ny, ctl, slots, queued, (flags & 1) ? (flags & 6) : 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
     hd_prof_begin("fill_async_kernel", s);
     fill_async_kernel<<<grid, FNT, smem, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, tiles_x, tiles_y, ctl,

@@ -19,6 +19,7 @@
 // the (1 - mask) product are folded into the load / store index arithmetic of those passes, so the shifted
 // spectrum is never materialised separately.
 #include <cmath>
+#include <cstdlib>
 #include <complex>
 #include <utility>
 #include <vector>
@@ -351,7 +352,7 @@ __device__ __forceinline__ void fft_dit_all(float2* s, int m, int lgm, const Pas
     }
 }
 
-enum LoadMode { LOAD_REAL = 0, LOAD_C64 = 1, LOAD_MASKED_SHIFTED = 2 };
+enum LoadMode { LOAD_REAL = 0, LOAD_C64 = 1, LOAD_MASKED_SHIFTED = 2, LOAD_C64_HPAIR = 3 };
 
 struct RowsArgs {
     const void* in;          // f32 (LOAD_REAL) or float2 rows
@@ -364,6 +365,7 @@ struct RowsArgs {
     int shift_rows, shift_cols;   // LOAD_MASKED_SHIFTED: source = ((row + shift_rows) % nrows, (col + shift_cols) % n)
     int inverse;             // conj in, conj out, scale 1/n
     int store_abs;           // write |z| as float instead of z
+    int rows_total;          // LOAD_MASKED_SHIFTED: modulus of the row shift when only the first nrows rows are transformed
     int n1;                  // outer factor of a long row (1 = the whole row fits one transform)
     int n_total;             // n1 * n
     const float2* w1;        // [n1 * n1]
@@ -382,7 +384,8 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
     // LOAD_REAL with n1 == 1 packs TWO real rows into one complex transform (x = row_a + i row_b) and separates the
     // two spectra afterwards: A[k] = (X[k] + conj X[n-k]) / 2, B[k] = (X[k] - conj X[n-k]) / 2i.
     const bool pair = (LOAD == LOAD_REAL) && n1 == 1;
-    const int nwork = pair ? (a.nrows + 1) / 2 : a.nrows * n1;
+    const bool hpair = (LOAD == LOAD_C64_HPAIR);
+    const int nwork = pair ? (a.nrows + 1) / 2 : (hpair ? (a.nrows + 1) / 2 : a.nrows) * n1;
     // one element of the (virtual) input row, natural column index `col`
     auto elem = [&](int row, int col) -> float2 {
         float2 v = make_float2(0.f, 0.f);
@@ -390,8 +393,15 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
             v.x = reinterpret_cast<const float*>(a.in)[(int64_t)row * a.in_pitch + col];
         } else if (LOAD == LOAD_C64) {
             v = reinterpret_cast<const float2*>(a.in)[(int64_t)row * a.in_pitch + col];
+        } else if (LOAD == LOAD_C64_HPAIR) {
+            // two Hermitian rows (real inverse transforms) packed as a + i b: the real / imaginary parts of the result
+            // are the two real output rows
+            const float2* src = reinterpret_cast<const float2*>(a.in) + (int64_t)row * a.in_pitch + col;
+            const float2 ra = src[0];
+            v = ra;
+            if (row + 1 < a.nrows) { const float2 rb = src[a.in_pitch]; v.x = ra.x - rb.y; v.y = ra.y + rb.x; }
         } else {
-            int sr = row + a.shift_rows; if (sr >= a.nrows) sr -= a.nrows;
+            int sr = row + a.shift_rows; if (sr >= a.rows_total) sr -= a.rows_total;
             int sc = col + a.shift_cols; if (sc >= a.n_total) sc -= a.n_total;
             v = reinterpret_cast<const float2*>(a.in)[(int64_t)sr * a.in_pitch + sc];
             const float keep = 1.0f - (float)a.mask[(int64_t)sr * a.mask_pitch + sc];   // SubtractionFilter(minuend=1)
@@ -401,8 +411,8 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
         return v;
     };
     for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
-        const int row = pair ? 2 * item : item / n1;
-        const int k1 = pair ? 0 : item - row * n1;
+        const int row = pair ? 2 * item : (hpair ? 2 * (item / n1) : item / n1);
+        const int k1 = pair ? 0 : item % n1;
         const bool has_b = pair && (row + 1 < a.nrows);
         // ---- load (+ n1-point DFT and twiddle for long rows, + chirp for Bluestein) --------------------------
         for (int k = threadIdx.x; k < m; k += FNT) {
@@ -456,6 +466,11 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
                     dst[0] = fa;
                     if (has_b) dst[a.out_pitch] = fb;
                 }
+            } else if (hpair) {
+                if (a.inverse) v.y = -v.y;
+                float* dst = reinterpret_cast<float*>(a.out) + obase + k;           // store_abs layout (float rows)
+                dst[0] = fabsf(v.x * scale);
+                if (row + 1 < a.nrows) dst[a.out_pitch] = fabsf(v.y * scale);
             } else {
                 if (a.inverse) v.y = -v.y;
                 v.x *= scale; v.y *= scale;
@@ -477,12 +492,13 @@ template <typename T, bool WITH_ABS>
 __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int64_t in_pitch, T* __restrict__ out,
                                                         int64_t out_pitch, float* __restrict__ out_abs, int64_t abs_pitch,
                                                         int rows, int cols, int shift_r, int shift_c, int pn1, int pn2,
-                                                        int keep_max = -1, int mirror_rows = 0)
+                                                        int keep_max = -1, int mirror_rows = 0, int mirror_cols = 1)
 {
     // keep_max >= 0: only input columns whose (unpermuted) index is <= keep_max are written (half spectrum of a real
     //                transform).
     // mirror_rows > 0: the input holds rows 0 .. rows-1 of a Hermitian spectrum whose full height is mirror_rows
     //                (X[mirror_rows - r][cols - c] = conj X[r][c]); the missing rows are written from their mirror.
+    //                mirror_cols = 0: the symmetry is X[mirror_rows - r][c] = conj X[r][c] (second axis already real-space).
     __shared__ T tile[32][33];
     const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
     const int ntiles = tiles_c * tiles_r;
@@ -514,7 +530,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
                 }
                 if (mirror_rows > 0 && r > 0 && 2 * r != mirror_rows) {
                     // conjugate partner: (r, kc) -> (mirror_rows - r, (cols - kc) % cols)
-                    int mrow = (kc ? cols - kc : 0) + shift_c; if (mrow >= cols) mrow -= cols;
+                    int mrow = (mirror_cols ? (kc ? cols - kc : 0) : kc) + shift_c; if (mrow >= cols) mrow -= cols;
                     int mcol = (mirror_rows - r) + shift_r; if (mcol >= full_rows) mcol -= full_rows;
                     if (out) {
                         T cv = v;
@@ -575,6 +591,7 @@ int launch_rows(const Plan1D& p, const RowsArgs& a_in, int load, cudaStream_t s)
 {
     RowsArgs a = a_in;
     a.n1 = p.n1;
+    if (a.rows_total == 0) a.rows_total = a.nrows;
     a.n_total = p.n_total;
     a.w1 = p.d_w1;
     a.wn = p.d_wn;
@@ -588,7 +605,8 @@ int launch_rows(const Plan1D& p, const RowsArgs& a_in, int load, cudaStream_t s)
         int per_sm = 1;                                                                                \
         HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FNT, smem));            \
         int grid = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);                                           \
-        const int nwork = (LOADV == LOAD_REAL && p.n1 == 1) ? (a.nrows + 1) / 2 : a.nrows * p.n1;      \
+        const int nwork = (LOADV == LOAD_REAL && p.n1 == 1) ? (a.nrows + 1) / 2                       \
+                          : (LOADV == LOAD_C64_HPAIR ? (a.nrows + 1) / 2 : a.nrows) * p.n1;            \
         if (grid > nwork) grid = nwork;                                                                \
         hd_prof_begin("fft_rows_kernel", s);                                                           \
         kern<<<grid, FNT, smem, s>>>(a, p.n, p.m, p.log2m, plan, p.d_tw, p.d_w, p.d_bhat);              \
@@ -596,10 +614,12 @@ int launch_rows(const Plan1D& p, const RowsArgs& a_in, int load, cudaStream_t s)
     if (p.bluestein) {
         if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, true)
         else if (load == LOAD_C64) HD_ROWS(LOAD_C64, true)
+        else if (load == LOAD_C64_HPAIR) HD_ROWS(LOAD_C64_HPAIR, true)
         else HD_ROWS(LOAD_MASKED_SHIFTED, true)
     } else {
         if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, false)
         else if (load == LOAD_C64) HD_ROWS(LOAD_C64, false)
+        else if (load == LOAD_C64_HPAIR) HD_ROWS(LOAD_C64_HPAIR, false)
         else HD_ROWS(LOAD_MASKED_SHIFTED, false)
     }
 #undef HD_ROWS
@@ -691,15 +711,32 @@ int hd_fft2_masked_inverse_abs(void* plan, const void* fshift, int64_t fshift_pi
     float2* A = (float2*)workspace;
     float2* At = A + (int64_t)ny * nx;
     // ifftshift: unshifted index k reads shifted index (k + n/2) % n
-    RowsArgs r1{fshift, fshift_pitch, A, nx, (const uint8_t*)mask, mask_pitch, ny, ny / 2, nx / 2, 1, 0};
-    if (int e = launch_rows(p->px, r1, LOAD_MASKED_SHIFTED, s)) return e;
-    hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0, p->px.n1,
-                                                                          p->px.n);
-    HD_LAUNCH_CHECK(); hd_count_launch();
     float* absT = (float*)A;                        // [nx][ny] float, reuses A
-    RowsArgs r2{At, ny, (float2*)absT, ny, nullptr, 0, nx, 0, 0, 1, 1};
-    if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
+    if ((ny & 1) && (nx & 1) && !getenv("HD_FFT_NO_HERMITIAN")) {
+        // Odd x odd: the assembled mask is exactly point-symmetric about DC (custom_filters.py:1042-1049) and F is
+        // the spectrum of a real raster, so (1 - mask) * F is Hermitian and the inverse is real.  Only rows
+        // ky = 0 .. ny/2 go through the first pass; the other rows of the intermediate are conjugates
+        // (c[ny - ky][x] = conj c[ky][x]) written by the transpose; the second pass packs two real-output columns
+        // into one complex transform.  abs() of a real number: |re| (the reference's imaginary part is rounding noise).
+        const int nyh = ny / 2 + 1;
+        RowsArgs r1{fshift, fshift_pitch, A, nx, (const uint8_t*)mask, mask_pitch, nyh, ny / 2, nx / 2, 1, 0, ny};
+        if (int e = launch_rows(p->px, r1, LOAD_MASKED_SHIFTED, s)) return e;
+        hd_prof_begin("transpose_kernel", s);
+        transpose_kernel<float2, false><<<transpose_grid(nyh, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, nyh, nx, 0, 0,
+                                                                               p->px.n1, p->px.n, -1, ny, 0);
+        HD_LAUNCH_CHECK(); hd_count_launch();
+        RowsArgs r2{At, ny, (float2*)absT, ny, nullptr, 0, nx, 0, 0, 1, 1};
+        if (int e = launch_rows(p->py, r2, LOAD_C64_HPAIR, s)) return e;
+    } else {
+        RowsArgs r1{fshift, fshift_pitch, A, nx, (const uint8_t*)mask, mask_pitch, ny, ny / 2, nx / 2, 1, 0};
+        if (int e = launch_rows(p->px, r1, LOAD_MASKED_SHIFTED, s)) return e;
+        hd_prof_begin("transpose_kernel", s);
+        transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0,
+                                                                              p->px.n1, p->px.n);
+        HD_LAUNCH_CHECK(); hd_count_launch();
+        RowsArgs r2{At, ny, (float2*)absT, ny, nullptr, 0, nx, 0, 0, 1, 1};
+        if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
+    }
     hd_prof_begin("transpose_real_kernel", s);
     if (out_dtype == HD_F32)
         transpose_real_kernel<float><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (float*)out, out_pitch, nx, ny,

@@ -36,15 +36,18 @@ METRIC = "Mcells/s, full conditioning chain"
 UNIT = "Mcells/s"
 
 # Algorithmic HBM bytes per cell and per launch of each kernel in this workload.
-# fft_rows: the four row passes of one forward + one masked inverse 2-D transform are
-#   real->c64 (4+8), c64->c64 (8+8), masked c64->c64 (8+1+8), c64->|.| (8+4)  = 57 B/cell over 4 launches.
+# fft_rows: the four row passes of one forward + one masked inverse 2-D transform of an odd x odd raster are
+#   real->c64 (4+8), c64->c64 on the Hermitian half (8+8)/2, masked c64->c64 on half the rows (8+1+8)/2,
+#   c64 pairs->|re| (8+4)  = 40.5 B/cell over 4 launches.
+# fill_async: 12 B per cell of every tile VISIT (z + W read, W written) -- bench.py multiplies by the visit count.
 ALGO_BYTES_PER_CELL = {
-    "fft_rows_kernel": 57.0 / 4.0,
+    "fft_rows_kernel": 40.5 / 4.0,
     "transpose_kernel": 16.0,
     "transpose_real_kernel": 8.0,
     "quadratic_kernel": 9.0,
     "majority_kernel": 8.0,
     "fill_sweep_kernel": 12.0,
+    "fill_async_kernel": 12.0,
     "hollow_kernel": 9.0 * 0.25,        # runs on a spectrum quarter
     "expand_kernel": 2.0,
     "morph_kernel": 2.0,
@@ -266,9 +269,13 @@ def run_gpu(args):
     peak, peak_kind = measured_peak()
     top_avg_ms = kernels[top]["total_ms"] / kernels[top]["launches"]
     algo_bytes = ALGO_BYTES_PER_CELL.get(top, 8.0) * cells
+    if top == "fill_async_kernel" and sweeps and sweeps[-1]:
+        algo_bytes = 12.0 * 64 * 64 * sweeps[-1]                          # bytes actually staged: tile visits x 64 x 64 cells
     achieved = algo_bytes / (top_avg_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
+    ncu_traffic = {"fft_rows_kernel": 125.0e6}
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "launches_per_step": kernels[top]["launches"],
+                "frac": achieved / peak, "traffic": ncu_traffic.get(top), "launches_per_step": kernels[top]["launches"],
                 "avg_launch_ms": top_avg_ms, "share_of_step": kernels[top]["total_ms"] / prof_total,
                 "algorithmic_bytes_per_launch": algo_bytes}
     breakdown = {n: round(k["total_ms"], 4) for n, k in sorted(kernels.items(), key=lambda kv: -kv[1]["total_ms"])}

@@ -325,12 +325,21 @@ __global__ void __launch_bounds__(FNT) fill_async_kernel(const float* __restrict
                 const float nv = ws[(r + 1) * WS_STRIDE + c + 1], ov = wold[(r + 1) * WS_STRIDE + c + 1];
                 if (y < ny && x < nx && nv != ov && !(nv != nv)) {
                     w[y * w_pitch + x] = nv;
-                    // which neighbours read this cell as halo: bit = (dy+1)*3 + (dx+1)
-                    const int dy0 = (r == 0) ? -1 : 0, dy1 = (r == FT - 1 || y == ny - 1) ? 1 : 0;
-                    const int dx0 = (c == 0) ? -1 : 0, dx1 = (c == FT - 1 || x == nx - 1) ? 1 : 0;
-                    for (int dy = dy0; dy <= dy1; ++dy)
-                        for (int dx = dx0; dx <= dx1; ++dx)
-                            if (dy | dx) edges |= 1u << ((dy + 1) * 3 + (dx + 1));
+                    // Poke a neighbouring tile only if this cell can still lower one of ITS cells: the halo ring holds the
+                    // neighbour's edge values as loaded (they only ever decrease), so nv >= that value means
+                    // max(z, nv) cannot undercut it.  This drops the useless "poke back" to the tile the level came from.
+                    // bit = (dy+1)*3 + (dx+1)
+                    if (r == 0 || r == FT - 1 || c == 0 || c == FT - 1) {
+#pragma unroll
+                        for (int a = -1; a <= 1; ++a)
+#pragma unroll
+                            for (int b = -1; b <= 1; ++b) {
+                                const int rr = r + a, cc = c + b;
+                                const int dy = rr < 0 ? -1 : (rr >= FT ? 1 : 0), dx = cc < 0 ? -1 : (cc >= FT ? 1 : 0);
+                                if ((dy | dx) && nv < wold[(rr + 1) * WS_STRIDE + cc + 1])     // NaN (outside the raster): false
+                                    edges |= 1u << ((dy + 1) * 3 + (dx + 1));
+                            }
+                    }
                 }
             }
             if (edges) atomicOr(&s_edges, edges);

@@ -219,8 +219,10 @@ def run_gpu(args):
     d_in = chain.upload_inputs(host["srtm"], host["groves"], host["hsheds"])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
 
+    captured = None if args.no_graph else chain.capture(*d_in)             # one CUDA graph per pass
+
     def step_resident():
-        return chain.run_device(*d_in)
+        return captured.replay() if captured is not None else chain.run_device(*d_in)
 
     # ---- resident-input timing ------------------------------------------------------------------------
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
@@ -242,7 +244,7 @@ def run_gpu(args):
         ev[k][1].record()
         sweeps.append(res.info.get("fill_sweeps"))
     barrier()
-    launches = int(lib.hd_launch_count())
+    launches = int(lib.hd_launch_count()) if captured is None else captured.launches * args.steps
     clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     total_ms = max_over_ranks(total_ms)
@@ -255,7 +257,7 @@ def run_gpu(args):
     # ---- per-kernel profile of one more step (event pair around every launch) -----------------------------
     lib.hd_profile_enable(1)
     flush.fill_(1)
-    step_resident()
+    chain.run_device(*d_in)                                               # eager launches: an event pair around each
     import ctypes
     cbuf = ctypes.create_string_buffer(1 << 16)
     lib.hd_profile_report(cbuf, 1 << 16)
@@ -315,6 +317,7 @@ def run_gpu(args):
                                  "max 7x7, combine, mean3+round, sink-fill, D8",
                        "tile": [ny, nx], "seed": SEED, "parallelism": f"tile-parallel x{world}, no collective",
                        "l2": "256 MB flush buffer written between timed steps (untimed)",
+                       "launch": "eager launches" if captured is None else f"one CUDA graph of {captured.launches} kernels per step",
                        "fill_tile_visits": sweeps[-1] if sweeps else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -345,6 +348,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1024, help="edge of the CPU baseline sample tile")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,6 +39,7 @@ SIGNATURES = {
     "hd_elementwise": (_i, [_i, _p, _i, _i64, _p, _i, _i64, _d, _p, _i, _i64, _i64, _i64, _p]),
     "hd_final_terms": (_i, [_p, _i, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _p]),
     "hd_expand": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i64, _i, _p]),
+    "hd_expand_select": (_i, [_p, _i, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _p]),
     "hd_majority": (_i, [_p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),
     "hd_nanfix": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),
     "hd_isolated": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),
@@ -61,7 +62,7 @@ SIGNATURES = {
     "hd_d8": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_binary_morph": (_i, [_p, _i, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _p]),
     "hd_max_filter": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
-    "hd_convolve3": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, ctypes.POINTER(_d), _d, _i, _p]),
+    "hd_convolve3": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, ctypes.POINTER(_d), _d, _i, _p, _i64, _p]),
 }
 
 _lib = None

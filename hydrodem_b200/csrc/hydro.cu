@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(int tiles_x, int tiles_y
     }
 }
 
+__global__ void fill_ctl_init_kernel(FillCtl* ctl, int qcap) { ctl->qcap = qcap; }
+
 constexpr int ZS_STRIDE = FT + 1;         // 65: odd stride, the row-marching groups read z down a column
 
 __global__ void __launch_bounds__(FNT) fill_async_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
@@ -421,11 +423,12 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel, FNT, smem));
     int grid = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);       // every CTA must be co-resident: they wait on each other
     if (grid > ntiles) grid = ntiles;
-    FillCtl h{};
-    h.qcap = qcap;
+    // (no host-to-device copy of a stack object here: the whole call must be capturable in a CUDA graph)
+    HD_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(FillCtl), s));
     HD_CUDA_OK(cudaMemsetAsync(slots, 0xff, (size_t)qcap * sizeof(int), s));        // SLOT_EMPTY = -1
     HD_CUDA_OK(cudaMemsetAsync(queued, 0, (size_t)ntiles * sizeof(int), s));
-    HD_CUDA_OK(cudaMemcpyAsync(ctl, &h, sizeof h, cudaMemcpyHostToDevice, s));
+    fill_ctl_init_kernel<<<1, 1, 0, s>>>(ctl, qcap);
+    HD_LAUNCH_CHECK();
     if (!(flags & 1)) {
         hd_prof_begin("fill_init_kernel", s);
         fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, flags & 2,

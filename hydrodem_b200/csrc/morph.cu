@@ -43,7 +43,8 @@ __device__ __forceinline__ uint64_t win64(const uint32_t* row, int k)
 // write a TH x TW tile of 0/1 results held as bit words res[ro * 4 + k]
 template <typename OutT>
 __device__ __forceinline__ void write_bits(const uint32_t* res, OutT* out, int64_t out_pitch, int ty0, int tx0,
-                                           int64_t ny, int64_t nx, int border)
+                                           int64_t ny, int64_t nx, int border, const float* __restrict__ select = nullptr,
+                                           int64_t sel_pitch = 0)
 {
 #pragma unroll
     for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
@@ -56,6 +57,12 @@ __device__ __forceinline__ void write_bits(const uint32_t* res, OutT* out, int64
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = (yin && (x + j >= border) && (x + j < nx - border) && ((nib >> j) & 1u)) ? 1.f : 0.f;
+        if (select) {
+            // fused ProductFilter(factor = select): factor * expanded  (TidyingLagoons, custom_filters.py:589-590, :607)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j < nx) v[j] = __fmul_rn(select[y * sel_pitch + x + j], v[j]);
+        }
         store4<OutT>(out, out_pitch, y, x, nx, v);
     }
 }
@@ -64,7 +71,8 @@ __device__ __forceinline__ void write_bits(const uint32_t* res, OutT* out, int64
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(NT) expand_kernel(const __grid_constant__ CUtensorMap tm_in, OutT* __restrict__ out,
                                                     int64_t out_pitch, int64_t ny, int64_t nx, int h, int in_w, int in_h,
-                                                    int tiles_x, int ntiles)
+                                                    int tiles_x, int ntiles, const float* __restrict__ select,
+                                                    int64_t sel_pitch)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(NT) expand_kernel(const __grid_constant__ CUte
             res[threadIdx.x] = acc;
         }
         __syncthreads();
-        write_bits<OutT>(res, out, out_pitch, ty0, tx0, ny, nx, h);
+        write_bits<OutT>(res, out, out_pitch, ty0, tx0, ny, nx, h, select, sel_pitch);
     });
 }
 
@@ -230,14 +238,14 @@ __global__ void __launch_bounds__(NT) maxfilter_kernel(const __grid_constant__ C
 
 template <typename InT, typename OutT>
 int launch_expand(const CUtensorMap& tm, void* out, int64_t out_pitch, int64_t ny, int64_t nx, int h, int in_w, int in_h,
-                  cudaStream_t stream)
+                  cudaStream_t stream, const float* select = nullptr, int64_t sel_pitch = 0)
 {
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
     const size_t smem = 2 * STAGE_BYTES;
     HD_CUDA_OK(cudaFuncSetAttribute(expand_kernel<InT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hd_prof_begin("expand_kernel", stream);
     expand_kernel<InT, OutT><<<grid_for(ntiles, 3), NT, smem, stream>>>(tm, (OutT*)out, out_pitch, ny, nx, h, in_w, in_h,
-                                                                        tiles_x, ntiles);
+                                                                        tiles_x, ntiles, select, sel_pitch);
     HD_LAUNCH_CHECK();
     hd_count_launch();
     return HD_OK;
@@ -269,6 +277,25 @@ extern "C" int hd_expand(const void* in, int in_dtype, int64_t in_pitch, void* o
     HD_EXPAND_CASE(uint8_t, HD_U8, double, HD_F64)
 #undef HD_EXPAND_CASE
     return HD_ERR_UNSUPPORTED;
+}
+
+extern "C" int hd_expand_select(const void* in, int in_dtype, int64_t in_pitch, const void* select, int64_t sel_pitch,
+                                void* out, int64_t out_pitch, int64_t ny, int64_t nx, int ws, void* stream)
+{
+    if (!in || !out || !select) return HD_ERR_NULL;
+    if (int e = check_window(ny, nx, ws)) return e;
+    const int h = ws / 2;
+    if (h < 1 || h > MAX_HALO - 1) return HD_ERR_UNSUPPORTED;
+    if (in_pitch < nx || out_pitch < nx || sel_pitch < nx) return HD_ERR_ARG;
+    if (in_dtype != HD_U8 && in_dtype != HD_F32) return HD_ERR_UNSUPPORTED;
+    const int in_w = TW + 2 * hd_halo_x(h, (int)hd_dtype_size(in_dtype)), in_h = TH + 2 * h;
+    if (in_w > MAX_IN_W) return HD_ERR_UNSUPPORTED;
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, in, in_dtype, ny, nx, in_pitch, in_w, in_h, false)) return e;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (in_dtype == HD_U8)
+        return launch_expand<uint8_t, float>(tm, out, out_pitch, ny, nx, h, in_w, in_h, s, (const float*)select, sel_pitch);
+    return launch_expand<float, float>(tm, out, out_pitch, ny, nx, h, in_w, in_h, s, (const float*)select, sel_pitch);
 }
 
 extern "C" int hd_binary_morph(const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny,

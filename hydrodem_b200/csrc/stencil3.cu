@@ -117,8 +117,8 @@ template <> __device__ __forceinline__ double div_round<double>(double v, double
 
 template <typename T>
 __global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUtensorMap tm_in, T* __restrict__ out,
-                                                   int64_t out_pitch, int64_t ny, int64_t nx, Conv3Params p, int in_w,
-                                                   int tiles_x, int ntiles)
+                                                   int64_t out_pitch, float* __restrict__ out32, int64_t out32_pitch,
+                                                   int64_t ny, int64_t nx, Conv3Params p, int in_w, int tiles_x, int ntiles)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUten
                 v[j] = div_round<T>((T)acc, p.divisor, p.do_round);
             }
             store4v<T>(out, out_pitch, y, x, nx, v);
+            if (out32) {                                      // optional float32 copy of the result (feeds the sink-fill)
+                const float f[4] = {(float)v[0], (float)v[1], (float)v[2], (float)v[3]};
+                store4<float>(out32, out32_pitch, y, x, nx, f);
+            }
         }
     });
 }
@@ -207,10 +211,11 @@ extern "C" int hd_isolated(const void* in, int64_t in_pitch, void* out, int64_t 
 }
 
 extern "C" int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny,
-                            int64_t nx, const double* weights, double divisor, int do_round, void* stream)
+                            int64_t nx, const double* weights, double divisor, int do_round, void* out32,
+                            int64_t out32_pitch, void* stream)
 {
     if (!in || !out || !weights) return HD_ERR_NULL;
-    if (ny < 1 || nx < 1 || in_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
+    if (ny < 1 || nx < 1 || in_pitch < nx || out_pitch < nx || (out32 && out32_pitch < nx)) return HD_ERR_ARG;
     if (dtype != HD_F32 && dtype != HD_F64) return HD_ERR_UNSUPPORTED;
     Conv3Params p;
     for (int k = 0; k < 9; ++k) p.w[k] = weights[k];
@@ -225,12 +230,13 @@ extern "C" int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == HD_F32) {
         hd_prof_begin("conv3_kernel", s);
-        conv3_kernel<float><<<grid_for(ntiles, 4), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, p, in_w, tiles_x, ntiles);
+        conv3_kernel<float><<<grid_for(ntiles, 4), NT, smem, s>>>(tm, (float*)out, out_pitch, (float*)out32, out32_pitch, ny, nx, p,
+                                                                 in_w, tiles_x, ntiles);
     } else {
         HD_CUDA_OK(cudaFuncSetAttribute(conv3_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hd_prof_begin("conv3_kernel", s);
-        conv3_kernel<double><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, p, in_w, tiles_x,
-                                                                  ntiles);
+        conv3_kernel<double><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (double*)out, out_pitch, (float*)out32, out32_pitch, ny, nx,
+                                                                  p, in_w, tiles_x, ntiles);
     }
     HD_LAUNCH_CHECK();
     hd_count_launch();

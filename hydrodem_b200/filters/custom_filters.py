@@ -296,10 +296,10 @@ class PostProcessingFinal(ComposedFilter):
         super().__init__()
         self.filters = [Convolve(), Around()]
 
-    def run_device(self, raster):
+    def run_device(self, raster, copy32=None):
         conv, rnd = self.filters
         if type(conv) is Convolve and type(rnd) is Around:
-            return conv.run_device(raster, do_round=True)
+            return conv.run_device(raster, do_round=True, copy32=copy32)
         return super().run_device(raster)
 
     def apply(self, image_to_filter):

@@ -61,7 +61,8 @@ class Convolve(DeviceFilter):
     def __init__(self, weights=np.ones((3, 3))):
         self.weights = weights
 
-    def run_device(self, raster, do_round=False):
+    def run_device(self, raster, do_round=False, copy32=None):
+        """``copy32``: optional F32 device raster that receives a float32 copy of the result (chain plumbing)."""
         w = np.asarray(self.weights, dtype=np.float64)
         if w.shape != (3, 3):
             raise DeviceError(f"Convolve: only 3x3 weights are implemented on the device (got {w.shape})")
@@ -72,7 +73,8 @@ class Convolve(DeviceFilter):
         corr = np.ascontiguousarray(w[::-1, ::-1])                    # convolution = correlation with the flipped kernel
         cw = (ctypes.c_double * 9)(*corr.ravel())
         _lib.check(_lib.load().hd_convolve3(src.ptr, src.pitch, out.ptr, out.pitch, src.dtype, src.ny, src.nx, cw,
-                                            float(w.size), int(do_round), dev.stream_ptr()))
+                                            float(w.size), int(do_round), copy32.ptr if copy32 is not None else None,
+                                            copy32.pitch if copy32 is not None else 0, dev.stream_ptr()))
         return out
 
 

@@ -50,6 +50,18 @@ class ChainResult:
         raise AttributeError(name)
 
 
+class CapturedChain:
+    """A CUDA graph of one pass of the chain (see ConditioningChain.capture)."""
+
+    def __init__(self, graph, result, launches):
+        self.graph, self.result, self.launches = graph, result, launches
+
+    def replay(self):
+        self.graph.replay()
+        self.result._host.clear()
+        return self.result
+
+
 class ConditioningChain:
     """Run the whole chain on the GPU.
 
@@ -98,9 +110,9 @@ class ConditioningChain:
         fixed = cf.CorrectNANValues().run_device(hsheds)
         majority = cf.MajorityFilter(window_size=11).run_device(fixed)
         eroded = ef.BinaryErosion(iterations=2).run_device(majority)
-        grown = cf.ExpandFilter(window_size=7).run_device(eroded)
-        prod = dev.empty(ny, nx, _lib.F32, np.float64)                      # majority * expand: exact in float32
-        dev.elementwise(_lib.OP_MUL, grown, majority, 0.0, prod)
+        prod = dev.empty(ny, nx, _lib.F32, np.float64)                      # majority * expand(7): one fused kernel
+        _lib.check(lib.hd_expand_select(eroded.ptr, eroded.dtype, eroded.pitch, majority.ptr, majority.pitch, prod.ptr,
+                                        prod.pitch, ny, nx, 7, dev.stream_ptr()))
         tidy = ef.GreyDilation(size=(7, 7)).run_device(prod)                # lagoons_values
         # combine + post-processing, float64 like the reference
         fixed32 = dev.convert(fixed, _lib.F32)
@@ -111,17 +123,35 @@ class ConditioningChain:
         _lib.check(lib.hd_final_terms(dem.ptr, dem.dtype, dem.pitch, tidy.ptr, tidy.pitch, fixed32.ptr, fixed32.pitch,
                                       riv.ptr if riv is not None else None, riv.pitch if riv is not None else 0,
                                       complete.ptr, complete.dtype, complete.pitch, ny, nx, dev.stream_ptr()))
-        final = cf.PostProcessingFinal().run_device(complete)
+        final32 = dev.empty(ny, nx, _lib.F32, np.float32) if self.with_hydrology else None   # integer metres: exact
+        final = cf.PostProcessingFinal().run_device(complete, copy32=final32)
         emit("final", final)
         if self.with_hydrology:
             fill = nf.SinkFill(want_stats=self.fill_stats)
-            emit("filled", fill.run_device(final))
+            emit("filled", fill.run_device(final32))
             info["fill_sweeps"] = fill.sweeps
             emit("d8", nf.D8FlowDirection().run_device(out["filled"]))
         if self.keep_intermediates:
             out.update(fourier=corrected, fourier_mask=daf._mask_dev, fabs=daf._fabs_dev, groves=groves, srtm=dem,
                        hsheds_nan_fixed=fixed, majority=majority, lagoons_values=tidy, dem_complete=complete)
         return ChainResult(out, info)
+
+    def capture(self, srtm, groves_class, hsheds, rivers=None):
+        """Capture the whole device-resident chain for these (static) input rasters in ONE CUDA graph.
+
+        The chain is ~40 short kernel launches; issued one by one from Python the host cannot keep a B200 busy
+        (~4 ms of interpreter + ctypes time per pass).  A captured graph replays them with a single launch.  Returns a
+        CapturedChain: ``replay()`` re-runs the chain on whatever the input rasters hold at that moment and returns
+        the same ChainResult (its rasters are the graph's static output buffers)."""
+        import torch
+        self.run_device(srtm, groves_class, hsheds, rivers)          # warm-up: FFT plans, function attributes
+        torch.cuda.synchronize()
+        lib = _lib.load()
+        n0 = lib.hd_launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            result = self.run_device(srtm, groves_class, hsheds, rivers)
+        return CapturedChain(graph, result, int(lib.hd_launch_count() - n0))
 
     # ---- host API ---------------------------------------------------------------------------------
     def upload_inputs(self, srtm_raw, groves_class_raw, hsheds, rivers=None):

@@ -100,6 +100,10 @@ int hd_final_terms(const void* srtm, int srtm_dtype, int64_t srtm_pitch, const v
  * (1 where any non-NaN cell of the corner-less ws*ws window is > 0, else 0; ws/2 border = 0). */
 int hd_expand(const void* in, int in_dtype, int64_t in_pitch, void* out, int out_dtype, int64_t out_pitch, int64_t ny,
               int64_t nx, int ws, void* stream);
+/* ExpandFilter(ws) followed by ProductFilter(factor = select): the two middle stages of TidyingLagoons
+ * (custom_filters.py:587-610) in one kernel.  in: F32 or U8; select, out: F32; out = select * expanded. */
+int hd_expand_select(const void* in, int in_dtype, int64_t in_pitch, const void* select, int64_t sel_pitch, void* out,
+                     int64_t out_pitch, int64_t ny, int64_t nx, int ws, void* stream);
 /* MajorityFilter.apply, custom_filters.py:48-73.  in: F32; out: F32 / F64, every cell written (mode of the
  * corner-less window if its count >= min_count, else 0; border 0).  min_count = floor((ws*ws-1)*0.7)+1. */
 int hd_majority(const void* in, int64_t in_pitch, void* out, int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx,
@@ -182,9 +186,9 @@ int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_t out_pitch
  * custom_filters.py:1124-1125.  3x3 correlation with `weights` (9 doubles, row-major, already reversed for
  * a convolution), mode='reflect', double accumulator in row-major order (scipy NI_Correlate), result cast
  * to the raster dtype, divided by `divisor` in that dtype, then rounded half-to-even if do_round.
- * dtype: F32 or F64 (in and out alike). */
+ * dtype: F32 or F64 (in and out alike).  out32 (may be NULL): an additional F32 copy of the result. */
 int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
-                 const double* weights, double divisor, int do_round, void* stream);
+                 const double* weights, double divisor, int do_round, void* out32, int64_t out32_pitch, void* stream);
 
 /* ---- NEW hydrology stages (not in the reference) ----------------------------------- */
 /* Sink-fill: Planchon-Darboux fixed point with eps = 0, 8-connectivity; frame cells and NaN cells are outlets.

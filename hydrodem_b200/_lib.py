@@ -36,6 +36,7 @@ SIGNATURES = {
     "hd_memcpy2d_h2d": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_memcpy2d_d2h": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_stream_synchronize": (_i, [_p]),
+    "hd_host_widen_f32_f64": (_i, [_p, _p, _i64, _i]),
     "hd_elementwise": (_i, [_i, _p, _i, _i64, _p, _i, _i64, _d, _p, _i, _i64, _i64, _i64, _p]),
     "hd_final_terms": (_i, [_p, _i, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _p]),
     "hd_expand": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i64, _i, _p]),

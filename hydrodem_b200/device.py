@@ -196,7 +196,20 @@ def upload_async(array, stream):
     return r, ev
 
 
-def download_async(raster, stream):
+def upload_into(raster, array, stream):
+    """Pinned host ndarray -> an existing device raster of the same shape / dtype, on ``stream``; returns the event."""
+    if array.shape != raster.shape or hd_dtype_of(array.dtype) != raster.dtype:
+        raise DeviceError("upload_into: shape / dtype mismatch")
+    es = array.dtype.itemsize
+    ny, nx = array.shape
+    _lib.check(_lib.load().hd_memcpy2d_h2d(raster.ptr, raster.pitch * es, ctypes.c_void_p(array.ctypes.data), nx * es,
+                                           nx * es, ny, ctypes.c_void_p(stream.cuda_stream)))
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    return ev
+
+
+def download_async(raster, stream, record=True):
     """Device raster (already in its reference dtype) -> pinned host array on ``stream``; returns (array, event)."""
     ref = raster.ref_dtype
     if hd_dtype_of(ref) != raster.dtype:
@@ -205,7 +218,8 @@ def download_async(raster, stream):
     es = ref.itemsize
     _lib.check(_lib.load().hd_memcpy2d_d2h(ctypes.c_void_p(host.ctypes.data), raster.nx * es, raster.ptr, raster.pitch * es,
                                            raster.nx * es, raster.ny, ctypes.c_void_p(stream.cuda_stream)))
-    raster.buf.record_stream(stream)
+    if record:
+        raster.buf.record_stream(stream)
     ev = torch.cuda.Event()
     ev.record(stream)
     return host, ev

@@ -69,6 +69,10 @@ int hd_memcpy2d_h2d(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t
 int hd_memcpy2d_d2h(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
                     int64_t rows, void* stream);
 int hd_stream_synchronize(void* stream);
+/* HOST helper: dst[i] = (double)src[i] on nthreads host threads.  The final DEM (float64 in the reference,
+ * hydro_dem_process.py:149) holds integer metres, exact in float32: the host API moves it over PCIe as float32 and
+ * widens it here. */
+int hd_host_widen_f32_f64(double* dst, const float* src, int64_t n, int nthreads);
 
 /* ---- elementwise filters (filters/simple_filters.py, extension_filters.py:12-130) -------------- */
 typedef enum {

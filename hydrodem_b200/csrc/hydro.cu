@@ -151,6 +151,7 @@ struct FillCtl {
     int head, tail, pending, error;
     unsigned long long visits, changed_visits, iterations;
     int qcap, pad_[3];
+    unsigned long long cycles[6];     // per-phase SM cycles of thread 0, summed over visits (HD_FILL_TRACE)
 };
 constexpr int SLOT_EMPTY = -1;
 constexpr int SPIN_LIMIT = 1 << 22;
@@ -195,26 +196,97 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(int tiles_x, int tiles_y
 
 __global__ void fill_ctl_init_kernel(FillCtl* ctl, int qcap) { ctl->qcap = qcap; }
 
-constexpr int ZS_STRIDE = FT + 1;         // 65: odd stride, the row-marching groups read z down a column
+// three-input min (FMNMX3 on sm_100); like fminf it returns the non-NaN operand(s)
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 
-__global__ void __launch_bounds__(FNT) fill_async_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
+// One marching sweep of a 64-thread group through the tile: F = shared-memory step along the march, L = step to the
+// neighbouring thread's line.  Per cell: three reads for the row ahead (which then serve as the next step's current
+// row), the thread's own result carried in a register, the two diagonal cells behind fetched from the neighbouring
+// lanes by shuffle (they were updated one step ago: a level runs diagonally through the tile in a single sweep).
+// At the two ends of a warp the diagonal cell comes from the value read two steps earlier instead (a halo cell, or
+// the other warp's line: at worst that information arrives one iteration later).  All offsets are immediates.
+// One relaxation of every cell of the tile, no dependency chain: warp w takes tile rows 8w..8w+7, a lane two columns,
+// sliding a three-row window down its strip.
+__device__ __forceinline__ bool fill_check(float* __restrict__ ws, const float* __restrict__ zs, int warp, int lane32)
+{
+    bool changed = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float* wp = ws + (8 * warp) * WS_STRIDE + lane32 + 32 * h + 1;         // box row above the strip
+        const float* zp = zs + (8 * warp + 1) * WS_STRIDE + lane32 + 32 * h + 1;
+        float am = wp[-1], a0 = wp[0], ap = wp[1];
+        float cm = wp[WS_STRIDE - 1], c0 = wp[WS_STRIDE], cp = wp[WS_STRIDE + 1];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float bm = wp[(i + 2) * WS_STRIDE - 1], b0 = wp[(i + 2) * WS_STRIDE], bp = wp[(i + 2) * WS_STRIDE + 1];
+            const float m = fminf(fmin3(am, a0, ap), fmin3(bm, b0, bp));
+            const float cand = fmaxf(zp[i * WS_STRIDE], fmin3(cm, cp, m));
+            if (cand < c0) { wp[(i + 1) * WS_STRIDE] = cand; c0 = cand; changed = true; }
+            am = cm; a0 = c0; ap = cp;
+            cm = bm; c0 = b0; cp = bp;
+        }
+    }
+    return changed;
+}
+
+template <int F, int L>
+__device__ __forceinline__ bool fill_march(float* __restrict__ ws, const float* __restrict__ zs, int p0, int lane32)
+{
+    float* wp = ws + p0;
+    const float* zp = zs + p0;
+    float bm = wp[-F - L], b0 = wp[-F], bp = wp[-F + L];
+    float cm = wp[-L], own = wp[0], cp = wp[L];
+    float zc = zp[0];
+    bool changed = false;
+#pragma unroll 1
+    for (int kk = 0; kk < FT; kk += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float fm = wp[(j + 1) * F - L], f0 = wp[(j + 1) * F], fp = wp[(j + 1) * F + L];
+            const float zn = zp[(j + 1) * F];
+            const float ahead = fmin3(f0, fp, fmin3(cm, cp, fm));
+            const float cand = fmaxf(zc, fminf(fmin3(bm, b0, bp), ahead));      // fmin / fmax skip NaN operands
+            if (cand < own) { wp[j * F] = cand; own = cand; changed = true; }   // only ever lowers W
+            const float um = __shfl_up_sync(0xffffffffu, own, 1), up = __shfl_down_sync(0xffffffffu, own, 1);
+            bm = (lane32 == 0) ? cm : um;
+            bp = (lane32 == 31) ? cp : up;
+            b0 = own; cm = fm; own = f0; cp = fp; zc = zn;
+        }
+        wp += 8 * F;
+        zp += 8 * F;
+    }
+    return changed;
+}
+
+__global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
                                                          int64_t w_pitch, int64_t ny, int64_t nx, int tiles_x, int tiles_y,
                                                          FillCtl* ctl, int* slots, int* queued)
 {
-    // This kernel does not use TMA: W must be read L2-coherently (ld.global.cg) while other CTAs update it, and z
-    // has to land in a padded (conflict-free) layout that a dense TMA box cannot produce.
+    // This kernel does not use TMA: W must be read L2-coherently (ld.global.cg) while other CTAs update it, and both
+    // boxes have to land in a padded (conflict-free) layout that a dense TMA box cannot produce.
+    // Shared memory: three (FT+2) x WS_STRIDE boxes with a one-cell halo and the same indexing -- z, W as loaded, W.
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_tile;
     __shared__ unsigned s_edges;
-    float* zs = reinterpret_cast<float*>(smem);                           // [FT][ZS_STRIDE]
-    float* wold = zs + FT * ZS_STRIDE;                                    // [(FT+2)][WS_STRIDE] as loaded
-    float* ws = wold + (FT + 2) * WS_STRIDE;                              // [(FT+2)][WS_STRIDE] working copy
+    constexpr int BOX = (FT + 2) * WS_STRIDE;
+    float* zs = reinterpret_cast<float*>(smem);
+    float* wold = zs + BOX;
+    float* ws = wold + BOX;
     const int qcap = ctl->qcap;
-    const int group = threadIdx.x >> 6, lane64 = threadIdx.x & 63;
+    const int group = threadIdx.x >> 6, lane64 = threadIdx.x & 63, lane32 = threadIdx.x & 31;
     const float qnan = __int_as_float(0x7fc00000);
+    const bool zvec_ok = ((z_pitch & 3) == 0) && ((((uintptr_t)z) & 15) == 0);
+    const bool wvec_ok = ((w_pitch & 3) == 0) && ((((uintptr_t)w) & 15) == 0);
     for (;;) {
         // ---- take a ticket and wait for its slot --------------------------------------------------------------------
+        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0, tc4 = 0;
         if (threadIdx.x == 0) {
+            tc0 = clock64();
             int tile = -1;
             const int my = atomicAdd(&ctl->head, 1);
             volatile int* slot = slots + (my % qcap);
@@ -223,149 +295,176 @@ __global__ void __launch_bounds__(FNT) fill_async_kernel(const float* __restrict
                 if (v != SLOT_EMPTY) { *slot = SLOT_EMPTY; tile = v; break; }
                 if (*(volatile int*)&ctl->pending <= 0 || *(volatile int*)&ctl->error) break;
                 if (spin > SPIN_LIMIT) { atomicExch(&ctl->error, 1); break; }
-                __nanosleep(200);
+                __nanosleep(100);
             }
             if (tile >= 0) { atomicExch(&queued[tile], T_RUNNING); __threadfence(); }
             s_tile = tile;
             s_edges = 0u;
+            tc1 = clock64();
         }
         __syncthreads();
         const int tile = s_tile;
         if (tile < 0) return;
         const int ty0 = (tile / tiles_x) * FT, tx0 = (tile % tiles_x) * FT;
-        // z tile (read-only path), zero outside the raster like a TMA box
-        const bool zvec_ok = ((z_pitch & 3) == 0) && ((((uintptr_t)z) & 15) == 0);
-#pragma unroll 2
-        for (int t = threadIdx.x; t < FT * 16; t += FNT) {
-            const int r = t >> 4, k = t & 15;
-            const int64_t y = (int64_t)ty0 + r, x = (int64_t)tx0 + 4 * k;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y < ny) {
-                if (zvec_ok && x + 3 < nx) {
-                    v = __ldg(reinterpret_cast<const float4*>(z + y * z_pitch + x));
-                } else {
-                    if (x < nx) v.x = __ldg(z + y * z_pitch + x);
-                    if (x + 1 < nx) v.y = __ldg(z + y * z_pitch + x + 1);
-                    if (x + 2 < nx) v.z = __ldg(z + y * z_pitch + x + 2);
-                    if (x + 3 < nx) v.w = __ldg(z + y * z_pitch + x + 3);
-                }
-            }
-            float* pz = zs + r * ZS_STRIDE + 4 * k;
-            pz[0] = v.x; pz[1] = v.y; pz[2] = v.z; pz[3] = v.w;
-        }
-        // W with a one-cell halo straight from L2; outside the raster = NaN (ignored by fminf)
-        const bool vec_ok = ((w_pitch & 3) == 0) && ((((uintptr_t)w) & 15) == 0);
-#pragma unroll 2
-        for (int t = threadIdx.x; t < (FT + 2) * 18; t += FNT) {
-            // per row of the box: 16 aligned float4 (the 64 tile columns) + the two halo columns
-            const int r = t / 18, k = t - r * 18;
-            const int64_t y = (int64_t)ty0 - 1 + r;
-            const bool yin = y >= 0 && y < ny;
-            float* po = wold + r * WS_STRIDE;
-            float* pw = ws + r * WS_STRIDE;
-            if (k < 16) {
-                const int64_t x = (int64_t)tx0 + 4 * k;
-                float4 v = make_float4(qnan, qnan, qnan, qnan);
-                if (yin && vec_ok && x + 3 < nx) {
-                    v = __ldcg(reinterpret_cast<const float4*>(w + y * w_pitch + x));
-                } else if (yin) {
-                    if (x < nx) v.x = __ldcg(w + y * w_pitch + x);
-                    if (x + 1 < nx) v.y = __ldcg(w + y * w_pitch + x + 1);
-                    if (x + 2 < nx) v.z = __ldcg(w + y * w_pitch + x + 2);
-                    if (x + 3 < nx) v.w = __ldcg(w + y * w_pitch + x + 3);
-                }
-                const int c = 1 + 4 * k;
-                po[c] = v.x; po[c + 1] = v.y; po[c + 2] = v.z; po[c + 3] = v.w;
-                pw[c] = v.x; pw[c + 1] = v.y; pw[c + 2] = v.z; pw[c + 3] = v.w;
-            } else {
-                const int c = (k == 16) ? 0 : FT + 1;
-                const int64_t x = (int64_t)tx0 - 1 + c;
-                float v = qnan;
-                if (yin && x >= 0 && x < nx) v = __ldcg(w + y * w_pitch + x);
-                po[c] = v;
-                pw[c] = v;
-            }
-        }
-        __syncthreads();
-        bool tile_changed = false;
-        int iters = 0;
-        // marching geometry of this thread group: f = step along the march, l = step to the neighbouring thread
-        const int f = (group == 0) ? WS_STRIDE : (group == 1) ? -WS_STRIDE : (group == 2) ? 1 : -1;
-        const int l = (group < 2) ? 1 : WS_STRIDE;
-        const int zf = (group == 0) ? ZS_STRIDE : (group == 1) ? -ZS_STRIDE : (group == 2) ? 1 : -1;
-        const int p0 = (group == 0) ? (1 * WS_STRIDE + lane64 + 1) : (group == 1) ? (FT * WS_STRIDE + lane64 + 1)
-                     : (group == 2) ? ((lane64 + 1) * WS_STRIDE + 1) : ((lane64 + 1) * WS_STRIDE + FT);
-        const int z0 = (group == 0) ? lane64 : (group == 1) ? ((FT - 1) * ZS_STRIDE + lane64)
-                     : (group == 2) ? (lane64 * ZS_STRIDE) : (lane64 * ZS_STRIDE + FT - 1);
-        for (int iter = 0; iter < 4096; ++iter) {
-            bool changed = false;
-            int p = p0, zp = z0;
-            // the row behind (b*), the current row's lateral neighbours (cm, cp) and the row ahead (f*): the row
-            // ahead of step k is the current row of step k+1 and this thread's own result is the next "behind"
-            // centre, so 7 shared-memory reads per cell instead of 10
-            float b0 = ws[p - f], cm = ws[p - l], cp = ws[p + l];
-            for (int step = 0; step < FT; ++step) {
-                const float bm = ws[p - f - l], bp = ws[p - f + l];
-                const float fm = ws[p + f - l], f0 = ws[p + f], fp = ws[p + f + l];
-                float m = fminf(fminf(fminf(bm, b0), fminf(bp, cm)), fminf(fminf(cp, fm), fminf(f0, fp)));
-                const float cand = fmaxf(zs[zp], m);                       // fminf / fmaxf skip NaN operands
-                float own = ws[p];
-                if (cand < own) { ws[p] = cand; own = cand; changed = true; }   // only ever lowers W
-                b0 = own; cm = fm; cp = fp;
-                p += f; zp += zf;
-            }
-            ++iters;
-            if (!__syncthreads_or(changed)) break;
-            tile_changed = true;
-        }
-        if (threadIdx.x == 0) atomicAdd(&ctl->iterations, (unsigned long long)iters);
-        if (tile_changed) {
-            unsigned edges = 0u;
-            for (int t = threadIdx.x; t < FT * FT; t += FNT) {
-                const int r = t >> 6, c = t & 63;
-                const int64_t y = ty0 + r, x = tx0 + c;
-                const float nv = ws[(r + 1) * WS_STRIDE + c + 1], ov = wold[(r + 1) * WS_STRIDE + c + 1];
-                if (y < ny && x < nx && nv != ov && !(nv != nv)) {
-                    w[y * w_pitch + x] = nv;
-                    // Poke a neighbouring tile only if this cell can still lower one of ITS cells: the halo ring holds the
-                    // neighbour's edge values as loaded (they only ever decrease), so nv >= that value means
-                    // max(z, nv) cannot undercut it.  This drops the useless "poke back" to the tile the level came from.
-                    // bit = (dy+1)*3 + (dx+1)
-                    if (r == 0 || r == FT - 1 || c == 0 || c == FT - 1) {
+
+        // ---- load z and W boxes: all global loads of a thread are issued before the first shared store ---------------
+        // items 0..1055: row r = item / 16 of the box, aligned quad k = item % 16 of the 64 tile columns
+        // items 1056..1187: the two halo columns.  Outside the raster: W = NaN (ignored by fmin), z = 0.
+        {
+            float4 zq[5], wq[5];
 #pragma unroll
-                        for (int a = -1; a <= 1; ++a)
-#pragma unroll
-                            for (int b = -1; b <= 1; ++b) {
-                                const int rr = r + a, cc = c + b;
-                                const int dy = rr < 0 ? -1 : (rr >= FT ? 1 : 0), dx = cc < 0 ? -1 : (cc >= FT ? 1 : 0);
-                                if ((dy | dx) && nv < wold[(rr + 1) * WS_STRIDE + cc + 1])     // NaN (outside the raster): false
-                                    edges |= 1u << ((dy + 1) * 3 + (dx + 1));
-                            }
+            for (int j = 0; j < 5; ++j) {
+                const int item = threadIdx.x + j * FNT;
+                zq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                wq[j] = make_float4(qnan, qnan, qnan, qnan);
+                if (item < 1056) {
+                    const int r = item >> 4, k = item & 15;
+                    const int64_t y = (int64_t)ty0 - 1 + r, x = (int64_t)tx0 + 4 * k;
+                    if (y >= 0 && y < ny) {
+                        const float* pz = z + y * z_pitch + x;
+                        const float* pw = w + y * w_pitch + x;
+                        if (x + 3 < nx && zvec_ok && wvec_ok) {
+                            zq[j] = __ldg(reinterpret_cast<const float4*>(pz));
+                            wq[j] = __ldcg(reinterpret_cast<const float4*>(pw));
+                        } else {
+                            if (x < nx) { zq[j].x = __ldg(pz); wq[j].x = __ldcg(pw); }
+                            if (x + 1 < nx) { zq[j].y = __ldg(pz + 1); wq[j].y = __ldcg(pw + 1); }
+                            if (x + 2 < nx) { zq[j].z = __ldg(pz + 2); wq[j].z = __ldcg(pw + 2); }
+                            if (x + 3 < nx) { zq[j].w = __ldg(pz + 3); wq[j].w = __ldcg(pw + 3); }
+                        }
+                    }
+                } else if (item < 1056 + 2 * (FT + 2)) {
+                    const int h = item - 1056, r = h >> 1;
+                    const int64_t y = (int64_t)ty0 - 1 + r, x = (h & 1) ? (int64_t)tx0 + FT : (int64_t)tx0 - 1;
+                    if (y >= 0 && y < ny && x >= 0 && x < nx) {
+                        zq[j].x = __ldg(z + y * z_pitch + x);
+                        wq[j].x = __ldcg(w + y * w_pitch + x);
                     }
                 }
             }
-            if (edges) atomicOr(&s_edges, edges);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int item = threadIdx.x + j * FNT;
+                if (item < 1056) {
+                    const int o = (item >> 4) * WS_STRIDE + 1 + 4 * (item & 15);
+                    zs[o] = zq[j].x; zs[o + 1] = zq[j].y; zs[o + 2] = zq[j].z; zs[o + 3] = zq[j].w;
+                    ws[o] = wq[j].x; ws[o + 1] = wq[j].y; ws[o + 2] = wq[j].z; ws[o + 3] = wq[j].w;
+                    wold[o] = wq[j].x; wold[o + 1] = wq[j].y; wold[o + 2] = wq[j].z; wold[o + 3] = wq[j].w;
+                } else if (item < 1056 + 2 * (FT + 2)) {
+                    const int h = item - 1056;
+                    const int o = (h >> 1) * WS_STRIDE + ((h & 1) ? FT + 1 : 0);
+                    zs[o] = zq[j].x; ws[o] = wq[j].x; wold[o] = wq[j].x;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) tc2 = clock64();
+
+        // ---- relax to the local fixed point ------------------------------------------------------------------------
+        // A marching iteration (four groups going down / up / right / left simultaneously) carries a level across the
+        // whole tile but costs 64 dependent steps; the check pass relaxes every cell once with no dependency chain at
+        // 1/6 of the instructions.  The visit starts with a check (almost half of all visits find nothing to lower and
+        // end right there) and every marching iteration is followed by one: a check that stores nothing has read a
+        // static tile, i.e. verified the local fixed point.
+        bool tile_changed = false;
+        int iters = 0;
+        const int warp = threadIdx.x >> 5;
+        while (__syncthreads_or(fill_check(ws, zs, warp, lane32))) {
+            tile_changed = true;
+            if (group == 0)      fill_march<WS_STRIDE, 1>(ws, zs, 1 * WS_STRIDE + lane64 + 1, lane32);
+            else if (group == 1) fill_march<-WS_STRIDE, 1>(ws, zs, FT * WS_STRIDE + lane64 + 1, lane32);
+            else if (group == 2) fill_march<1, WS_STRIDE>(ws, zs, (lane64 + 1) * WS_STRIDE + 1, lane32);
+            else                 fill_march<-1, WS_STRIDE>(ws, zs, (lane64 + 1) * WS_STRIDE + FT, lane32);
+            ++iters;
+            __syncthreads();
+            if (iters > 4096) break;
+        }
+        if (threadIdx.x == 0) { atomicAdd(&ctl->iterations, (unsigned long long)iters); tc3 = clock64(); }
+
+        // ---- write the lowered cells back; decide which neighbours have to look again ------------------------------------
+        if (tile_changed) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int item = threadIdx.x + j * FNT;                  // quad k of tile row r
+                const int r = item >> 4, k = item & 15;
+                const int o = (r + 1) * WS_STRIDE + 1 + 4 * k;
+                const float n0 = ws[o], n1 = ws[o + 1], n2 = ws[o + 2], n3 = ws[o + 3];
+                const bool any = n0 != wold[o] || n1 != wold[o + 1] || n2 != wold[o + 2] || n3 != wold[o + 3];
+                const int64_t y = (int64_t)ty0 + r, x = (int64_t)tx0 + 4 * k;
+                if (any && y < ny) {                                     // (NaN cells lie outside the raster: never changed)
+                    float* pw = w + y * w_pitch + x;
+                    if (x + 3 < nx && wvec_ok) {
+                        *reinterpret_cast<float4*>(pw) = make_float4(n0, n1, n2, n3);
+                    } else {
+                        if (x < nx) pw[0] = n0;
+                        if (x + 1 < nx) pw[1] = n1;
+                        if (x + 2 < nx) pw[2] = n2;
+                        if (x + 3 < nx) pw[3] = n3;
+                    }
+                }
+            }
+            // One thread per cell of the tile's outer ring.  A neighbouring tile is poked only if a lowered ring cell can
+            // still lower one of ITS cells h: max(z(h), new value) < W(h), with z(h) and W(h) from the halo as loaded
+            // (W only ever decreases, so a stale W(h) errs on the safe side).  This test is exact: it drops the "poke
+            // back" to the tile the level came from and every poke that z(h) would absorb.    bit = (dy+1)*3 + (dx+1)
+            unsigned edges = 0u;
+            if (threadIdx.x < 4 * FT - 4) {
+                const int t = threadIdx.x;
+                int r, c;
+                if (t < FT) { r = 0; c = t; }
+                else if (t < 2 * FT) { r = FT - 1; c = t - FT; }
+                else if (t < 3 * FT - 2) { r = t - 2 * FT + 1; c = 0; }
+                else { r = t - (3 * FT - 2) + 1; c = FT - 1; }
+                const int o = (r + 1) * WS_STRIDE + c + 1;
+                const float nv = ws[o];
+                if (nv < wold[o]) {
+#pragma unroll
+                    for (int a = -1; a <= 1; ++a)
+#pragma unroll
+                        for (int b = -1; b <= 1; ++b) {
+                            const int rr = r + a, cc = c + b;
+                            const int dy = rr < 0 ? -1 : (rr >= FT ? 1 : 0), dx = cc < 0 ? -1 : (cc >= FT ? 1 : 0);
+                            if (dy | dx) {
+                                const int oh = o + a * WS_STRIDE + b;
+                                if (fmaxf(zs[oh], nv) < ws[oh])                 // halo W outside the raster is NaN: false
+                                    edges |= 1u << ((dy + 1) * 3 + (dx + 1));
+                            }
+                        }
+                }
+            }
+            edges = __reduce_or_sync(0xffffffffu, edges);
+            if (edges && lane32 == 0) atomicOr(&s_edges, edges);
             __threadfence();                                   // W stores visible device-wide before neighbours are published
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0) tc4 = clock64();
+        // ---- publish: one thread per neighbour, then the tile's own state -----------------------------------------------
+        if (threadIdx.x < 32) {
             const unsigned edges = s_edges;
-            const int ty = tile / tiles_x, tx = tile % tiles_x;
-            for (int k = 0; k < 9; ++k) {
-                if (!((edges >> k) & 1u)) continue;
-                const int tyy = ty + k / 3 - 1, txx = tx + k % 3 - 1;
-                if (tyy < 0 || tyy >= tiles_y || txx < 0 || txx >= tiles_x) continue;
-                fill_poke(ctl, slots, qcap, queued, tyy * tiles_x + txx);
+            const int k = threadIdx.x;
+            if (k < 9 && ((edges >> k) & 1u)) {
+                const int tyy = tile / tiles_x + k / 3 - 1, txx = tile % tiles_x + k % 3 - 1;
+                if (tyy >= 0 && tyy < tiles_y && txx >= 0 && txx < tiles_x)
+                    fill_poke(ctl, slots, qcap, queued, tyy * tiles_x + txx);
             }
-            atomicAdd(&ctl->visits, 1ull);
-            if (tile_changed) atomicAdd(&ctl->changed_visits, 1ull);
-            __threadfence();
-            if (atomicCAS(&queued[tile], T_RUNNING, T_IDLE) != T_RUNNING) {     // poked while running: go again
-                atomicExch(&queued[tile], T_QUEUED);
-                fill_push(ctl, slots, qcap, tile);
+            __syncwarp();
+            if (k == 0) {
+                atomicAdd(&ctl->visits, 1ull);
+                if (tile_changed) atomicAdd(&ctl->changed_visits, 1ull);
+                __threadfence();
+                if (atomicCAS(&queued[tile], T_RUNNING, T_IDLE) != T_RUNNING) {     // poked while running: go again
+                    atomicExch(&queued[tile], T_QUEUED);
+                    fill_push(ctl, slots, qcap, tile);
+                }
+                __threadfence();
+                atomicSub(&ctl->pending, 1);
+                const long long tc5 = clock64();
+                atomicAdd(&ctl->cycles[0], (unsigned long long)(tc1 - tc0));
+                atomicAdd(&ctl->cycles[1], (unsigned long long)(tc2 - tc1));
+                atomicAdd(&ctl->cycles[2], (unsigned long long)(tc3 - tc2));
+                atomicAdd(&ctl->cycles[3], (unsigned long long)(tc4 - tc3));
+                atomicAdd(&ctl->cycles[4], (unsigned long long)(tc5 - tc4));
             }
-            __threadfence();
-            atomicSub(&ctl->pending, 1);
         }
         __syncthreads();
     }
@@ -417,7 +516,7 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     const int qcap = ntiles + 8192;
     int* slots = (int*)((char*)workspace + 256);
     int* queued = slots + qcap;
-    const size_t smem = (size_t)FT * ZS_STRIDE * 4 + 2 * (size_t)(FT + 2) * WS_STRIDE * 4;
+    const size_t smem = 3 * (size_t)(FT + 2) * WS_STRIDE * 4;
     HD_CUDA_OK(cudaFuncSetAttribute(fill_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel, FNT, smem));
@@ -456,6 +555,11 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     if (getenv("HD_FILL_TRACE"))
         fprintf(stderr, "pdfill async: %llu tile visits (%llu changed, %llu in-tile iterations) over %d tiles, grid %d\n",
                 h_ctl->visits, h_ctl->changed_visits, h_ctl->iterations, ntiles, grid);
+    if (getenv("HD_FILL_TRACE") && h_ctl->visits)
+        fprintf(stderr, "  cycles per visit: wait %.0f  load %.0f  iterate %.0f  writeback %.0f  publish %.0f\n",
+                (double)h_ctl->cycles[0] / h_ctl->visits, (double)h_ctl->cycles[1] / h_ctl->visits,
+                (double)h_ctl->cycles[2] / h_ctl->visits, (double)h_ctl->cycles[3] / h_ctl->visits,
+                (double)h_ctl->cycles[4] / h_ctl->visits);
     if (visits_out) *visits_out = (int)h_ctl->visits;
     if (h_ctl->error || h_ctl->pending != 0) return HD_ERR_UNSUPPORTED;    // worklist stalled (should not happen)
     return HD_OK;

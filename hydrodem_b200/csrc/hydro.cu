@@ -205,11 +205,11 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 }
 
 // One marching sweep of a 64-thread group through the tile: F = shared-memory step along the march, L = step to the
-// neighbouring thread's line.  Per cell: three reads for the row ahead (which then serve as the next step's current
-// row), the thread's own result carried in a register, the two diagonal cells behind fetched from the neighbouring
-// lanes by shuffle (they were updated one step ago: a level runs diagonally through the tile in a single sweep).
-// At the two ends of a warp the diagonal cell comes from the value read two steps earlier instead (a halo cell, or
-// the other warp's line: at worst that information arrives one iteration later).  All offsets are immediates.
+// neighbouring thread's line.  A cell is relaxed against the three cells behind it and its two lateral neighbours
+// (the opposite group covers the three ahead; the check pass covers all eight).  Per step: three reads of the next
+// row, the thread's own previous result in a register and the two diagonal cells behind from the neighbouring lanes
+// by shuffle -- they were updated one step ago, so a level runs diagonally through the tile in a single sweep and no
+// step waits for a shared-memory store to come back.
 // One relaxation of every cell of the tile, no dependency chain: warp w takes tile rows 8w..8w+7, a lane two columns,
 // sliding a three-row window down its strip.
 __device__ __forceinline__ bool fill_check(float* __restrict__ ws, const float* __restrict__ zs, int warp, int lane32)
@@ -235,32 +235,31 @@ __device__ __forceinline__ bool fill_check(float* __restrict__ ws, const float* 
 }
 
 template <int F, int L>
-__device__ __forceinline__ bool fill_march(float* __restrict__ ws, const float* __restrict__ zs, int p0, int lane32)
+__device__ __forceinline__ void fill_march(float* __restrict__ ws, const float* __restrict__ zs, int p0)
 {
     float* wp = ws + p0;
     const float* zp = zs + p0;
     float bm = wp[-F - L], b0 = wp[-F], bp = wp[-F + L];
     float cm = wp[-L], own = wp[0], cp = wp[L];
     float zc = zp[0];
-    bool changed = false;
 #pragma unroll 1
     for (int kk = 0; kk < FT; kk += 8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            // the next step's current row, read before this step's store (all offsets are immediates)
             const float fm = wp[(j + 1) * F - L], f0 = wp[(j + 1) * F], fp = wp[(j + 1) * F + L];
             const float zn = zp[(j + 1) * F];
-            const float ahead = fmin3(f0, fp, fmin3(cm, cp, fm));
-            const float cand = fmaxf(zc, fminf(fmin3(bm, b0, bp), ahead));      // fmin / fmax skip NaN operands
-            if (cand < own) { wp[j * F] = cand; own = cand; changed = true; }   // only ever lowers W
-            const float um = __shfl_up_sync(0xffffffffu, own, 1), up = __shfl_down_sync(0xffffffffu, own, 1);
-            bm = (lane32 == 0) ? cm : um;
-            bp = (lane32 == 31) ? cp : up;
+            const float cand = fmaxf(zc, fmin3(cm, cp, fmin3(bm, b0, bp)));     // fmin / fmax skip NaN operands
+            if (cand < own) { wp[j * F] = cand; own = cand; }                   // only ever lowers W
+            // the diagonal cells behind the next step: the neighbouring lanes' results of this step.  The end lanes of
+            // a warp get their own value back (no information, no harm)
+            bm = __shfl_up_sync(0xffffffffu, own, 1);
+            bp = __shfl_down_sync(0xffffffffu, own, 1);
             b0 = own; cm = fm; own = f0; cp = fp; zc = zn;
         }
         wp += 8 * F;
         zp += 8 * F;
     }
-    return changed;
 }
 
 __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
@@ -282,29 +281,31 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
     const float qnan = __int_as_float(0x7fc00000);
     const bool zvec_ok = ((z_pitch & 3) == 0) && ((((uintptr_t)z) & 15) == 0);
     const bool wvec_ok = ((w_pitch & 3) == 0) && ((((uintptr_t)w) & 15) == 0);
-    for (;;) {
-        // ---- take a ticket and wait for its slot --------------------------------------------------------------------
-        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0, tc4 = 0;
-        if (threadIdx.x == 0) {
-            tc0 = clock64();
-            int tile = -1;
-            const int my = atomicAdd(&ctl->head, 1);
-            volatile int* slot = slots + (my % qcap);
-            for (int spin = 0;; ++spin) {
-                const int v = *slot;
-                if (v != SLOT_EMPTY) { *slot = SLOT_EMPTY; tile = v; break; }
-                if (*(volatile int*)&ctl->pending <= 0 || *(volatile int*)&ctl->error) break;
-                if (spin > SPIN_LIMIT) { atomicExch(&ctl->error, 1); break; }
-                __nanosleep(100);
-            }
-            if (tile >= 0) { atomicExch(&queued[tile], T_RUNNING); __threadfence(); }
-            s_tile = tile;
-            s_edges = 0u;
-            tc1 = clock64();
+    // Thread 32 takes the tickets: it waits for the next tile while warp 0 is still publishing the previous one.
+    auto take_ticket = [&]() {
+        const long long t0 = clock64();
+        int tile = -1;
+        const int my = atomicAdd(&ctl->head, 1);
+        volatile int* slot = slots + (my % qcap);
+        for (int spin = 0;; ++spin) {
+            const int v = *slot;
+            if (v != SLOT_EMPTY) { *slot = SLOT_EMPTY; tile = v; break; }
+            if (*(volatile int*)&ctl->pending <= 0 || *(volatile int*)&ctl->error) break;
+            if (spin > SPIN_LIMIT) { atomicExch(&ctl->error, 1); break; }
+            __nanosleep(100);
         }
+        if (tile >= 0) { atomicExch(&queued[tile], T_RUNNING); __threadfence(); }
+        s_tile = tile;
+        atomicAdd(&ctl->cycles[0], (unsigned long long)(clock64() - t0));
+    };
+    if (threadIdx.x == 0) s_edges = 0u;
+    if (threadIdx.x == 32) take_ticket();
+    for (;;) {
+        long long tc1 = 0, tc2 = 0, tc3 = 0, tc4 = 0;
         __syncthreads();
         const int tile = s_tile;
         if (tile < 0) return;
+        if (threadIdx.x == 0) tc1 = clock64();
         const int ty0 = (tile / tiles_x) * FT, tx0 = (tile % tiles_x) * FT;
 
         // ---- load z and W boxes: all global loads of a thread are issued before the first shared store ---------------
@@ -371,10 +372,10 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
         const int warp = threadIdx.x >> 5;
         while (__syncthreads_or(fill_check(ws, zs, warp, lane32))) {
             tile_changed = true;
-            if (group == 0)      fill_march<WS_STRIDE, 1>(ws, zs, 1 * WS_STRIDE + lane64 + 1, lane32);
-            else if (group == 1) fill_march<-WS_STRIDE, 1>(ws, zs, FT * WS_STRIDE + lane64 + 1, lane32);
-            else if (group == 2) fill_march<1, WS_STRIDE>(ws, zs, (lane64 + 1) * WS_STRIDE + 1, lane32);
-            else                 fill_march<-1, WS_STRIDE>(ws, zs, (lane64 + 1) * WS_STRIDE + FT, lane32);
+            if (group == 0)      fill_march<WS_STRIDE, 1>(ws, zs, 1 * WS_STRIDE + lane64 + 1);
+            else if (group == 1) fill_march<-WS_STRIDE, 1>(ws, zs, FT * WS_STRIDE + lane64 + 1);
+            else if (group == 2) fill_march<1, WS_STRIDE>(ws, zs, (lane64 + 1) * WS_STRIDE + 1);
+            else                 fill_march<-1, WS_STRIDE>(ws, zs, (lane64 + 1) * WS_STRIDE + FT);
             ++iters;
             __syncthreads();
             if (iters > 4096) break;
@@ -426,8 +427,12 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
                             const int dy = rr < 0 ? -1 : (rr >= FT ? 1 : 0), dx = cc < 0 ? -1 : (cc >= FT ? 1 : 0);
                             if (dy | dx) {
                                 const int oh = o + a * WS_STRIDE + b;
-                                if (fmaxf(zs[oh], nv) < ws[oh])                 // halo W outside the raster is NaN: false
-                                    edges |= 1u << ((dy + 1) * 3 + (dx + 1));
+                                const float lim = fmaxf(zs[oh], nv);
+                                if (lim < ws[oh]) {                             // halo W outside the raster is NaN: false
+                                    // the neighbour may have lowered h since this tile was loaded: look again
+                                    const float fresh = __ldcg(w + ((int64_t)ty0 + rr) * w_pitch + (int64_t)tx0 + cc);
+                                    if (lim < fresh) edges |= 1u << ((dy + 1) * 3 + (dx + 1));
+                                }
                             }
                         }
                 }
@@ -438,7 +443,9 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
         }
         __syncthreads();
         if (threadIdx.x == 0) tc4 = clock64();
-        // ---- publish: one thread per neighbour, then the tile's own state -----------------------------------------------
+        // ---- publish (warp 0) while thread 32 already fetches the next tile ---------------------------------------------
+        // lanes 0..8 poke one neighbour each, lane 9 moves the tile's own state; `pending` drops last, after a fence, so it
+        // can never read 0 while a poke of this visit is still on its way
         if (threadIdx.x < 32) {
             const unsigned edges = s_edges;
             const int k = threadIdx.x;
@@ -446,27 +453,28 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
                 const int tyy = tile / tiles_x + k / 3 - 1, txx = tile % tiles_x + k % 3 - 1;
                 if (tyy >= 0 && tyy < tiles_y && txx >= 0 && txx < tiles_x)
                     fill_poke(ctl, slots, qcap, queued, tyy * tiles_x + txx);
-            }
-            __syncwarp();
-            if (k == 0) {
-                atomicAdd(&ctl->visits, 1ull);
-                if (tile_changed) atomicAdd(&ctl->changed_visits, 1ull);
-                __threadfence();
+            } else if (k == 9) {
                 if (atomicCAS(&queued[tile], T_RUNNING, T_IDLE) != T_RUNNING) {     // poked while running: go again
                     atomicExch(&queued[tile], T_QUEUED);
                     fill_push(ctl, slots, qcap, tile);
                 }
+            }
+            __syncwarp();
+            if (k == 0) {
+                s_edges = 0u;
+                atomicAdd(&ctl->visits, 1ull);
+                if (tile_changed) atomicAdd(&ctl->changed_visits, 1ull);
                 __threadfence();
                 atomicSub(&ctl->pending, 1);
                 const long long tc5 = clock64();
-                atomicAdd(&ctl->cycles[0], (unsigned long long)(tc1 - tc0));
                 atomicAdd(&ctl->cycles[1], (unsigned long long)(tc2 - tc1));
                 atomicAdd(&ctl->cycles[2], (unsigned long long)(tc3 - tc2));
                 atomicAdd(&ctl->cycles[3], (unsigned long long)(tc4 - tc3));
                 atomicAdd(&ctl->cycles[4], (unsigned long long)(tc5 - tc4));
             }
+        } else if (threadIdx.x == 32) {
+            take_ticket();
         }
-        __syncthreads();
     }
 }
 
@@ -520,6 +528,10 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     HD_CUDA_OK(cudaFuncSetAttribute(fill_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel, FNT, smem));
+    if (const char* e = getenv("HD_FILL_CTAS_PER_SM")) {      // experiments: fewer co-resident CTAs, less MIO contention
+        const int v = atoi(e);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     int grid = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);       // every CTA must be co-resident: they wait on each other
     if (grid > ntiles) grid = ntiles;
     // (no host-to-device copy of a stack object here: the whole call must be capturable in a CUDA graph)

@@ -290,12 +290,12 @@ def run_gpu(args):
         for _ in range(n):
             yield (host["srtm"], host["groves"], host["hsheds"])
 
-    for r in chain.stream(tiles(max(3, args.warmup))):
+    for r in chain.stream(tiles(max(8, args.warmup)), depth=args.stream_depth):
         del r                                                              # pinned result buffers go back to the cache
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    for r in chain.stream(tiles(e2e_steps)):
+    for r in chain.stream(tiles(e2e_steps), depth=args.stream_depth):
         outs = (r["final"], r["filled"], r["d8"])                          # host arrays (pinned), copies complete
         del r, outs
     torch.cuda.synchronize()
@@ -332,7 +332,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "for out in hydrodem_b200.pipeline.ConditioningChain.stream(tiles): out = {final, filled, d8} "
-                           "ndarrays; two slots, copies of neighbouring steps overlap the kernels",
+                           "ndarrays; {args.stream_depth} slots, copies of neighbouring steps overlap the kernels",
                     "single_tile_latency_ms": single_ms,
                     "single_tile_api": "ConditioningChain.apply_to_host(srtm, groves, hsheds)"},
             "gpu_launches": launches, "launches_per_step": launches / args.steps,
@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--size", type=int, default=TILE, help="tile edge (default 3601 = BASELINE.json configs[1])")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="edge of the CPU baseline sample tile")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--stream-depth", type=int, default=3, help="tiles in flight in the e2e streaming loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the kernels one by one instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
     __shared__ float s_ref;
+    __shared__ uint32_t s_groves[GROVES ? TH * TW / 4 : 1];     // the tile's groves mask, four cells per word
     float* v1 = reinterpret_cast<float*>(smem + 2 * STAGE);     // [TH][CW]  sum_dy (w - ref)
     float* vyy = v1 + TH * CW;                                   // [TH][CW]  sum_dy y^2 (w - ref)
     float c2f[WS];
@@ -56,6 +57,43 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
     const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * sizeof(T)), HX, H}};
     tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const T* tile = reinterpret_cast<const T*>(st);
+        // Groves tail: where groves == 0 the reference evaluates smooth + 1 * (dem - smooth), i.e. dem to the last bit or
+        // two -- those cells are copied, and a tile without a single groves cell (most of them: groves cover about one
+        // per cent of a scene) skips both filter passes.
+        if (GROVES) {
+            bool any = false;
+#pragma unroll
+            for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+                const int idx = rep * NT + threadIdx.x;
+                const int ro = idx >> 5, c4 = idx & 31;
+                const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+                uint32_t g = 0u;
+                if (y < ny && x < nx) {
+                    const uint8_t* pg = groves + y * groves_pitch + x;
+                    if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(pg) & 3) == 0)) {
+                        g = __ldg(reinterpret_cast<const uint32_t*>(pg));
+                    } else {
+                        for (int j = 0; j < 4 && x + j < nx; ++j) g |= (uint32_t)__ldg(pg + j) << (8 * j);
+                    }
+                }
+                s_groves[idx] = g;                                  // read back by this same thread only
+                any |= g != 0u;
+            }
+            if (!__syncthreads_or(any)) {
+#pragma unroll
+                for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+                    const int idx = rep * NT + threadIdx.x;
+                    const int ro = idx >> 5, c4 = idx & 31;
+                    const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+                    if (y >= ny || x >= nx) continue;
+                    OutT res[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[j] = (OutT)tile[(ro + H) * IN_W + 4 * c4 + j + HX];
+                    store4v<OutT>(out, out_pitch, y, x, nx, res);
+                }
+                return;
+            }
+        }
         // The kernel sums to 1, so smoothed = ref + K * (w - ref) for any constant ref.  Taking ref from the tile
         // keeps the float32 partial sums small (terrain relief instead of absolute elevation): ~5e-7 relative.
         if (threadIdx.x == 0) {
@@ -91,6 +129,14 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
             const int ro = idx >> 5, c4 = idx & 31;
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
+            const uint32_t gq = GROVES ? s_groves[idx] : 0u;
+            if (GROVES && gq == 0u) {                     // no groves cell in this quad: copy
+                OutT cp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cp[j] = (OutT)tile[(ro + H) * IN_W + 4 * c4 + j + HX];
+                store4v<OutT>(out, out_pitch, y, x, nx, cp);
+                continue;
+            }
             constexpr int NQ = (WS + 3 + 3) / 4;        // float4 loads covering the WS + 3 columns of 4 windows
             float a[4 * NQ], b[4 * NQ];
             const float4* pa = reinterpret_cast<const float4*>(v1 + ro * CW + 4 * c4);    // lanes 16 B apart: conflict free
@@ -119,7 +165,9 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
                     smooth = (T)((double)ref + (((double)s2 + (double)s3) * p.r1 - (double)s1 * p.r23) / p.den);
                 }
                 if (GROVES) {
-                    const double g = (x + j < nx) ? (double)groves[y * groves_pitch + x + j] : 0.0;
+                    const uint32_t gbyte = (gq >> (8 * j)) & 0xffu;
+                    if (gbyte == 0u) { res[j] = (OutT)ctr; continue; }
+                    const double g = (double)gbyte;
                     const T hi = ctr - smooth;                                        // SubtractionFilter (:725)
                     const double tall = (hi > (T)p.thr) ? 1.0 : 0.0;                  // MaskTallGroves
                     const double keep = 1.0 - g * tall;                               // Product, 1 - .

@@ -176,16 +176,27 @@ class _StreamSlot:
             done.record(down)
             pending[name] = (host, done, np.dtype(np_dtype))
 
+        trace = getattr(self.chain, "_trace", None)                   # tools/e2e_prof.py: per-tile compute spans
+        if trace is not None:
+            t_begin = torch.cuda.Event(enable_timing=True)
+            cur.wait_event(ready[self.segments[0][0]])
+            t_begin.record(cur)
+            marks = [t_begin]
         for needs, g in self.segments:
             if needs is not None:
                 cur.wait_event(ready[needs])
             g.replay()
+            if trace is not None:
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record(cur)
             if needs == "hsheds":
                 send(*self.outputs[0])
         for spec in self.outputs[1:]:
             send(*spec)
-        self.ev_compute = torch.cuda.Event()
+        self.ev_compute = torch.cuda.Event(enable_timing=trace is not None)
         self.ev_compute.record(cur)
+        if trace is not None:
+            trace.append((t_begin, self.ev_compute, marks))
         self.ev_down = torch.cuda.Event()
         self.ev_down.record(down)
         self.keep = keep

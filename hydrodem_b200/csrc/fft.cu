@@ -321,11 +321,36 @@ __device__ __forceinline__ void dit_pass(float2* s, int m, int lgm, int lgL, con
 
 struct PassPlan { int npass; int k[4]; };
 
+// Bluestein middle: the last DIF pass and the first inverse DIT pass work on the same 2^K contiguous elements with
+// unit twiddles, so they run as one pass in registers: DIF butterflies, x bhat (the pointwise product with the
+// transformed chirp), DIT butterflies -- one shared-memory round trip instead of two.
+template <int K>
+__device__ __forceinline__ void bluestein_mid_pass(float2* s, int m, const float2* __restrict__ bhat)
+{
+    constexpr int R = 1 << K;
+    for (int g = threadIdx.x; g < (m >> K); g += FNT) {
+        const int base = g << K;
+        float2 x[R], b[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) b[q] = __ldg(&bhat[base + q]);
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = s[pad(base + q)];
+        dif_regs<K>(x);
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = cmul(x[q], b[q]);
+        dit_regs<K, true>(x);
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[pad(base + q)] = x[q];
+    }
+    __syncthreads();
+}
+
 template <bool MULB_LAST>
-__device__ __forceinline__ void fft_dif_all(float2* s, int m, int lgm, const PassPlan& pl, const float2* tw, const float2* bhat)
+__device__ __forceinline__ void fft_dif_all(float2* s, int m, int lgm, const PassPlan& pl, const float2* tw, const float2* bhat,
+                                            int skip_last = 0)
 {
     int lgL = lgm;
-    for (int i = 0; i < pl.npass; ++i) {
+    for (int i = 0; i < pl.npass - skip_last; ++i) {
         const bool last = MULB_LAST && i == pl.npass - 1;
         switch (pl.k[i]) {
             case 1: last ? dif_pass<1, true>(s, m, lgm, lgL, tw, bhat) : dif_pass<1, false>(s, m, lgm, lgL, tw, bhat); break;
@@ -338,10 +363,10 @@ __device__ __forceinline__ void fft_dif_all(float2* s, int m, int lgm, const Pas
 }
 
 template <bool CONJ>
-__device__ __forceinline__ void fft_dit_all(float2* s, int m, int lgm, const PassPlan& pl, const float2* tw)
+__device__ __forceinline__ void fft_dit_all(float2* s, int m, int lgm, const PassPlan& pl, const float2* tw, int skip_first = 0)
 {
-    int lgL = 0;
-    for (int i = pl.npass - 1; i >= 0; --i) {
+    int lgL = skip_first ? pl.k[pl.npass - 1] : 0;
+    for (int i = pl.npass - 1 - skip_first; i >= 0; --i) {
         lgL += pl.k[i];
         switch (pl.k[i]) {
             case 1: dit_pass<1, CONJ>(s, m, lgm, lgL, tw); break;
@@ -415,38 +440,61 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
         const int k1 = pair ? 0 : item % n1;
         const bool has_b = pair && (row + 1 < a.nrows);
         // ---- load (+ n1-point DFT and twiddle for long rows, + chirp for Bluestein) --------------------------
-        for (int k = threadIdx.x; k < m; k += FNT) {
-            float2 v = make_float2(0.f, 0.f);
-            if (k < n) {
-                if (pair) {
-                    const float* src = reinterpret_cast<const float*>(a.in) + (int64_t)row * a.in_pitch + k;
-                    v.x = src[0];
-                    if (has_b) v.y = src[a.in_pitch];        // real rows: the inverse conj is applied after the split
-                } else if (n1 == 1) {
-                    v = elem(row, k);
-                } else {
-                    for (int aa = 0; aa < n1; ++aa) {
-                        const float2 x = elem(row, aa * n + k), w = __ldg(&a.w1[aa * n1 + k1]);
-                        v.x = fmaf(x.x, w.x, fmaf(-x.y, w.y, v.x));
-                        v.y = fmaf(x.x, w.y, fmaf(x.y, w.x, v.y));
+        // batches of LB elements per thread: all global loads of a batch are issued before the first is used
+        constexpr int LB = 8;
+        for (int k0 = threadIdx.x; k0 < m; k0 += LB * FNT) {
+            float2 v[LB], ch[LB];
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                const int k = k0 + j * FNT;
+                v[j] = make_float2(0.f, 0.f);
+                ch[j] = make_float2(1.f, 0.f);
+                if (k < n) {
+                    if (pair) {
+                        const float* src = reinterpret_cast<const float*>(a.in) + (int64_t)row * a.in_pitch + k;
+                        v[j].x = src[0];
+                        if (has_b) v[j].y = src[a.in_pitch];     // real rows: the inverse conj is applied after the split
+                    } else if (n1 == 1) {
+                        v[j] = elem(row, k);
+                    } else {
+                        for (int aa = 0; aa < n1; ++aa) {
+                            const float2 x = elem(row, aa * n + k), w = __ldg(&a.w1[aa * n1 + k1]);
+                            v[j].x = fmaf(x.x, w.x, fmaf(-x.y, w.y, v[j].x));
+                            v[j].y = fmaf(x.x, w.y, fmaf(x.y, w.x, v[j].y));
+                        }
+                        v[j] = cmul(v[j], __ldg(&a.wn[k * k1]));
                     }
-                    v = cmul(v, __ldg(&a.wn[k * k1]));
+                    if (BLUE) ch[j] = __ldg(&chirp[k]);
                 }
-                if (BLUE) v = cmul(v, __ldg(&chirp[k]));
             }
-            if (BLUE) s[pad(k)] = v;
-            else s[pad(log2m ? (int)(__brev((unsigned)k) >> (32 - log2m)) : 0)] = v;   // DIT wants bit-reversed input
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                const int k = k0 + j * FNT;
+                if (k >= m) continue;
+                float2 u = v[j];
+                if (BLUE && k < n) u = cmul(u, ch[j]);
+                if (BLUE) s[pad(k)] = u;
+                else s[pad(log2m ? (int)(__brev((unsigned)k) >> (32 - log2m)) : 0)] = u;   // DIT wants bit-reversed input
+            }
         }
         __syncthreads();
         if (BLUE) {
-            fft_dif_all<true>(s, m, log2m, plan, tw, bhat);       // ... * FFT(conj chirp) / m fused into the last pass
-            fft_dit_all<true>(s, m, log2m, plan, tw);
+            // DIF passes, the fused middle (last DIF pass x FFT(conj chirp) / m x first inverse DIT pass), DIT passes
+            fft_dif_all<false>(s, m, log2m, plan, tw, bhat, 1);
+            switch (plan.k[plan.npass - 1]) {
+                case 1: bluestein_mid_pass<1>(s, m, bhat); break;
+                case 2: bluestein_mid_pass<2>(s, m, bhat); break;
+                case 3: bluestein_mid_pass<3>(s, m, bhat); break;
+                default: bluestein_mid_pass<4>(s, m, bhat); break;
+            }
+            fft_dit_all<true>(s, m, log2m, plan, tw, 1);
         } else if (m > 1) {
             fft_dit_all<false>(s, m, log2m, plan, tw);
         }
         // ---- store: X[k1 + n1 * k] goes to position k1 * n + k (see Plan1D) ------------------------------------
         const int64_t obase = (int64_t)row * a.out_pitch + (int64_t)k1 * n;
-        for (int k = threadIdx.x; k < n; k += FNT) {
+#pragma unroll 4
+        for (int k = threadIdx.x; k < n; k += FNT) {                       // unrolled: the chirp loads of four steps overlap
             float2 v = s[pad(k)];
             if (BLUE) v = cmul(v, __ldg(&chirp[k]));
             if (pair) {

@@ -14,6 +14,18 @@ if stage == "fft":
     r = dev.upload(sc.srtm())
     for _ in range(3):
         cf.FourierInitial().run_device(r)
+elif stage == "daf":
+    r = dev.upload(sc.srtm())
+    for _ in range(2):
+        cf.DetectApplyFourier().run_device(r)
+elif stage == "chainfill":
+    from hydrodem_b200 import _lib
+    from hydrodem_b200.pipeline import ConditioningChain
+    chain = ConditioningChain(with_hydrology=False)
+    res = chain.run_device(*chain.upload_inputs(sc.srtm(), sc.groves(), sc.hsheds()))
+    z = dev.convert(res.rasters["final"], _lib.F32, np.float32)
+    for _ in range(2):
+        nf.SinkFill(want_stats=False).run_device(z)
 elif stage == "fill":
     r = dev.upload(np.round(sc.srtm()))
     for _ in range(2):

@@ -29,7 +29,12 @@ constexpr int IN_W = BT + 2 * HX;                   // 120
 constexpr int IN_H = BT + 2 * H;                    // 118
 constexpr int IS = IN_W + 1;                        // integral-image row stride (odd -> conflict-free column scans)
 constexpr uint32_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
-constexpr size_t SMEM = STAGE + (size_t)(IN_H + 1) * IS * sizeof(double);
+constexpr int NSEG = 4, SEG_ROWS = (IN_H + NSEG - 1) / NSEG;          // column scans run as NSEG row segments
+constexpr size_t I_BYTES = (size_t)(IN_H + 1) * IS * sizeof(double);
+constexpr size_t CTR_BYTES = (size_t)BT * BT * sizeof(float);
+constexpr size_t OFF_BYTES = (size_t)NSEG * IN_W * sizeof(double);
+constexpr size_t SMEM = STAGE + I_BYTES + CTR_BYTES + OFF_BYTES;
+static_assert(NSEG * IN_W <= BNT, "one thread per (segment, column)");
 
 __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                         const uint8_t* __restrict__ mask_prev, int64_t prev_pitch,
@@ -38,34 +43,70 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
                                                         int64_t nx, float factor, int tiles_x, int ntiles)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bar;
+    const float* tile = reinterpret_cast<const float*>(smem);
     double* I = reinterpret_cast<double*>(smem + STAGE);       // [(IN_H + 1)][IS], I[r][c] = sum tile[<r][<c]
-    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * 4), HX, H}};
+    float* ctrs = reinterpret_cast<float*>(smem + STAGE + I_BYTES);             // the tile's own 64 x 64 cells
+    double* off = reinterpret_cast<double*>(smem + STAGE + I_BYTES + CTR_BYTES);   // [NSEG][IN_W] segment offsets
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int t = threadIdx.x; t < IS; t += BNT) I[t] = 0.0;                    // row 0
     for (int t = threadIdx.x; t <= IN_H; t += BNT) I[t * IS] = 0.0;            // column 0
-    tile_loop<1, 1>(smem, STAGE, bars, planes, BT, BT, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
-        const float* tile = reinterpret_cast<const float*>(st);
-        // ---- integral image, two serial passes with conflict-free access patterns ---------------------------------
-        // pass 1: one thread per tile COLUMN runs down the rows (lanes = consecutive columns);
-        //         I[r+1][c+1] = sum_{r' <= r} tile[r'][c]
-        if (threadIdx.x < IN_W) {
-            const int c = threadIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tm_in);
+    }
+    __syncthreads();
+    auto issue = [&](int tl) {
+        const int ty0 = (tl / tiles_x) * BT, tx0 = (tl % tiles_x) * BT;
+        mbar_arrive_expect_tx(&bar, (uint32_t)(IN_W * IN_H * 4));
+        tma_load_2d(smem, &tm_in, tx0 - HX, ty0 - H, &bar);
+    };
+    if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x);
+    int k = 0;
+    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
+        const int ty0 = (tl / tiles_x) * BT, tx0 = (tl % tiles_x) * BT;
+        mbar_wait(&bar, k & 1);
+        // ---- pass 1: column sums, one thread per (row segment, column); lanes = consecutive columns -----------------
+        //      I[r+1][c+1] = sum of tile[r'][c] over the rows r' <= r of the SAME segment, off = totals of the segments above
+        if (threadIdx.x < NSEG * IN_W) {
+            const int seg = threadIdx.x / IN_W, c = threadIdx.x - seg * IN_W;
+            const int r0 = seg * SEG_ROWS, r1 = r0 + SEG_ROWS < IN_H ? r0 + SEG_ROWS : IN_H;
             double acc = 0.0;
-#pragma unroll 8
-            for (int r = 0; r < IN_H; ++r) {
+#pragma unroll 6
+            for (int r = r0; r < r1; ++r) {
                 acc += (double)tile[r * IN_W + c];
                 I[(r + 1) * IS + c + 1] = acc;
             }
+            off[seg * IN_W + c] = acc;
+        }
+#pragma unroll
+        for (int rep = 0; rep < BT * BT / BNT; ++rep) {
+            const int idx = rep * BNT + threadIdx.x;
+            ctrs[idx] = tile[(idx / BT + H) * IN_W + (idx % BT) + XOFF + H];
         }
         __syncthreads();
-        // pass 2: one thread per ROW runs along the columns (lanes = consecutive rows; the odd stride IS keeps the
-        //         64-bit accesses on distinct banks)
+        // the staged tile is no longer needed: fetch the next one underneath the rest of this tile's work
+        if (threadIdx.x == 0 && tl + (int)gridDim.x < ntiles) issue(tl + gridDim.x);
+        if (threadIdx.x < IN_W) {                                  // segment totals -> exclusive offsets
+            double run = 0.0;
+#pragma unroll
+            for (int sg = 0; sg < NSEG; ++sg) {
+                const double tot = off[sg * IN_W + threadIdx.x];
+                off[sg * IN_W + threadIdx.x] = run;
+                run += tot;
+            }
+        }
+        __syncthreads();
+        // ---- pass 2: row prefix sums, one thread per ROW runs along the columns (lanes = consecutive rows; the odd
+        //      stride IS keeps the 64-bit accesses on distinct banks); the segment offsets of pass 1 are added on the way
         if (threadIdx.x < IN_H) {
             double* row = I + (threadIdx.x + 1) * IS + 1;
+            const double* o = off + (threadIdx.x / SEG_ROWS) * IN_W;
             double acc = 0.0;
 #pragma unroll 8
             for (int c = 0; c < IN_W; ++c) {
-                acc += row[c];
+                acc += row[c] + o[c];
                 row[c] = acc;
             }
         }
@@ -88,13 +129,14 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
             };
             const int cnt = span(y, ny, H) * span(x, nx, H) - span(y, ny, HI) * span(x, nx, HI);
             const float mean = (float)((big - inner) / (double)cnt);               // np.nanmean -> float32  (:421)
-            const float ctr = tile[(ro + H) * IN_W + c0 + H];
+            const float ctr = ctrs[idx];
             const bool hit = ctr > __fmul_rn(factor, mean);                        // centre > 4 * mean      (:424)
             const uint8_t prev = mask_prev ? mask_prev[y * prev_pitch + x] : (uint8_t)0;
             mask_out[y * mask_pitch + x] = (uint8_t)(prev + (hit ? 1 : 0));        // final_mask += filtered (:461)
             modified[y * mod_pitch + x] = __fmul_rn(ctr, hit ? 0.f : 1.f);         // image * (1 - mask)     (:426)
         }
-    });
+        __syncthreads();                                           // I, ctrs and off are rewritten by the next tile
+    }
 }
 
 // ---- mask assembly ------------------------------------------------------------------------------------------
@@ -106,9 +148,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(const uint8_t* __restrict
                                                        int64_t out_pitch, int ny, int nx, int margin, int invert)
 {
     const int my = ny / 2, y_odd = ny & 1, mx = nx / 2, x_odd = nx & 1;
-    const int64_t total = (int64_t)ny * nx;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int y = (int)(t / nx), x = (int)(t - (int64_t)y * nx);
+    for (CellIter it(nx); it.y < ny; it.next()) {
+        const int y = (int)it.y, x = (int)it.x;
         int v = 0;
         // position inside one of the four (my, mx) blocks, or -1 on the odd middle row / column
         int by = -1, bx = -1, top = 0, left = 0;

@@ -46,9 +46,8 @@ __global__ void __launch_bounds__(256) elementwise_kernel(int op, const void* __
                                                           int64_t b_pitch, double b_scalar, void* __restrict__ out,
                                                           int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx)
 {
-    const int64_t total = ny * nx;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t y = t / nx, x = t - y * nx;
+    for (CellIter it(nx); it.y < ny; it.next()) {
+        const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
         const int64_t ia = y * a_pitch + x, io = y * out_pitch + x;
         if (op == HD_OP_XOR) {
             const int64_t va = load_int(a, a_dtype, ia);
@@ -118,9 +117,8 @@ __global__ void __launch_bounds__(256) final_terms_kernel(const SrtmT* __restric
                                                           const float* __restrict__ rivers, int64_t riv_pitch,
                                                           OutT* __restrict__ out, int64_t out_pitch, int64_t ny, int64_t nx)
 {
-    const int64_t total = ny * nx;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t y = t / nx, x = t - y * nx;
+    for (CellIter it(nx); it.y < ny; it.next()) {
+        const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
         const double s = (double)srtm[y * srtm_pitch + x];
         const double lv = (double)lagoons[y * lag_pitch + x];
         const double r = rivers ? (double)rivers[y * riv_pitch + x] : 0.0;

@@ -37,16 +37,16 @@ struct FillCounters { int changed_tiles; int pad[3]; };
 __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
                                                         int64_t w_pitch, int64_t ny, int64_t nx, int top_is_halo = 0,
                                                         int bottom_is_halo = 0, int* __restrict__ tile_has_nodata = nullptr,
-                                                        int tiles_x = 0)
+                                                        int tiles_x = 0, int* __restrict__ any_nodata = nullptr)
 {
-    const int64_t total = ny * nx;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t y = t / nx, x = t - y * nx;
+    for (CellIter it(nx); it.y < ny; it.next()) {
+        const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
         const float v = z[y * z_pitch + x];
         float r = __int_as_float(0x7f800000);                                    // +inf inside
         if (v != v) {
             r = __int_as_float(0xff800000);                                      // nodata: outlet at -inf
             if (tile_has_nodata) tile_has_nodata[(y / FT) * tiles_x + (x / FT)] = 1;   // benign race: every writer stores 1
+            if (any_nodata) *any_nodata = 1;
         }
         else if ((y == 0 && !top_is_halo) || x == 0 || (y == ny - 1 && !bottom_is_halo) || x == nx - 1)
             r = v;                                                               // frame: W = z (a band's halo rows are not frame)
@@ -55,11 +55,12 @@ __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) fill_finish_kernel(const float* __restrict__ z, int64_t z_pitch,
-                                                          float* __restrict__ w, int64_t w_pitch, int64_t ny, int64_t nx)
+                                                          float* __restrict__ w, int64_t w_pitch, int64_t ny, int64_t nx,
+                                                          const int* __restrict__ any_nodata = nullptr)
 {
-    const int64_t total = ny * nx;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t y = t / nx, x = t - y * nx;
+    if (any_nodata && *any_nodata == 0) return;          // fill_init_kernel saw no nodata cell: nothing to restore
+    for (CellIter it(nx); it.y < ny; it.next()) {
+        const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
         const float v = z[y * z_pitch + x];
         if (v != v) w[y * w_pitch + x] = v;                                      // nodata stays nodata
     }
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(FNT) fill_sweep_kernel(const __grid_constant__
 struct FillCtl {
     int head, tail, pending, error;
     unsigned long long visits, changed_visits, iterations;
-    int qcap, pad_[3];
+    int qcap, any_nodata, pad_[2];
     unsigned long long cycles[6];     // per-phase SM cycles of thread 0, summed over visits (HD_FILL_TRACE)
 };
 constexpr int SLOT_EMPTY = -1;
@@ -484,9 +485,8 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
 __global__ void __launch_bounds__(256) d8_kernel(const float* __restrict__ w, int64_t w_pitch, uint8_t* __restrict__ out,
                                                  int64_t out_pitch, int64_t ny, int64_t nx)
 {
-    const int64_t total = ny * nx;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t y = t / nx, x = t - y * nx;
+    for (CellIter it(nx); it.y < ny; it.next()) {
+        const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
         uint8_t code = 0;
         if (y > 0 && x > 0 && y < ny - 1 && x < nx - 1) {
             const float* p = w + y * w_pitch + x;
@@ -543,7 +543,7 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     if (!(flags & 1)) {
         hd_prof_begin("fill_init_kernel", s);
         fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, flags & 2,
-                                                             flags & 4, queued, tiles_x);
+                                                             flags & 4, queued, tiles_x, &ctl->any_nodata);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
     hd_prof_begin("fill_seed_kernel", s);
@@ -556,7 +556,8 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     HD_LAUNCH_CHECK(); hd_count_launch();
     if (finish) {
         hd_prof_begin("fill_finish_kernel", s);
-        fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
+        fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx,
+                                                               (flags & 1) ? nullptr : &ctl->any_nodata);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
     if (!visits_out && !getenv("HD_FILL_TRACE")) return HD_OK;      // fully asynchronous when nobody asks for statistics

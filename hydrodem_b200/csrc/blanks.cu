@@ -17,6 +17,7 @@
 //
 // Algorithmic HBM traffic per pass: 4 B read + 4 B (modified image) + 1 B (mask) written (+1 B previous mask).
 #include "common.cuh"
+#include "tile_common.cuh"
 
 namespace {
 
@@ -36,9 +37,10 @@ constexpr size_t OFF_BYTES = (size_t)NSEG * IN_W * sizeof(double);
 constexpr size_t SMEM = STAGE + I_BYTES + CTR_BYTES + OFF_BYTES;
 static_assert(NSEG * IN_W <= BNT, "one thread per (segment, column)");
 
+template <typename MaskT>
 __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                         const uint8_t* __restrict__ mask_prev, int64_t prev_pitch,
-                                                        uint8_t* __restrict__ mask_out, int64_t mask_pitch,
+                                                        MaskT* __restrict__ mask_out, int64_t mask_pitch,
                                                         float* __restrict__ modified, int64_t mod_pitch, int64_t ny,
                                                         int64_t nx, float factor, int tiles_x, int ntiles)
 {
@@ -66,6 +68,14 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
     int k = 0;
     for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
         const int ty0 = (tl / tiles_x) * BT, tx0 = (tl % tiles_x) * BT;
+        // the previous pass's mask for this thread's outputs: requested now, needed at the very end of the tile
+        uint8_t prevs[BT * BT / BNT];
+#pragma unroll
+        for (int rep = 0; rep < BT * BT / BNT; ++rep) {
+            const int idx = rep * BNT + threadIdx.x;
+            const int64_t y = ty0 + idx / BT, x = tx0 + idx % BT;
+            prevs[rep] = (mask_prev && y < ny && x < nx) ? __ldg(mask_prev + y * prev_pitch + x) : (uint8_t)0;
+        }
         mbar_wait(&bar, k & 1);
         // ---- pass 1: column sums, one thread per (row segment, column); lanes = consecutive columns -----------------
         //      I[r+1][c+1] = sum of tile[r'][c] over the rows r' <= r of the SAME segment, off = totals of the segments above
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
         }
         __syncthreads();
         // ---- outputs ----------------------------------------------------------------------------------------
-#pragma unroll 1
+#pragma unroll
         for (int rep = 0; rep < BT * BT / BNT; ++rep) {
             const int idx = rep * BNT + threadIdx.x;
             const int ro = idx / BT, xo = idx % BT;
@@ -131,9 +141,9 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
             const float mean = (float)((big - inner) / (double)cnt);               // np.nanmean -> float32  (:421)
             const float ctr = ctrs[idx];
             const bool hit = ctr > __fmul_rn(factor, mean);                        // centre > 4 * mean      (:424)
-            const uint8_t prev = mask_prev ? mask_prev[y * prev_pitch + x] : (uint8_t)0;
-            mask_out[y * mask_pitch + x] = (uint8_t)(prev + (hit ? 1 : 0));        // final_mask += filtered (:461)
-            modified[y * mod_pitch + x] = __fmul_rn(ctr, hit ? 0.f : 1.f);         // image * (1 - mask)     (:426)
+            const uint8_t prev = prevs[rep];
+            mask_out[y * mask_pitch + x] = (MaskT)(prev + (hit ? 1 : 0));          // final_mask += filtered (:461)
+            if (modified) modified[y * mod_pitch + x] = __fmul_rn(ctr, hit ? 0.f : 1.f);   // image * (1 - mask) (:426)
         }
         __syncthreads();                                           // I, ctrs and off are rewritten by the next tile
     }
@@ -148,48 +158,67 @@ __global__ void __launch_bounds__(256) assemble_kernel(const uint8_t* __restrict
                                                        int64_t out_pitch, int ny, int nx, int margin, int invert)
 {
     const int my = ny / 2, y_odd = ny & 1, mx = nx / 2, x_odd = nx & 1;
-    for (CellIter it(nx); it.y < ny; it.next()) {
-        const int y = (int)it.y, x = (int)it.x;
-        int v = 0;
-        // position inside one of the four (my, mx) blocks, or -1 on the odd middle row / column
-        int by = -1, bx = -1, top = 0, left = 0;
+    const int nxq = (nx + 3) / 4;                                  // four consecutive cells of a row per thread
+    for (CellIter it(nxq); it.y < ny; it.next()) {
+        const int y = (int)it.y, x4 = 4 * (int)it.x;
+        // row part of the block lookup: position inside one of the (my, mx) blocks, or -1 on the odd middle row
+        int by = -1, top = 0;
         if (y < my) { by = y; top = 1; } else if (y >= my + y_odd) { by = y - my - y_odd; }
-        if (x < mx) { bx = x; left = 1; } else if (x >= mx + x_odd) { bx = x - mx - x_odd; }
-        if (by >= 0 && bx >= 0) {
-            // bottom blocks: c3 = flip(c2) sits bottom-left, c4 = flip(c1) bottom-right
-            const int qy = top ? by : my - 1 - by;
-            const int qx = top ? bx : mx - 1 - bx;
-            const bool use_first = top ? left : !left;
-            if (use_first) {
-                if (qy < my - margin && qx < mx - margin) v = m1[(int64_t)qy * p1 + qx];
-            } else {
-                if (qy < my - margin && qx >= margin) v = m2[(int64_t)qy * p2 + (qx - margin)];
+        // bottom blocks: c3 = flip(c2) sits bottom-left, c4 = flip(c1) bottom-right
+        const int qy = top ? by : my - 1 - by;
+        const bool row_ok = by >= 0 && qy < my - margin;
+        OutT res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x4 + j;
+            int v = 0;
+            if (row_ok && x < nx) {
+                int bx = -1, left = 0;
+                if (x < mx) { bx = x; left = 1; } else if (x >= mx + x_odd) { bx = x - mx - x_odd; }
+                if (bx >= 0) {
+                    const int qx = top ? bx : mx - 1 - bx;
+                    const bool use_first = top ? left : !left;
+                    if (use_first) {
+                        if (qx < mx - margin) v = m1[(int64_t)qy * p1 + qx];
+                    } else {
+                        if (qx >= margin) v = m2[(int64_t)qy * p2 + (qx - margin)];
+                    }
+                }
             }
+            res[j] = invert ? (OutT)(1 - v) : (OutT)v;
         }
-        out[(int64_t)y * out_pitch + x] = invert ? (OutT)(1 - v) : (OutT)v;
+        store4v<OutT>(out, out_pitch, y, x4, nx, res);
     }
 }
 
 }  // namespace
 
 extern "C" int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch,
-                                     void* mask_out, int64_t mask_pitch, void* modified, int64_t mod_pitch, int64_t ny,
-                                     int64_t nx, int ws, int inner, double factor, void* stream)
+                                     void* mask_out, int mask_dtype, int64_t mask_pitch, void* modified, int64_t mod_pitch,
+                                     int64_t ny, int64_t nx, int ws, int inner, double factor, void* stream)
 {
-    if (!in || !mask_out || !modified) return HD_ERR_NULL;
+    if (!in || !mask_out) return HD_ERR_NULL;
     if (ws > ny || ws > nx) return HD_ERR_WINDOW_HIGH;
     if (ws % 2 != 1) return HD_ERR_WINDOW_EVEN;
     if (ws != WS || inner != INNER) return HD_ERR_UNSUPPORTED;     // the reference hard-codes 55 / 5 (:417-419, :457)
-    if (in_pitch < nx || mask_pitch < nx || mod_pitch < nx || (mask_prev && prev_pitch < nx)) return HD_ERR_ARG;
+    if (mask_dtype != HD_U8 && mask_dtype != HD_F32) return HD_ERR_UNSUPPORTED;
+    if (in_pitch < nx || mask_pitch < nx || (modified && mod_pitch < nx) || (mask_prev && prev_pitch < nx)) return HD_ERR_ARG;
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, HD_F32, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
     const int tiles_x = hd_cdiv(nx, BT), tiles_y = hd_cdiv(ny, BT), ntiles = tiles_x * tiles_y;
-    HD_CUDA_OK(cudaFuncSetAttribute(hollow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const int grid = ntiles < hd_num_sms() ? ntiles : hd_num_sms();
     hd_prof_begin("hollow_kernel", (cudaStream_t)stream);
-    hollow_kernel<<<grid, BNT, SMEM, (cudaStream_t)stream>>>(tm, (const uint8_t*)mask_prev, prev_pitch, (uint8_t*)mask_out,
-                                                           mask_pitch, (float*)modified, mod_pitch, ny, nx, (float)factor,
-                                                           tiles_x, ntiles);
+    if (mask_dtype == HD_U8) {
+        HD_CUDA_OK(cudaFuncSetAttribute(hollow_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        hollow_kernel<uint8_t><<<grid, BNT, SMEM, (cudaStream_t)stream>>>(
+            tm, (const uint8_t*)mask_prev, prev_pitch, (uint8_t*)mask_out, mask_pitch, (float*)modified, mod_pitch, ny, nx,
+            (float)factor, tiles_x, ntiles);
+    } else {
+        HD_CUDA_OK(cudaFuncSetAttribute(hollow_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        hollow_kernel<float><<<grid, BNT, SMEM, (cudaStream_t)stream>>>(
+            tm, (const uint8_t*)mask_prev, prev_pitch, (float*)mask_out, mask_pitch, (float*)modified, mod_pitch, ny, nx,
+            (float)factor, tiles_x, ntiles);
+    }
     HD_LAUNCH_CHECK();
     hd_count_launch();
     return HD_OK;
@@ -203,7 +232,7 @@ extern "C" int hd_fourier_mask_assemble(const void* q1, int64_t q1_pitch, const 
     if (ny < 2 || nx < 2 || ny > 0x7fffffff || nx > 0x7fffffff || out_pitch < nx || margin < 0) return HD_ERR_ARG;
     if (ny / 2 - margin < 1 || nx / 2 - margin < 1) return HD_ERR_ARG;
     if (q1_pitch < nx / 2 - margin || q2_pitch < nx / 2 - margin) return HD_ERR_ARG;
-    const int64_t total = ny * nx;
+    const int64_t total = ny * ((nx + 3) / 4);
     const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
     cudaStream_t s = (cudaStream_t)stream;
 #define HD_ASM(T, TAG)                                                                                              \

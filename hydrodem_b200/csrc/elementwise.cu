@@ -3,6 +3,7 @@
 // (they are folded into the neighbouring stencil kernels) -- this entry point exists so that each
 // reference class has a device implementation behind the same Filter.apply() API.
 #include "common.cuh"
+#include "tile_common.cuh"
 
 namespace {
 
@@ -117,17 +118,30 @@ __global__ void __launch_bounds__(256) final_terms_kernel(const SrtmT* __restric
                                                           const float* __restrict__ rivers, int64_t riv_pitch,
                                                           OutT* __restrict__ out, int64_t out_pitch, int64_t ny, int64_t nx)
 {
-    for (CellIter it(nx); it.y < ny; it.next()) {
-        const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
-        const double s = (double)srtm[y * srtm_pitch + x];
-        const double lv = (double)lagoons[y * lag_pitch + x];
-        const double r = rivers ? (double)rivers[y * riv_pitch + x] : 0.0;
-        const double mask = lv > 0.0 ? 1.0 : 0.0;
-        const double first = __dmul_rn(s, 1.0 - (mask + r));
-        double acc = __dadd_rn(first, lv);
-        if (rivers) acc = __dadd_rn(acc, __dmul_rn((double)hsheds[y * hs_pitch + x], r));
-        else acc = __dadd_rn(acc, 0.0 * (double)hsheds[y * hs_pitch + x]);
-        out[y * out_pitch + x] = (OutT)acc;
+    // four consecutive cells per thread: 16-byte loads, enough of them in flight to cover the HBM latency
+    const int64_t nxq = (nx + 3) / 4;
+    for (CellIter it(nxq); it.y < ny; it.next()) {
+        const int64_t y = it.y, x = 4 * it.x;
+        SrtmT sv[4];
+        float lv4[4], hv[4], rv[4] = {0.f, 0.f, 0.f, 0.f};
+        gload4(srtm + y * srtm_pitch + x, x, nx, sv);
+        gload4(lagoons + y * lag_pitch + x, x, nx, lv4);
+        gload4(hsheds + y * hs_pitch + x, x, nx, hv);
+        if (rivers) gload4(rivers + y * riv_pitch + x, x, nx, rv);
+        OutT res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double s = (double)sv[j];
+            const double lv = (double)lv4[j];
+            const double r = rivers ? (double)rv[j] : 0.0;
+            const double mask = lv > 0.0 ? 1.0 : 0.0;
+            const double first = __dmul_rn(s, 1.0 - (mask + r));
+            double acc = __dadd_rn(first, lv);
+            if (rivers) acc = __dadd_rn(acc, __dmul_rn((double)hv[j], r));
+            else acc = __dadd_rn(acc, 0.0 * (double)hv[j]);
+            res[j] = (OutT)acc;
+        }
+        store4v<OutT>(out, out_pitch, y, x, nx, res);
     }
 }
 }  // namespace
@@ -140,7 +154,7 @@ extern "C" int hd_final_terms(const void* srtm, int srtm_dtype, int64_t srtm_pit
     if (!srtm || !lagoon_values || !hsheds_fixed || !out) return HD_ERR_NULL;
     if (ny < 1 || nx < 1 || srtm_pitch < nx || lag_pitch < nx || hs_pitch < nx || out_pitch < nx || (rivers && riv_pitch < nx))
         return HD_ERR_ARG;
-    const int64_t total = ny * nx;
+    const int64_t total = ny * ((nx + 3) / 4);
     const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
     cudaStream_t s = (cudaStream_t)stream;
 #define HD_FT(ST, STAG, OT, OTAG)                                                                                      \

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tile_common.cuh"
 
 namespace {
 
@@ -39,18 +40,31 @@ __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict_
                                                         int bottom_is_halo = 0, int* __restrict__ tile_has_nodata = nullptr,
                                                         int tiles_x = 0, int* __restrict__ any_nodata = nullptr)
 {
-    for (CellIter it(nx); it.y < ny; it.next()) {
-        const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
-        const float v = z[y * z_pitch + x];
-        float r = __int_as_float(0x7f800000);                                    // +inf inside
-        if (v != v) {
-            r = __int_as_float(0xff800000);                                      // nodata: outlet at -inf
-            if (tile_has_nodata) tile_has_nodata[(y / FT) * tiles_x + (x / FT)] = 1;   // benign race: every writer stores 1
+    const int64_t nxq = (nx + 3) / 4;                                            // four consecutive cells per thread
+    for (CellIter it(nxq); it.y < ny; it.next()) {
+        const int64_t y = it.y, x0 = 4 * it.x;
+        float v4[4], r4[4];
+        gload4(z + y * z_pitch + x0, x0, nx, v4);
+        const bool yframe = (y == 0 && !top_is_halo) || (y == ny - 1 && !bottom_is_halo);
+        bool nodata = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t x = x0 + j;
+            const float v = v4[j];
+            float r = __int_as_float(0x7f800000);                                // +inf inside
+            if (v != v) {
+                r = __int_as_float(0xff800000);                                  // nodata: outlet at -inf
+                nodata |= x < nx;
+            }
+            else if (yframe || x == 0 || x == nx - 1)
+                r = v;                                                           // frame: W = z (a band's halo rows are not frame)
+            r4[j] = r;
+        }
+        if (nodata) {
+            if (tile_has_nodata) tile_has_nodata[(y / FT) * tiles_x + (x0 / FT)] = 1;   // benign race: every writer stores 1
             if (any_nodata) *any_nodata = 1;
         }
-        else if ((y == 0 && !top_is_halo) || x == 0 || (y == ny - 1 && !bottom_is_halo) || x == nx - 1)
-            r = v;                                                               // frame: W = z (a band's halo rows are not frame)
-        w[y * w_pitch + x] = r;
+        store4<float>(w, w_pitch, y, x0, nx, r4);
     }
 }
 
@@ -485,23 +499,42 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
 __global__ void __launch_bounds__(256) d8_kernel(const float* __restrict__ w, int64_t w_pitch, uint8_t* __restrict__ out,
                                                  int64_t out_pitch, int64_t ny, int64_t nx)
 {
-    for (CellIter it(nx); it.y < ny; it.next()) {
-        const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
-        uint8_t code = 0;
-        if (y > 0 && x > 0 && y < ny - 1 && x < nx - 1) {
-            const float* p = w + y * w_pitch + x;
-            const float c = p[0];
-            const float nb[8] = {p[1], p[w_pitch + 1], p[w_pitch], p[w_pitch - 1], p[-1], p[-w_pitch - 1], p[-w_pitch],
-                                 p[-w_pitch + 1]};
-            float best = 0.f;
+    // four consecutive cells per thread: three rows of (left neighbour, aligned quad, right neighbour)
+    const int64_t nxq = (nx + 3) / 4;
+    for (CellIter it(nxq); it.y < ny; it.next()) {
+        const int64_t y = it.y, x0 = 4 * it.x;
+        uint8_t codes[4] = {0, 0, 0, 0};
+        if (y > 0 && y < ny - 1) {
+            float win[3][6];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float drop = __fsub_rn(c, nb[k]);
-                if (k & 1) drop = __fmul_rn(drop, 0.70710678f);
-                if (drop > best) { best = drop; code = (uint8_t)(1u << k); }
+            for (int dy = 0; dy < 3; ++dy) {
+                const float* p = w + (y + dy - 1) * w_pitch + x0;
+                float q[4];
+                gload4(p, x0, nx, q);
+                win[dy][0] = x0 > 0 ? __ldg(p - 1) : 0.f;
+                win[dy][1] = q[0]; win[dy][2] = q[1]; win[dy][3] = q[2]; win[dy][4] = q[3];
+                win[dy][5] = x0 + 4 < nx ? __ldg(p + 4) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t x = x0 + j;
+                if (x == 0 || x >= nx - 1) continue;
+                const float c = win[1][j + 1];
+                // E, SE, S, SW, W, NW, N, NE
+                const float nb[8] = {win[1][j + 2], win[2][j + 2], win[2][j + 1], win[2][j], win[1][j], win[0][j],
+                                     win[0][j + 1], win[0][j + 2]};
+                float best = 0.f;
+                uint8_t code = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float drop = __fsub_rn(c, nb[k]);
+                    if (k & 1) drop = __fmul_rn(drop, 0.70710678f);
+                    if (drop > best) { best = drop; code = (uint8_t)(1u << k); }
+                }
+                codes[j] = code;
             }
         }
-        out[y * out_pitch + x] = code;
+        store4v<uint8_t>(out, out_pitch, y, x0, nx, codes);
     }
 }
 
@@ -542,7 +575,7 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     HD_LAUNCH_CHECK();
     if (!(flags & 1)) {
         hd_prof_begin("fill_init_kernel", s);
-        fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, flags & 2,
+        fill_init_kernel<<<stream_grid(ny * ((nx + 3) / 4)), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, flags & 2,
                                                              flags & 4, queued, tiles_x, &ctl->any_nodata);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
@@ -606,7 +639,7 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
     HD_CUDA_OK(cudaFuncSetAttribute(fill_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     hd_prof_begin("fill_init_kernel", s);
-    fill_init_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
+    fill_init_kernel<<<stream_grid(ny * ((nx + 3) / 4)), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx);
     HD_LAUNCH_CHECK(); hd_count_launch();
     // every tile starts active
     HD_CUDA_OK(cudaMemsetAsync(flags_a, 1, (size_t)ntiles * sizeof(int), s));   // any non-zero byte pattern = active
@@ -672,7 +705,7 @@ extern "C" int hd_d8(const void* w, int64_t w_pitch, void* out, int64_t out_pitc
     if (!w || !out) return HD_ERR_NULL;
     if (ny < 1 || nx < 1 || w_pitch < nx || out_pitch < nx) return HD_ERR_ARG;
     hd_prof_begin("d8_kernel", (cudaStream_t)stream);
-    d8_kernel<<<stream_grid(ny * nx), 256, 0, (cudaStream_t)stream>>>((const float*)w, w_pitch, (uint8_t*)out, out_pitch, ny,
+    d8_kernel<<<stream_grid(ny * ((nx + 3) / 4)), 256, 0, (cudaStream_t)stream>>>((const float*)w, w_pitch, (uint8_t*)out, out_pitch, ny,
                                                                     nx);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;

@@ -30,10 +30,10 @@ struct QuadParams {
 };
 
 template <int H, typename T, typename OutT, bool GROVES>
-__global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ CUtensorMap tm_in, OutT* __restrict__ out,
-                                                       int64_t out_pitch, const uint8_t* __restrict__ groves,
-                                                       int64_t groves_pitch, int64_t ny, int64_t nx, QuadParams p,
-                                                       int tiles_x, int ntiles)
+__global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                       const __grid_constant__ CUtensorMap tm_groves,
+                                                       OutT* __restrict__ out, int64_t out_pitch, int64_t ny, int64_t nx,
+                                                       QuadParams p, int tiles_x, int ntiles)
 {
     constexpr int WS = 2 * H + 1;
     constexpr int CWU = TW + 2 * H;                 // window columns touched by a tile
@@ -43,20 +43,24 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
     constexpr int XOFF = HX - H;
     constexpr int IN_W = TW + 2 * HX;
     constexpr int IN_H = TH + 2 * H;
-    constexpr uint32_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128;
+    constexpr uint32_t IN_BYTES = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128;
+    constexpr uint32_t STAGE = IN_BYTES + (GROVES ? TH * TW : 0);     // + the tile's groves mask (uint8), staged by TMA too
+    constexpr int NP = GROVES ? 2 : 1;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
     __shared__ float s_ref;
-    __shared__ uint32_t s_groves[GROVES ? TH * TW / 4 : 1];     // the tile's groves mask, four cells per word
     float* v1 = reinterpret_cast<float*>(smem + 2 * STAGE);     // [TH][CW]  sum_dy (w - ref)
     float* vyy = v1 + TH * CW;                                   // [TH][CW]  sum_dy y^2 (w - ref)
     float c2f[WS];
 #pragma unroll
     for (int k = 0; k < WS; ++k) c2f[k] = (float)p.c2[k];        // squared half-integers: exact in float32
 
-    const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * sizeof(T)), HX, H}};
-    tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+    const TilePlane planes[2] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * sizeof(T)), HX, H},
+                                 {&tm_groves, IN_BYTES, (uint32_t)(TH * TW), 0, 0}};
+    const TilePlane (&used)[NP] = reinterpret_cast<const TilePlane (&)[NP]>(planes);
+    tile_loop<NP>(smem, STAGE, bars, used, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const T* tile = reinterpret_cast<const T*>(st);
+        const uint32_t* gwords = reinterpret_cast<const uint32_t*>(st + IN_BYTES);   // [TH][TW / 4], zero outside the raster
         // Groves tail: where groves == 0 the reference evaluates smooth + 1 * (dem - smooth), i.e. dem to the last bit or
         // two -- those cells are copied, and a tile without a single groves cell (most of them: groves cover about one
         // per cent of a scene) skips both filter passes.
@@ -67,16 +71,7 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
                 const int idx = rep * NT + threadIdx.x;
                 const int ro = idx >> 5, c4 = idx & 31;
                 const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
-                uint32_t g = 0u;
-                if (y < ny && x < nx) {
-                    const uint8_t* pg = groves + y * groves_pitch + x;
-                    if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(pg) & 3) == 0)) {
-                        g = __ldg(reinterpret_cast<const uint32_t*>(pg));
-                    } else {
-                        for (int j = 0; j < 4 && x + j < nx; ++j) g |= (uint32_t)__ldg(pg + j) << (8 * j);
-                    }
-                }
-                s_groves[idx] = g;                                  // read back by this same thread only
+                const uint32_t g = (y < ny && x < nx) ? gwords[idx] : 0u;
                 any |= g != 0u;
             }
             if (!__syncthreads_or(any)) {
@@ -129,7 +124,7 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
             const int ro = idx >> 5, c4 = idx & 31;
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
-            const uint32_t gq = GROVES ? s_groves[idx] : 0u;
+            const uint32_t gq = GROVES ? gwords[idx] : 0u;
             if (GROVES && gq == 0u) {                     // no groves cell in this quad: copy
                 OutT cp[4];
 #pragma unroll
@@ -186,16 +181,18 @@ int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_p
            int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t stream)
 {
     constexpr int CW = (TW + 2 * H + 3) / 4 * 4 + 4, IN_W = TW + 2 * hd_halo_x(H, sizeof(T)), IN_H = TH + 2 * H;
-    constexpr size_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128;
+    constexpr size_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128 + (GROVES ? TH * TW : 0);
     constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * sizeof(float);
-    CUtensorMap tm;
+    CUtensorMap tm, tm_g;
     if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
+    tm_g = tm;
+    if (GROVES)
+        if (int e = hd_make_tmap_2d(&tm_g, groves, HD_U8, ny, nx, groves_pitch, TW, TH, false)) return e;
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
     auto kern = quadratic_kernel<H, T, OutT, GROVES>;
     HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     hd_prof_begin("quadratic_kernel", stream);
-    kern<<<grid_for(ntiles, 2), NT, SMEM, stream>>>(tm, (OutT*)out, out_pitch, (const uint8_t*)groves, groves_pitch, ny, nx,
-                                                    p, tiles_x, ntiles);
+    kern<<<grid_for(ntiles, 2), NT, SMEM, stream>>>(tm, tm_g, (OutT*)out, out_pitch, ny, nx, p, tiles_x, ntiles);
     HD_LAUNCH_CHECK();
     hd_count_launch();
     return HD_OK;

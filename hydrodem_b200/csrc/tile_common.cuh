@@ -63,6 +63,41 @@ template <> __device__ __forceinline__ void store4v<double>(double* p, int64_t p
     }
 }
 
+template <> __device__ __forceinline__ void store4v<uint8_t>(uint8_t* p, int64_t pitch, int64_t y, int64_t x, int64_t nx,
+                                                             const uint8_t (&v)[4])
+{
+    uint8_t* q = p + y * pitch + x;
+    if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+        *reinterpret_cast<uint32_t*>(q) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    } else {
+        for (int j = 0; j < 4; ++j)
+            if (x + j < nx) q[j] = v[j];
+    }
+}
+
+// four consecutive cells starting at p (column x of a row of nx cells) straight from global memory; cells past the
+// end of the row read as 0.  One 16-byte load when the address allows it.
+__device__ __forceinline__ void gload4(const float* p, int64_t x, int64_t nx, float (&v)[4])
+{
+    if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (x + j < nx) ? __ldg(p + j) : 0.f;
+    }
+}
+__device__ __forceinline__ void gload4(const double* p, int64_t x, int64_t nx, double (&v)[4])
+{
+    if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (x + j < nx) ? __ldg(p + j) : 0.0;
+    }
+}
+
 __device__ __forceinline__ int reflect_idx(int64_t i, int64_t n)
 {
     if (i < 0) i = -i - 1;

@@ -317,13 +317,15 @@ BLANKS_INNER = 5               # BlanksFourier (custom_filters.py:419)
 BLANKS_FACTOR = 4.0            # centre > 4 * mean (custom_filters.py:424)
 
 
-def _hollow_pass(src_f32, prev_mask, window_size):
-    """One BlanksFourier pass on the device -> (accumulated mask U8, modified image F32)."""
-    mask = dev.empty(src_f32.ny, src_f32.nx, _lib.U8, np.float64)
-    mod = dev.empty(src_f32.ny, src_f32.nx, _lib.F32, np.float64)
+def _hollow_pass(src_f32, prev_mask, window_size, last=False):
+    """One BlanksFourier pass on the device -> (accumulated mask, modified image F32).  ``last``: the mask is
+    stored as float32 (what IsolatedPoints reads next) and the modified image is not written."""
+    mask = dev.empty(src_f32.ny, src_f32.nx, _lib.F32 if last else _lib.U8, np.float64)
+    mod = None if last else dev.empty(src_f32.ny, src_f32.nx, _lib.F32, np.float64)
     pp, ppitch = (prev_mask.ptr, prev_mask.pitch) if prev_mask is not None else (None, 0)
-    _lib.check(_lib.load().hd_hollow_mean_detect(src_f32.ptr, src_f32.pitch, pp, ppitch, mask.ptr, mask.pitch, mod.ptr,
-                                                 mod.pitch, src_f32.ny, src_f32.nx, int(window_size), BLANKS_INNER,
+    mp, mpitch = (mod.ptr, mod.pitch) if mod is not None else (None, 0)
+    _lib.check(_lib.load().hd_hollow_mean_detect(src_f32.ptr, src_f32.pitch, pp, ppitch, mask.ptr, mask.dtype, mask.pitch,
+                                                 mp, mpitch, src_f32.ny, src_f32.nx, int(window_size), BLANKS_INNER,
                                                  BLANKS_FACTOR, dev.stream_ptr()),
                window_size=window_size, shape=src_f32.shape)
     return mask, mod
@@ -357,7 +359,7 @@ class DetectBlanksFourier(WindowFilter):
         check_window(raster.shape, BLANKS_WINDOW)
         src = as_f32(raster)
         mask, mod = _hollow_pass(src, None, BLANKS_WINDOW)
-        mask, _ = _hollow_pass(mod, mask, BLANKS_WINDOW)
+        mask, _ = _hollow_pass(mod, mask, BLANKS_WINDOW, last=True)
         return mask
 
 

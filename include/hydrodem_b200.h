@@ -140,11 +140,12 @@ int hd_median(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, in
 
 /* ---- Fourier stripe removal (filters/custom_filters.py:369-462, :834-1101) ------------------------ */
 /* BlanksFourier.apply, custom_filters.py:395-427 (ws = 55, inner = 5 as hard-coded there, :417-419, :457).
- * in: F32 spectrum quarter.  mask_out (U8) = mask_prev (U8, may be NULL) + (centre > factor * hollow mean);
- * modified (F32) = in * (1 - hit).  The window is clipped to the raster; the centre 5x5 block is excluded. */
+ * in: F32 spectrum quarter.  mask_out (U8 or F32, `mask_dtype`) = mask_prev (U8, may be NULL) + (centre > factor *
+ * hollow mean); modified (F32, may be NULL) = in * (1 - hit).  The window is clipped to the raster; the centre 5x5
+ * block is excluded. */
 int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch, void* mask_out,
-                          int64_t mask_pitch, void* modified, int64_t mod_pitch, int64_t ny, int64_t nx, int ws, int inner,
-                          double factor, void* stream);
+                          int mask_dtype, int64_t mask_pitch, void* modified, int64_t mod_pitch, int64_t ny, int64_t nx,
+                          int ws, int inner, double factor, void* stream);
 /* FourierProcessQuarters._fill_complete_quarters / _getting_reversed_masks / _fill_complete_mask,
  * custom_filters.py:968-1050.  q1, q2: U8 masks of the two upper quarters, each (ny/2 - margin, nx/2 - margin);
  * out (U8 / F32 / F64, ny x nx) = assembled point-symmetric mask, or 1 - mask when `invert`. */

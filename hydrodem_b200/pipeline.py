@@ -110,14 +110,16 @@ class _StreamSlot:
         self.outputs = [("final", "final32", np.float64)]
         if chain.with_hydrology:
             self.outputs += [("filled", "filled", np.float32), ("d8", "d8", np.uint8)]
-        # dense staging on the device: 1-D PCIe copies run ~4 % (float) to 2x (uint8, 3601-byte rows) faster than
-        # pitched 2-D ones; the re-pitching is a device-side copy on the copy stream
+        # Rasters travel as dense 1-D copies: with both PCIe directions busy, pitched 2-D copies reach 72 GB/s in total,
+        # dense ones 95 GB/s (uint8 rows of 3601 bytes: half the rate even alone).  Re-pitching / packing is a small
+        # device copy on the COMPUTE stream, so the copy streams carry nothing but DMA -- a kernel there would have
+        # to wait for a gap between the chain's kernels and hold up the copies queued behind it.
         self.dense_in = {n: torch.empty(r.ny * r.nx, dtype=r.buf.dtype, device=r.buf.device)
                          for n, r in self.inputs.items()}
         self.dense_out = {src: torch.empty(st[src].ny * st[src].nx, dtype=st[src].buf.dtype, device=st[src].buf.device)
                           for _, src, _ in self.outputs}
-        self.transfer_bytes = (sum(t.numel() * t.element_size() for t in self.dense_in.values()),
-                               sum(t.numel() * t.element_size() for t in self.dense_out.values()))
+        size = lambda r: r.ny * r.nx * r.buf.element_size()
+        self.transfer_bytes = (sum(size(r) for r in self.inputs.values()), sum(size(st[src]) for _, src, _ in self.outputs))
         local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
         self.host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(local, 1)))
         self.ev_compute = self.ev_down = None
@@ -144,14 +146,17 @@ class _StreamSlot:
                 host = pin
             keep.append(host)
             raster = self.inputs[name]
-            dense = self.dense_in[name]
-            nbytes = dense.numel() * dense.element_size()
-            _lib.check(lib.hd_memcpy2d_h2d(ctypes.c_void_p(dense.data_ptr()), nbytes, ctypes.c_void_p(host.ctypes.data),
-                                           nbytes, nbytes, 1, ctypes.c_void_p(up.cuda_stream)))
-            with torch.cuda.stream(up):
-                raster.tensor().copy_(dense.view(raster.ny, raster.nx))
-                ready[name] = torch.cuda.Event()
-                ready[name].record(up)
+            es = host.dtype.itemsize
+            dense = self.dense_in.get(name)
+            if dense is None:                                         # (no staging buffer: pitched DMA into the raster)
+                _lib.check(lib.hd_memcpy2d_h2d(raster.ptr, raster.pitch * es, ctypes.c_void_p(host.ctypes.data),
+                                               raster.nx * es, raster.nx * es, raster.ny, ctypes.c_void_p(up.cuda_stream)))
+            else:                                                     # dense DMA, re-pitched on the compute stream
+                nbytes = dense.numel() * dense.element_size()
+                _lib.check(lib.hd_memcpy2d_h2d(ctypes.c_void_p(dense.data_ptr()), nbytes, ctypes.c_void_p(host.ctypes.data),
+                                               nbytes, nbytes, 1, ctypes.c_void_p(up.cuda_stream)))
+            ready[name] = torch.cuda.Event()
+            ready[name].record(up)
         if "rivers" in ready:
             ready["hsheds"] = ready["rivers"]                         # uploaded last: covers both
         if self.ev_down is not None:
@@ -160,21 +165,36 @@ class _StreamSlot:
 
         def send(name, src, np_dtype):
             raster = self.st[src]
+            dense = self.dense_out.get(src)
+            if dense is not None:                                     # packed on the compute stream, dense DMA
+                with torch.cuda.stream(cur):
+                    dense.view(raster.ny, raster.nx).copy_(raster.tensor())
             ev = torch.cuda.Event()
             ev.record(cur)
             down.wait_event(ev)
-            dense = self.dense_out[src]
-            with torch.cuda.stream(down):
-                dense.view(raster.ny, raster.nx).copy_(raster.tensor())
             # plain pinned arrays + the library's copy: torch's host allocator then has no pending events on them
             # and hands the same blocks out again at once
             host = dev.pinned_empty(raster.shape, dev._HD2NP[raster.dtype])
-            nbytes = dense.numel() * dense.element_size()
-            _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(host.ctypes.data), nbytes, ctypes.c_void_p(dense.data_ptr()),
-                                           nbytes, nbytes, 1, ctypes.c_void_p(down.cuda_stream)))
+            es = host.dtype.itemsize
+            if dense is None:
+                _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(host.ctypes.data), raster.nx * es, raster.ptr,
+                                               raster.pitch * es, raster.nx * es, raster.ny,
+                                               ctypes.c_void_p(down.cuda_stream)))
+            else:
+                nbytes = dense.numel() * dense.element_size()
+                _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(host.ctypes.data), nbytes, ctypes.c_void_p(dense.data_ptr()),
+                                               nbytes, nbytes, 1, ctypes.c_void_p(down.cuda_stream)))
             done = torch.cuda.Event()
             done.record(down)
             pending[name] = (host, done, np.dtype(np_dtype))
+
+        def arrived(name):
+            cur.wait_event(ready[name])
+            for n in (("hsheds", "rivers") if name == "hsheds" else (name,)):
+                if n in self.dense_in and n in ready:
+                    r = self.inputs[n]
+                    with torch.cuda.stream(cur):
+                        r.tensor().copy_(self.dense_in[n].view(r.ny, r.nx))
 
         trace = getattr(self.chain, "_trace", None)                   # tools/e2e_prof.py: per-tile compute spans
         if trace is not None:
@@ -184,7 +204,7 @@ class _StreamSlot:
             marks = [t_begin]
         for needs, g in self.segments:
             if needs is not None:
-                cur.wait_event(ready[needs])
+                arrived(needs)
             g.replay()
             if trace is not None:
                 marks.append(torch.cuda.Event(enable_timing=True))

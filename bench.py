@@ -332,7 +332,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "for out in hydrodem_b200.pipeline.ConditioningChain.stream(tiles): out = {final, filled, d8} "
-                           "ndarrays; {args.stream_depth} slots, copies of neighbouring steps overlap the kernels",
+                           f"ndarrays; {args.stream_depth} slots, copies of neighbouring steps overlap the kernels",
                     "single_tile_latency_ms": single_ms,
                     "single_tile_api": "ConditioningChain.apply_to_host(srtm, groves, hsheds)"},
             "gpu_launches": launches, "launches_per_step": launches / args.steps,

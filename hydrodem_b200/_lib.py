@@ -37,6 +37,8 @@ SIGNATURES = {
     "hd_memcpy2d_d2h": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_stream_synchronize": (_i, [_p]),
     "hd_host_widen_f32_f64": (_i, [_p, _p, _i64, _i]),
+    "hd_host_widen_i16": (_i, [_p, _i, _p, _i64, _i]),
+    "hd_pack_i16": (_i, [_p, _i64, _p, _i64, _i64, _p, _p]),
     "hd_elementwise": (_i, [_i, _p, _i, _i64, _p, _i, _i64, _d, _p, _i, _i64, _i64, _i64, _p]),
     "hd_final_terms": (_i, [_p, _i, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _p]),
     "hd_expand": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i64, _i, _p]),

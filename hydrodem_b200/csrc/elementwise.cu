@@ -173,3 +173,44 @@ extern "C" int hd_final_terms(const void* srtm, int srtm_dtype, int64_t srtm_pit
 #undef HD_FT
     return HD_ERR_UNSUPPORTED;
 }
+
+// ---- lossless int16 transport of integer-valued float rasters (host API) -----------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) pack_i16_kernel(const float* __restrict__ src, int64_t src_pitch,
+                                                       int16_t* __restrict__ dst, int64_t ny, int64_t nx,
+                                                       int* __restrict__ inexact)
+{
+    const int64_t nxq = (nx + 3) / 4;
+    bool bad = false;
+    for (CellIter it(nxq); it.y < ny; it.next()) {
+        const int64_t y = it.y, x = 4 * it.x;
+        float v[4];
+        gload4(src + y * src_pitch + x, x, nx, v);
+        int16_t* q = dst + y * nx + x;                        // dense rows
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (x + j >= nx) break;
+            const float r = rintf(v[j]);
+            bad |= !(r == v[j] && r >= -32768.f && r <= 32767.f);      // NaN, fractions and out-of-range values
+            q[j] = (int16_t)(int)fminf(fmaxf(r, -32768.f), 32767.f);
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *inexact = 1;
+}
+}  // namespace
+
+extern "C" int hd_pack_i16(const void* src, int64_t src_pitch, void* dst_dense, int64_t ny, int64_t nx, int* inexact_flag,
+                           void* stream)
+{
+    if (!src || !dst_dense || !inexact_flag) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || src_pitch < nx) return HD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    HD_CUDA_OK(cudaMemsetAsync(inexact_flag, 0, sizeof(int), s));
+    const int64_t total = ny * ((nx + 3) / 4);
+    const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    hd_prof_begin("pack_i16_kernel", s);
+    pack_i16_kernel<<<blocks, 256, 0, s>>>((const float*)src, src_pitch, (int16_t*)dst_dense, ny, nx, inexact_flag);
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}

@@ -127,6 +127,23 @@ int hd_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t ny, i
     return HD_OK;
 }
 
+template <class Work>
+static void host_parallel(int64_t n, int nthreads, Work work)
+{
+    nthreads = nthreads < 1 ? 1 : (nthreads > 64 ? 64 : nthreads);
+    if (n < (int64_t)1 << 16) nthreads = 1;
+    if (nthreads == 1) { work((int64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const int64_t chunk = ((n + nthreads - 1) / nthreads + 63) & ~(int64_t)63;
+    for (int t = 1; t < nthreads; ++t) {
+        const int64_t a = std::min(n, t * chunk), b = std::min(n, (t + 1) * chunk);
+        if (a < b) pool.emplace_back(work, a, b);
+    }
+    work((int64_t)0, std::min(n, chunk));
+    for (auto& th : pool) th.join();
+}
+
+
 extern "C" {
 
 int hd_version(void) { return 100; }
@@ -228,20 +245,18 @@ int hd_memcpy2d_d2h(void* dst, int64_t dp, const void* src, int64_t sp, int64_t 
                                  (cudaStream_t)stream));
     return HD_OK;
 }
-// Host-side widening of a float32 result to the reference's float64 (the DEM travels over PCIe as float32: half
-// the bytes; integer metres are exact in both).  Split over nthreads host threads: one core converts ~10 GB/s,
-// far below what the copy it replaces moved.
+// ---- host-side widening of results that crossed PCIe in a narrower type ----------------------------------------------
+// The final DEM and the filled DEM hold integer metres: they travel as int16 (a quarter / half of the float64 /
+// float32 bytes; the packing kernel verifies that every value is representable and the caller falls back to float32
+// otherwise) and are widened here on nthreads host threads with streaming stores (the destination is written once
+// and not read back, so the read-for-ownership of its cache lines is skipped).
 int hd_host_widen_f32_f64(double* dst, const float* src, int64_t n, int nthreads)
 {
     if (!dst || !src) return HD_ERR_NULL;
     if (n <= 0) return HD_OK;
-    nthreads = nthreads < 1 ? 1 : (nthreads > 64 ? 64 : nthreads);
-    if (n < (int64_t)1 << 16) nthreads = 1;
-    auto work = [=](int64_t a, int64_t b) {
+    host_parallel(n, nthreads, [=](int64_t a, int64_t b) {
         int64_t i = a;
 #if defined(__SSE2__)
-        // streaming stores: the destination is written once and not read back here, so skip the
-        // read-for-ownership of its cache lines (2/5 of the memory traffic of this loop)
         for (; i < b && ((uintptr_t)(dst + i) & 15); ++i) dst[i] = (double)src[i];
         for (; i + 4 <= b; i += 4) {
             const __m128 v = _mm_loadu_ps(src + i);
@@ -251,19 +266,50 @@ int hd_host_widen_f32_f64(double* dst, const float* src, int64_t n, int nthreads
         _mm_sfence();
 #endif
         for (; i < b; ++i) dst[i] = (double)src[i];
-    };
-    if (nthreads == 1) {
-        work(0, n);
-        return HD_OK;
+    });
+    return HD_OK;
+}
+
+int hd_host_widen_i16(void* dst, int dst_dtype, const int16_t* src, int64_t n, int nthreads)
+{
+    if (!dst || !src) return HD_ERR_NULL;
+    if (dst_dtype != HD_F32 && dst_dtype != HD_F64) return HD_ERR_UNSUPPORTED;
+    if (n <= 0) return HD_OK;
+    if (dst_dtype == HD_F32) {
+        float* d = (float*)dst;
+        host_parallel(n, nthreads, [=](int64_t a, int64_t b) {
+            int64_t i = a;
+#if defined(__SSE2__)
+            for (; i < b && ((uintptr_t)(d + i) & 15); ++i) d[i] = (float)src[i];
+            for (; i + 8 <= b; i += 8) {
+                const __m128i v = _mm_loadu_si128((const __m128i*)(src + i));
+                const __m128i lo = _mm_srai_epi32(_mm_unpacklo_epi16(v, v), 16), hi = _mm_srai_epi32(_mm_unpackhi_epi16(v, v), 16);
+                _mm_stream_ps(d + i, _mm_cvtepi32_ps(lo));
+                _mm_stream_ps(d + i + 4, _mm_cvtepi32_ps(hi));
+            }
+            _mm_sfence();
+#endif
+            for (; i < b; ++i) d[i] = (float)src[i];
+        });
+    } else {
+        double* d = (double*)dst;
+        host_parallel(n, nthreads, [=](int64_t a, int64_t b) {
+            int64_t i = a;
+#if defined(__SSE2__)
+            for (; i < b && ((uintptr_t)(d + i) & 15); ++i) d[i] = (double)src[i];
+            for (; i + 8 <= b; i += 8) {
+                const __m128i v = _mm_loadu_si128((const __m128i*)(src + i));
+                const __m128i lo = _mm_srai_epi32(_mm_unpacklo_epi16(v, v), 16), hi = _mm_srai_epi32(_mm_unpackhi_epi16(v, v), 16);
+                _mm_stream_pd(d + i, _mm_cvtepi32_pd(lo));
+                _mm_stream_pd(d + i + 2, _mm_cvtepi32_pd(_mm_shuffle_epi32(lo, 0xEE)));
+                _mm_stream_pd(d + i + 4, _mm_cvtepi32_pd(hi));
+                _mm_stream_pd(d + i + 6, _mm_cvtepi32_pd(_mm_shuffle_epi32(hi, 0xEE)));
+            }
+            _mm_sfence();
+#endif
+            for (; i < b; ++i) d[i] = (double)src[i];
+        });
     }
-    std::vector<std::thread> pool;
-    const int64_t chunk = ((n + nthreads - 1) / nthreads + 15) & ~(int64_t)15;
-    for (int t = 1; t < nthreads; ++t) {
-        const int64_t a = std::min(n, t * chunk), b = std::min(n, (t + 1) * chunk);
-        if (a < b) pool.emplace_back(work, a, b);
-    }
-    work(0, std::min(n, chunk));
-    for (auto& th : pool) th.join();
     return HD_OK;
 }
 

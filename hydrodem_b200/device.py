@@ -149,9 +149,10 @@ def elementwise(op, a, b, scalar, out):
 
 def pinned_empty(shape, np_dtype):
     """Pinned host array from torch's caching host allocator (returned to the cache when dropped)."""
-    t = torch.empty(shape, dtype=_HD2TORCH[hd_dtype_of(np_dtype)], pin_memory=True)
-    a = t.numpy()
-    return a.view(np.bool_) if np.dtype(np_dtype) == np.bool_ else a
+    dt = np.dtype(np_dtype)
+    tdt = torch.uint8 if dt == np.bool_ else torch.from_numpy(np.empty(0, dtype=dt)).dtype
+    a = torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+    return a.view(np.bool_) if dt == np.bool_ else a
 
 
 def download(raster, out=None):

@@ -107,19 +107,26 @@ class _StreamSlot:
         self.st = st
         # what travels down: (result name, device raster, dtype the caller gets).  The final DEM goes as float32
         # (integer metres, |z| < 2**24: exact) and is widened to the reference's float64 on the host.
-        self.outputs = [("final", "final32", np.float64)]
+        # what travels down: (result name, device raster, dtype the caller gets, int16 transport?).  The final DEM and
+        # the filled DEM hold integer metres: they cross PCIe as int16 (checked on the device: a tile with a NaN, a
+        # fraction or |z| > 32767 falls back to float32) and are widened to the reference dtypes on the host.
+        self.outputs = [("final", "final32", np.float64, True)]
         if chain.with_hydrology:
-            self.outputs += [("filled", "filled", np.float32), ("d8", "d8", np.uint8)]
+            self.outputs += [("filled", "filled", np.float32, True), ("d8", "d8", np.uint8, False)]
         # Rasters travel as dense 1-D copies: with both PCIe directions busy, pitched 2-D copies reach 72 GB/s in total,
         # dense ones 95 GB/s (uint8 rows of 3601 bytes: half the rate even alone).  Re-pitching / packing is a small
-        # device copy on the COMPUTE stream, so the copy streams carry nothing but DMA -- a kernel there would have
+        # device kernel on the COMPUTE stream, so the copy streams carry nothing but DMA -- a kernel there would have
         # to wait for a gap between the chain's kernels and hold up the copies queued behind it.
         self.dense_in = {n: torch.empty(r.ny * r.nx, dtype=r.buf.dtype, device=r.buf.device)
                          for n, r in self.inputs.items()}
-        self.dense_out = {src: torch.empty(st[src].ny * st[src].nx, dtype=st[src].buf.dtype, device=st[src].buf.device)
-                          for _, src, _ in self.outputs}
-        size = lambda r: r.ny * r.nx * r.buf.element_size()
-        self.transfer_bytes = (sum(size(r) for r in self.inputs.values()), sum(size(st[src]) for _, src, _ in self.outputs))
+        self.dense_out, self.flags = {}, {}
+        for _, src, _, narrow in self.outputs:
+            r = st[src]
+            self.dense_out[src] = torch.empty(r.ny * r.nx, dtype=torch.int16 if narrow else r.buf.dtype, device=r.buf.device)
+            if narrow:
+                self.flags[src] = torch.zeros(1, dtype=torch.int32, device=r.buf.device)
+        size = lambda t: t.numel() * t.element_size()
+        self.transfer_bytes = (sum(size(t) for t in self.dense_in.values()), sum(size(t) for t in self.dense_out.values()))
         local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
         self.host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(local, 1)))
         self.ev_compute = self.ev_down = None
@@ -163,30 +170,33 @@ class _StreamSlot:
             cur.wait_event(self.ev_down)                              # static outputs are free again
         pending = {}
 
-        def send(name, src, np_dtype):
+        def send(name, src, np_dtype, narrow):
             raster = self.st[src]
-            dense = self.dense_out.get(src)
-            if dense is not None:                                     # packed on the compute stream, dense DMA
-                with torch.cuda.stream(cur):
+            dense = self.dense_out[src]
+            flag_host = None
+            with torch.cuda.stream(cur):                              # pack on the compute stream, dense DMA
+                if narrow:
+                    _lib.check(lib.hd_pack_i16(raster.ptr, raster.pitch, ctypes.c_void_p(dense.data_ptr()), raster.ny,
+                                               raster.nx, ctypes.c_void_p(self.flags[src].data_ptr()), dev.stream_ptr()))
+                else:
                     dense.view(raster.ny, raster.nx).copy_(raster.tensor())
             ev = torch.cuda.Event()
             ev.record(cur)
             down.wait_event(ev)
             # plain pinned arrays + the library's copy: torch's host allocator then has no pending events on them
             # and hands the same blocks out again at once
-            host = dev.pinned_empty(raster.shape, dev._HD2NP[raster.dtype])
-            es = host.dtype.itemsize
-            if dense is None:
-                _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(host.ctypes.data), raster.nx * es, raster.ptr,
-                                               raster.pitch * es, raster.nx * es, raster.ny,
+            host = dev.pinned_empty(raster.shape, np.int16 if narrow else dev._HD2NP[raster.dtype])
+            nbytes = dense.numel() * dense.element_size()
+            _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(host.ctypes.data), nbytes, ctypes.c_void_p(dense.data_ptr()),
+                                           nbytes, nbytes, 1, ctypes.c_void_p(down.cuda_stream)))
+            if narrow:
+                flag_host = dev.pinned_empty((1,), np.int32)
+                _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(flag_host.ctypes.data), 4,
+                                               ctypes.c_void_p(self.flags[src].data_ptr()), 4, 4, 1,
                                                ctypes.c_void_p(down.cuda_stream)))
-            else:
-                nbytes = dense.numel() * dense.element_size()
-                _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(host.ctypes.data), nbytes, ctypes.c_void_p(dense.data_ptr()),
-                                               nbytes, nbytes, 1, ctypes.c_void_p(down.cuda_stream)))
             done = torch.cuda.Event()
             done.record(down)
-            pending[name] = (host, done, np.dtype(np_dtype))
+            pending[name] = (host, done, np.dtype(np_dtype), flag_host, raster)
 
         def arrived(name):
             cur.wait_event(ready[name])
@@ -223,13 +233,17 @@ class _StreamSlot:
 
         def collect():
             out = {}
-            for name, (host, done, np_dtype) in pending.items():
+            for name, (host, done, np_dtype, flag_host, raster) in pending.items():
                 done.synchronize()
                 arr = host
-                if arr.dtype != np_dtype:                             # float32 -> float64 on host threads
+                if flag_host is not None and int(flag_host[0]) != 0:
+                    # not int16-representable: fetch the float32 raster itself (still intact: the slot is not reused
+                    # before this tile has been collected)
+                    arr = dev.download(raster.with_ref(np_dtype))
+                elif arr.dtype != np_dtype:                           # int16 -> float32 / float64 on host threads
                     wide = dev.pinned_empty(arr.shape, np_dtype)
-                    _lib.check(lib.hd_host_widen_f32_f64(ctypes.c_void_p(wide.ctypes.data),
-                                                         ctypes.c_void_p(arr.ctypes.data), arr.size, self.host_threads))
+                    _lib.check(lib.hd_host_widen_i16(ctypes.c_void_p(wide.ctypes.data), dev.hd_dtype_of(np_dtype),
+                                                     ctypes.c_void_p(arr.ctypes.data), arr.size, self.host_threads))
                     arr = wide
                 out[name] = arr
             return out

@@ -69,10 +69,13 @@ int hd_memcpy2d_h2d(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t
 int hd_memcpy2d_d2h(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
                     int64_t rows, void* stream);
 int hd_stream_synchronize(void* stream);
-/* HOST helper: dst[i] = (double)src[i] on nthreads host threads.  The final DEM (float64 in the reference,
- * hydro_dem_process.py:149) holds integer metres, exact in float32: the host API moves it over PCIe as float32 and
- * widens it here. */
+/* Narrow PCIe transport of integer-valued rasters (host API; the final DEM of hydro_dem_process.py:149 and the filled
+ * DEM hold integer metres).  hd_pack_i16: F32 pitched raster -> dense int16 rows on the device; *inexact_flag (device
+ * int) is set to 1 if any value is not an integer in [-32768, 32767] (NaN included) -- the caller then moves float32
+ * instead.  hd_host_widen_*: HOST helpers, dst[i] = (T)src[i] on nthreads host threads with streaming stores. */
+int hd_pack_i16(const void* src, int64_t src_pitch, void* dst_dense, int64_t ny, int64_t nx, int* inexact_flag, void* stream);
 int hd_host_widen_f32_f64(double* dst, const float* src, int64_t n, int nthreads);
+int hd_host_widen_i16(void* dst, int dst_dtype, const int16_t* src, int64_t n, int nthreads);
 
 /* ---- elementwise filters (filters/simple_filters.py, extension_filters.py:12-130) -------------- */
 typedef enum {

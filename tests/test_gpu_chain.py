@@ -123,3 +123,24 @@ def test_stream_with_rivers_and_no_hydrology():
     for o in outs:
         assert set(o) == {"final"}
         np.testing.assert_array_equal(o["final"], want)
+
+
+def test_stream_falls_back_to_float32_transport():
+    """Elevations outside int16 (or NaN / fractional results) cannot use the int16 transport of the streaming API:
+    the device-side check flags the tile and the float32 raster is fetched instead -- same bits as the plain path."""
+    sc = SynthScene(210, 300, 21)
+    srtm, groves, hsheds = sc.srtm() + np.float32(40000), sc.groves(), sc.hsheds() + np.float32(40000)
+    chain = ConditioningChain()
+    want = chain.apply(srtm, groves, hsheds.copy())
+    assert want.final.max() > 32767
+    ok = SynthScene(210, 300, 22)
+    items = [(srtm, groves, hsheds), (ok.srtm(), ok.groves(), ok.hsheds()), (srtm, groves, hsheds)]
+    got = list(chain.stream(items))
+    for g in (got[0], got[2]):
+        np.testing.assert_array_equal(g["final"], want.final)
+        np.testing.assert_array_equal(g["filled"], want.filled)
+        np.testing.assert_array_equal(g["d8"], want.d8)
+    want_ok = chain.apply(ok.srtm(), ok.groves(), ok.hsheds())
+    np.testing.assert_array_equal(got[1]["final"], want_ok.final)
+    np.testing.assert_array_equal(got[1]["filled"], want_ok.filled)
+    assert got[1]["final"].dtype == np.float64 and got[1]["filled"].dtype == np.float32

@@ -197,25 +197,55 @@ template <typename T> __device__ __forceinline__ T tmax(T a, T b);
 template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
 template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
 
-template <typename T>
+// HC > 0: half-window known at compile time (the chain's GreyDilation is 7x7): loops unroll and the horizontal pass
+// shares its loads between four neighbouring outputs.  HC = 0: any half-window, plain loops.
+template <typename T, int HC>
 __global__ void __launch_bounds__(NT) maxfilter_kernel(const __grid_constant__ CUtensorMap tm_in, T* __restrict__ out,
-                                                       int64_t out_pitch, int64_t ny, int64_t nx, int h, int in_w, int in_h,
+                                                       int64_t out_pitch, int64_t ny, int64_t nx, int h_rt, int in_w, int in_h,
                                                        int tiles_x, int ntiles)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
     constexpr uint32_t STAGE = MAX_IN_H * (TW + 2 * MAX_HALO) * sizeof(T);
     T* hmax = reinterpret_cast<T*>(smem + 2 * STAGE);          // [in_h][TW] horizontal maxima
+    const int h = HC > 0 ? HC : h_rt;
     const int hx = hd_halo_x(h, sizeof(T)), xoff = hx - h;
     const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * in_h * sizeof(T)), hx, h}};
     tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         T* tile = reinterpret_cast<T*>(st);
         patch_reflect<T>(tile, in_w, in_h, ty0 - h, tx0 - hx, ny, nx);
-        for (int t = threadIdx.x; t < in_h * TW; t += NT) {
-            const int r = t / TW, c = t - r * TW;
-            T m = tile[r * in_w + c + xoff];
-            for (int s = 1; s <= 2 * h; ++s) m = tmax<T>(m, tile[r * in_w + c + xoff + s]);
-            hmax[t] = m;
+        if constexpr (HC > 0) {
+            // horizontal: four consecutive outputs per thread from 4 + 2 HC loaded cells
+            for (int t = threadIdx.x; t < in_h * (TW / 4); t += NT) {
+                const int r = t / (TW / 4), c = 4 * (t - r * (TW / 4));
+                const T* src = tile + r * in_w + c + xoff;
+                T v[4 + 2 * HC];
+#pragma unroll
+                for (int k = 0; k < 4 + 2 * HC; ++k) v[k] = src[k];
+                T mid = v[3];                                  // cells 3 .. 2 HC are shared by all four windows
+#pragma unroll
+                for (int k = 4; k <= 2 * HC; ++k) mid = tmax<T>(mid, v[k]);
+                T o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    T m = mid;
+#pragma unroll
+                    for (int k = j; k < 3; ++k) m = tmax<T>(m, v[k]);
+#pragma unroll
+                    for (int k = 2 * HC + 1; k <= 2 * HC + j; ++k) m = tmax<T>(m, v[k]);
+                    o[j] = m;
+                }
+                T* dst = hmax + r * TW + c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = o[j];
+            }
+        } else {
+            for (int t = threadIdx.x; t < in_h * TW; t += NT) {
+                const int r = t / TW, c = t - r * TW;
+                T m = tile[r * in_w + c + xoff];
+                for (int s = 1; s <= 2 * h; ++s) m = tmax<T>(m, tile[r * in_w + c + xoff + s]);
+                hmax[t] = m;
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -227,9 +257,17 @@ __global__ void __launch_bounds__(NT) maxfilter_kernel(const __grid_constant__ C
             T v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = hmax[ro * TW + 4 * c4 + j];
-            for (int s = 1; s <= 2 * h; ++s) {
+            if constexpr (HC > 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = tmax<T>(v[j], hmax[(ro + s) * TW + 4 * c4 + j]);
+                for (int s = 1; s <= 2 * HC; ++s) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = tmax<T>(v[j], hmax[(ro + s) * TW + 4 * c4 + j]);
+                }
+            } else {
+                for (int s = 1; s <= 2 * h; ++s) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = tmax<T>(v[j], hmax[(ro + s) * TW + 4 * c4 + j]);
+                }
             }
             store4v<T>(out, out_pitch, y, x, nx, v);
         }
@@ -363,16 +401,21 @@ extern "C" int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
     const size_t smem = 2 * MAX_IN_H * (TW + 2 * MAX_HALO) * es + MAX_IN_H * TW * es;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == HD_F32) {
-        HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dtype == HD_F32 && h == 3) {
+        HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hd_prof_begin("maxfilter_kernel", s);
-        maxfilter_kernel<float><<<grid_for(ntiles, 2), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, h, in_w, in_h,
-                                                                     tiles_x, ntiles);
+        maxfilter_kernel<float, 3><<<grid_for(ntiles, 2), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, h, in_w, in_h,
+                                                                        tiles_x, ntiles);
+    } else if (dtype == HD_F32) {
+        HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hd_prof_begin("maxfilter_kernel", s);
+        maxfilter_kernel<float, 0><<<grid_for(ntiles, 2), NT, smem, s>>>(tm, (float*)out, out_pitch, ny, nx, h, in_w, in_h,
+                                                                        tiles_x, ntiles);
     } else {
-        HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HD_CUDA_OK(cudaFuncSetAttribute(maxfilter_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hd_prof_begin("maxfilter_kernel", s);
-        maxfilter_kernel<double><<<grid_for(ntiles, 1), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, h, in_w, in_h,
-                                                                      tiles_x, ntiles);
+        maxfilter_kernel<double, 0><<<grid_for(ntiles, 1), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, h, in_w, in_h,
+                                                                         tiles_x, ntiles);
     }
     HD_LAUNCH_CHECK();
     hd_count_launch();

@@ -70,7 +70,7 @@ class _StreamSlot:
 
     ORDER = ("srtm", "groves", "hsheds", "rivers")
 
-    def __init__(self, chain, arrays):
+    def __init__(self, chain, arrays, narrow_filled=True):
         import torch
         lib = _lib.load()
         self.chain = chain
@@ -81,6 +81,12 @@ class _StreamSlot:
         self.names = [n for n in self.ORDER if n in arrays]
         self.inputs = {n: dev.empty(*arrays[n].shape, dev.hd_dtype_of(arrays[n].dtype), arrays[n].dtype)
                        for n in self.names}
+        if arrays["srtm"].dtype == np.float32:
+            # the raw SRTM raster is only read by the row FFT (plain loads, any pitch): it lives densely and is the
+            # direct target of its upload -- no staging copy, no re-pitch kernel
+            ny, nx = arrays["srtm"].shape
+            self.inputs["srtm"] = dev.DeviceRaster(torch.empty((ny, nx), dtype=torch.float32, device=dev.device()), ny, nx,
+                                                   _lib.F32, np.float32)
         for r in self.inputs.values():
             r.buf.zero_()
         self.staging = {}
@@ -112,12 +118,13 @@ class _StreamSlot:
         # fraction or |z| > 32767 falls back to float32) and are widened to the reference dtypes on the host.
         self.outputs = [("final", "final32", np.float64, True)]
         if chain.with_hydrology:
-            self.outputs += [("filled", "filled", np.float32, True), ("d8", "d8", np.uint8, False)]
+            self.outputs += [("filled", "filled", np.float32, bool(narrow_filled)), ("d8", "d8", np.uint8, False)]
         # Rasters travel as dense 1-D copies: with both PCIe directions busy, pitched 2-D copies reach 72 GB/s in total,
         # dense ones 95 GB/s (uint8 rows of 3601 bytes: half the rate even alone).  Re-pitching / packing is a small
         # device kernel on the COMPUTE stream, so the copy streams carry nothing but DMA -- a kernel there would have
         # to wait for a gap between the chain's kernels and hold up the copies queued behind it.
-        self.dense_in = {n: torch.empty(r.ny * r.nx, dtype=r.buf.dtype, device=r.buf.device)
+        self.dense_in = {n: (r.buf.view(-1) if r.pitch == r.nx else
+                             torch.empty(r.ny * r.nx, dtype=r.buf.dtype, device=r.buf.device))
                          for n, r in self.inputs.items()}
         self.dense_out, self.flags = {}, {}
         for _, src, _, narrow in self.outputs:
@@ -201,8 +208,8 @@ class _StreamSlot:
         def arrived(name):
             cur.wait_event(ready[name])
             for n in (("hsheds", "rivers") if name == "hsheds" else (name,)):
-                if n in self.dense_in and n in ready:
-                    r = self.inputs[n]
+                r = self.inputs.get(n)
+                if r is not None and n in ready and r.pitch != r.nx:
                     with torch.cuda.stream(cur):
                         r.tensor().copy_(self.dense_in[n].view(r.ny, r.nx))
 
@@ -383,12 +390,15 @@ class ConditioningChain:
         inflight = collections.deque()
         for k, item in enumerate(items):
             arrays = self._check_inputs(*item)
-            key = tuple((n, a.shape, a.dtype.str) for n, a in arrays.items())
+            # one tile at a time (depth 1) is a latency call: the filled DEM then travels as float32, because widening it
+            # on the host would sit at the very end of the critical path
+            narrow_filled = depth > 1
+            key = tuple((n, a.shape, a.dtype.str) for n, a in arrays.items()) + (narrow_filled,)
             ring = rings.setdefault(key, [])
             if k % depth >= len(ring):
                 while inflight:                                      # capturing synchronises the device anyway
                     yield inflight.popleft()[1]()
-                ring.append(_StreamSlot(self, arrays))               # captured once per shape, kept for later calls
+                ring.append(_StreamSlot(self, arrays, narrow_filled))    # captured once per shape, kept for later calls
             slot = ring[min(k % depth, len(ring) - 1)]
             while any(s is slot for s, _ in inflight):               # the slot's previous tile must be collected first
                 yield inflight.popleft()[1]()

@@ -93,6 +93,9 @@ class ClockSampler:
         """Drop what was sampled so far (warm-up); keep sampling."""
         self.first = len(self.lines)
 
+    def count(self):
+        return len(self.lines) - getattr(self, "first", 0) if self.proc else 1 << 30
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -245,7 +248,19 @@ def run_gpu(args):
         sweeps.append(res.info.get("fill_sweeps"))
     barrier()
     launches = int(lib.hd_launch_count()) if captured is None else captured.launches * args.steps
+    # nvidia-smi delivers a sample every 20-100 ms; a timed region of K x 2.5 ms can end before the first one.  If so,
+    # the identical steps keep running (untimed) until a few samples under the same load exist, and the line says so.
+    extra = 0
+    if rank == 0:
+        t_end = time.perf_counter() + 1.5
+        while sampler.count() < 4 and time.perf_counter() < t_end:
+            step_resident()
+            torch.cuda.synchronize()
+            extra += 1
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        clocks["sampled"] = ("during the timed steps" if extra == 0 else
+                             f"during the timed steps and {extra} identical untimed steps run right after them")
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
@@ -275,7 +290,9 @@ def run_gpu(args):
         algo_bytes = 12.0 * 64 * 64 * sweeps[-1]                          # bytes actually staged: tile visits x 64 x 64 cells
     achieved = algo_bytes / (top_avg_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-    ncu_traffic = {"fft_rows_kernel": 125.0e6}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures of this round
+    # (profiles/r1_fft_rows_final_raw.csv: four launches 100.3 / 60.8 / 69.3 / 121.8 MB; profiles/r1_fill_async_raw.csv)
+    ncu_traffic = {"fft_rows_kernel": 88.0e6, "fill_async_kernel": 130.9e6}
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic.get(top), "launches_per_step": kernels[top]["launches"],
                 "avg_launch_ms": top_avg_ms, "share_of_step": kernels[top]["total_ms"] / prof_total,

@@ -195,6 +195,9 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (the conditioning path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...") and any NCCL_DEBUG output to stdout by default: stdout carries
+        # exactly one JSON line, so send NCCL's log to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     ny = nx = args.size
@@ -351,6 +354,7 @@ def run_gpu(args):
                     "api": "for out in hydrodem_b200.pipeline.ConditioningChain.stream(tiles): out = {final, filled, d8} "
                            f"ndarrays; {args.stream_depth} slots, copies of neighbouring steps overlap the kernels",
                     "single_tile_latency_ms": single_ms,
+                    "host": {"cpus": len(os.sched_getaffinity(0)), "ranks_on_box": env_int("LOCAL_WORLD_SIZE", 1)},
                     "single_tile_api": "ConditioningChain.apply_to_host(srtm, groves, hsheds)"},
             "gpu_launches": launches, "launches_per_step": launches / args.steps,
             "roofline": roofline, "kernel_ms": breakdown, "clocks": clocks,

@@ -57,6 +57,7 @@ SIGNATURES = {
     "hd_fft2_forward_shift_abs": (_i, [_p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p]),
     "hd_fft2_masked_inverse_abs": (_i, [_p, _p, _i64, _p, _i64, _p, _i, _i64, _p, _i64, _p]),
     "hd_fft2_c2c": (_i, [_p, _p, _i, _i64, _p, _i64, _i, _p, _i64, _p]),
+    "hd_fft_rows": (_i, [_p, _p, _i, _i64, _p, _i64, _i64, _i, _i, _p, _i64, _p]),
     "hd_fftshift2": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
     "hd_pdfill_workspace_bytes": (_i64, [_i64, _i64]),
     "hd_pdfill": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _i, ctypes.POINTER(_i), _p]),

@@ -823,6 +823,43 @@ int hd_fft2_c2c(void* plan, const void* in, int in_dtype, int64_t in_pitch, void
     return HD_OK;
 }
 
+// Batched 1-D transforms along the rows of an (nrows x nx) array (nx = the plan's row length): the building block of
+// the row-band distributed fft2 (hydrodem_b200/sharding.py: local row transforms, all-to-all, local column transforms).
+// transpose_out: out is (nx x nrows) -- the layout the all-to-all wants, and for free (the transpose also undoes the
+// permuted storage of long rows).
+int hd_fft_rows(void* plan, const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int64_t nrows,
+                int inverse, int transpose_out, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    if (!plan || !in || !out || !workspace) return HD_ERR_NULL;
+    Plan2D* p = (Plan2D*)plan;
+    const int nx = (int)p->nx;
+    if (nrows < 1 || nrows > 0x7fffffff) return HD_ERR_ARG;
+    if (workspace_bytes < hd_fft2_workspace_bytes(nrows, nx)) return HD_ERR_WORKSPACE;
+    if (in_pitch < nx || out_pitch < (transpose_out ? nrows : nx)) return HD_ERR_ARG;
+    if (in_dtype != HD_F32 && in_dtype != HD_C64) return HD_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    float2* A = (float2*)workspace;
+    float2* At = A + nrows * nx;
+    const bool direct = !transpose_out && p->px.n1 == 1;
+    // LOAD_REAL would pack two real rows per transform and emit both spectra: fine here (full spectra are stored)
+    RowsArgs r1{in, in_pitch, direct ? (float2*)out : A, direct ? out_pitch : (int64_t)nx, nullptr, 0, (int)nrows, 0, 0,
+                inverse ? 1 : 0, 0};
+    if (int e = launch_rows(p->px, r1, in_dtype == HD_F32 ? LOAD_REAL : LOAD_C64, s)) return e;
+    if (direct) return HD_OK;
+    float2* t_out = transpose_out ? (float2*)out : At;
+    const int64_t t_pitch = transpose_out ? out_pitch : nrows;
+    hd_prof_begin("transpose_kernel", s);
+    transpose_kernel<float2, false><<<transpose_grid((int)nrows, nx), 256, 0, s>>>(A, nx, t_out, t_pitch, nullptr, 0,
+                                                                                  (int)nrows, nx, 0, 0, p->px.n1, p->px.n);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    if (transpose_out) return HD_OK;
+    hd_prof_begin("transpose_kernel", s);                         // long rows, row layout wanted: transpose back
+    transpose_kernel<float2, false><<<transpose_grid(nx, (int)nrows), 256, 0, s>>>(At, nrows, (float2*)out, out_pitch, nullptr,
+                                                                                  0, nx, (int)nrows, 0, 0, 1, nx);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
 int hd_fftshift2(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
                  int inverse, void* stream)
 {

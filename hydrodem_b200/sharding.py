@@ -16,9 +16,11 @@ local fixed point, the ranks exchange their edge rows of W, and the loop ends
 when an all-reduce says no halo row was lowered.  The fixed point is unique,
 so the banded result equals the single-GPU one bit for bit.
 
-The Fourier stage needs a global transform (all-to-all transpose); that is
-not built yet, so the banded path covers the stencil
-stages and sink-fill / D8 (BASELINE.json configs[3]).
+The Fourier transforms of a banded mosaic are distributed too (``Band.fft2`` /
+``Band.ifft2``: local row transforms, ONE all-to-all, local column
+transforms).  The peak detector and the point-mirrored mask assembly between
+them still run on one GPU, so the fully banded path
+covers the stencil stages, the transforms and sink-fill / D8.
 
 The communicator is abstract: ``DistComm`` (torch.distributed) for real runs,
 ``ThreadComm`` to emulate the ranks as threads of one process on one device
@@ -73,6 +75,25 @@ class DistComm:
                 req.wait()
         return recv_up, recv_down
 
+    def all_to_all_shaped(self, chunks, recv_shapes):
+        """chunks[j] goes to rank j; returns the chunks received (index = source rank).  The shapes that arrive are
+        known from the global band table (``recv_shapes``), so no size exchange is needed.  Grouped isend / irecv
+        pairs: NCCL fuses them into one all-to-all over NVLink, gloo runs them as P2P."""
+        dist = self.dist
+        out = [None] * self.world
+        ops = []
+        for j in range(self.world):
+            if j == self.rank:
+                out[j] = chunks[j].contiguous()
+                continue
+            out[j] = torch.empty(recv_shapes[j], dtype=chunks[j].dtype, device=chunks[j].device)
+            ops.append(dist.P2POp(dist.isend, chunks[j].contiguous(), j, self.group))
+            ops.append(dist.P2POp(dist.irecv, out[j], j, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return out
+
     def any(self, flag):
         t = torch.tensor([1 if flag else 0], dtype=torch.int32,
                          device="cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu")
@@ -107,6 +128,19 @@ class ThreadComm:
         recv_down = sh.box[(self.rank + 1, "up")] if self.rank < self.world - 1 else None
         sh.barrier.wait()
         return recv_up, recv_down
+
+    def all_to_all_shaped(self, chunks, recv_shapes):
+        sh = self.shared
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        for j in range(self.world):
+            sh.box[("a2a", self.rank, j)] = chunks[j].clone()
+        sh.barrier.wait()
+        out = [sh.box[("a2a", i, self.rank)] for i in range(self.world)]
+        sh.barrier.wait()
+        for i, t in enumerate(out):
+            assert tuple(t.shape) == tuple(recv_shapes[i]), (t.shape, recv_shapes[i])
+        return out
 
     def any(self, flag):
         sh = self.shared
@@ -177,6 +211,53 @@ class Band:
         ext, n_up = self.extend(raster, h)
         out = filt.run_device(ext)
         return out.sub(n_up, n_up + raster.ny, 0, raster.nx)
+
+    # -- distributed 2-D Fourier transform (FourierTransform / FourierITransform, extension_filters.py:363-480)
+    def _rows_fft(self, src, n, inverse, transpose_out):
+        """hd_fft_rows on a local (rows x n) raster -> C64 raster, (n x rows) when transposed."""
+        lib = _lib.load()
+        rows = src.ny
+        plan = dev.fft_plan(n, n)
+        nbytes = lib.hd_fft2_workspace_bytes(rows, n)
+        work = dev.scratch(nbytes)
+        out = dev.empty(n, rows, _lib.C64, np.complex64) if transpose_out else dev.empty(rows, n, _lib.C64, np.complex64)
+        _lib.check(lib.hd_fft_rows(plan, src.ptr, src.dtype, src.pitch, out.ptr, out.pitch, rows, int(inverse),
+                                   int(transpose_out), ctypes.c_void_p(work.data_ptr()), nbytes, dev.stream_ptr()))
+        return out
+
+    def _exchange_transposed(self, t_raster, my_bounds, other_bounds):
+        """t_raster: (n_other x my_len) -- the transposed local block.  Sends rows [a, b) of it to the rank that owns
+        [a, b) of the other axis; returns the (my_other_len x total_len) raster assembled from what arrives."""
+        comm = self.comm
+        tt = t_raster.tensor()
+        chunks = [tt[a:b] for (a, b) in other_bounds]
+        mine = other_bounds[comm.rank][1] - other_bounds[comm.rank][0]
+        shapes = [(mine, b - a) for (a, b) in my_bounds]
+        got = comm.all_to_all_shaped([torch.view_as_real(c.contiguous()) for c in chunks],
+                                     [sh + (2,) for sh in shapes])
+        total = sum(b - a for (a, b) in my_bounds)
+        out = dev.empty(mine, total, _lib.C64, np.complex64)
+        to = out.tensor()
+        for (a, b), g in zip(my_bounds, got):
+            to[:, a:b].copy_(torch.view_as_complex(g))
+        return out
+
+    def fft2(self, band):
+        """Forward 2-D DFT of the mosaic whose row band this rank holds (F32 or C64 device raster, rows r0:r1).
+        Returns the spectrum in TRANSPOSED band layout: a C64 raster (c1 - c0, ny) with out[c - c0, k] = F[k, c] for
+        this rank's column band [c0, c1) = band_bounds(nx, world)[rank].  One all-to-all, as in SURVEY.md section 8(e):
+        local row transforms -> exchange -> local column transforms."""
+        rows_b, cols_b = band_bounds(self.ny, self.comm.world), band_bounds(self.nx, self.comm.world)
+        t = self._rows_fft(band, self.nx, False, True)                    # (nx, rows) transposed row spectra
+        cols = self._exchange_transposed(t, rows_b, cols_b)               # (my cols, ny)
+        return self._rows_fft(cols, self.ny, False, False)                # transform along ny, stays (my cols, ny)
+
+    def ifft2(self, spec_t):
+        """Inverse of fft2: transposed-layout spectrum band (c1 - c0, ny) -> C64 row band (r1 - r0, nx)."""
+        rows_b, cols_b = band_bounds(self.ny, self.comm.world), band_bounds(self.nx, self.comm.world)
+        t = self._rows_fft(spec_t, self.ny, True, True)                   # (ny, my cols)
+        rows = self._exchange_transposed(t, cols_b, rows_b)               # (my rows, nx)
+        return self._rows_fft(rows, self.nx, True, False)
 
     # -- sink-fill + D8
     def sinkfill(self, z, max_rounds=10000):

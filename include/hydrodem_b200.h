@@ -175,6 +175,12 @@ int hd_fft2_masked_inverse_abs(void* plan, const void* fshift, int64_t fshift_pi
 int hd_fft2_c2c(void* plan, const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int inverse,
                 void* workspace, int64_t workspace_bytes, void* stream);
 /* FourierShift / FourierIShift.apply, extension_filters.py:432-447, :465-480.  Any 4 / 8 / 16-byte dtype. */
+/* Batched 1-D c2c transforms along the rows of an (nrows x nx) array, nx = the plan's row length (in: F32 or C64,
+ * out: C64; transpose_out: out is (nx x nrows)).  Building block of the row-band distributed fft2
+ * (extension_filters.py:363-480 on a mosaic sharded over several GPUs): local row transforms, all-to-all, local column
+ * transforms.  Workspace: hd_fft2_workspace_bytes(nrows, nx). */
+int hd_fft_rows(void* plan, const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int64_t nrows,
+                int inverse, int transpose_out, void* workspace, int64_t workspace_bytes, void* stream);
 int hd_fftshift2(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
                  int inverse, void* stream);
 

@@ -147,3 +147,47 @@ def test_thread_comm_emulation():
         return (None if up is None else float(up[0, 0]), None if down is None else float(down[0, 0]), comm.any(comm.rank == 2))
     res = sharding.ThreadComm.run(3, fn)
     assert res == [(None, 1.0, True), (0.0, 2.0, True), (1.0, None, True)]
+
+
+def _a2a_worker(rank, world, port, ny, nx, out):
+    """The all-to-all of the distributed fft2 over gloo: block (rows of rank i, columns of rank j) of a matrix must
+    land on rank j, i.e. the exchange of transposed blocks reassembles full columns."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = sharding.DistComm()
+        mat = torch.arange(ny * nx, dtype=torch.float32).reshape(ny, nx)
+        rows_b, cols_b = sharding.band_bounds(ny, world), sharding.band_bounds(nx, world)
+        r0, r1 = rows_b[rank]
+        t = mat[r0:r1].t().contiguous()                              # (nx, my rows): the transposed local band
+        chunks = [t[a:b] for (a, b) in cols_b]
+        mine = cols_b[rank][1] - cols_b[rank][0]
+        got = comm.all_to_all_shaped(chunks, [(mine, b - a) for (a, b) in rows_b])
+        cols = torch.cat(got, dim=1)                                 # (my cols, ny)
+        c0, c1 = cols_b[rank]
+        out[rank] = int(torch.equal(cols, mat[:, c0:c1].t()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_to_all_gloo_world2():
+    world = 2
+    out = mp.Array("i", [0] * world)
+    port = _free_port()
+    procs = [mp.Process(target=_a2a_worker, args=(r, world, port, 11, 7, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(out) == [1, 1]
+
+
+def test_thread_comm_all_to_all():
+    def fn(comm):
+        chunks = [torch.full((1, 2), float(10 * comm.rank + j)) for j in range(comm.world)]
+        got = comm.all_to_all_shaped(chunks, [(1, 2)] * comm.world)
+        return [float(g[0, 0]) for g in got]
+    res = sharding.ThreadComm.run(3, fn)
+    assert res == [[0.0, 10.0, 20.0], [1.0, 11.0, 21.0], [2.0, 12.0, 22.0]]

@@ -259,6 +259,69 @@ class Band:
         rows = self._exchange_transposed(t, cols_b, rows_b)               # (my rows, nx)
         return self._rows_fft(rows, self.nx, True, False)
 
+    def detect_apply_fourier(self, band):
+        """DetectApplyFourier (custom_filters.py:1053-1101) on a banded mosaic: distributed forward transform, the
+        |F| bands all-gathered so that every rank runs the (cheap, window-55) peak detector and the point-mirrored
+        mask assembly on the whole spectrum, mask applied to the local spectrum band, distributed inverse, abs.
+        Returns this rank's rows of the stripe-free DEM (F32 storage, float64 reference dtype)."""
+        from .filters import custom_filters as cf, extension_filters as ef
+        comm = self.comm
+        cols_b = band_bounds(self.nx, comm.world)
+        c0, c1 = cols_b[comm.rank]
+        spec_t = self.fft2(band)                                           # (c1 - c0, ny): F[k, c] at [c - c0, k]
+        fabs_loc = dev.empty(spec_t.ny, spec_t.nx, _lib.F32, np.float32)
+        dev.elementwise(_lib.OP_ABS, spec_t, None, 0.0, fabs_loc)          # AbsoluteValues, extension_filters.py:78-95
+        part = fabs_loc.tensor().contiguous()
+        parts = comm.all_to_all_shaped([part] * comm.world, [(b - a, self.ny) for (a, b) in cols_b])   # all-gather
+        fabs = dev.empty(self.ny, self.nx, _lib.F32, np.float32)
+        fabs.tensor().copy_(torch.cat(parts, dim=0).t())                   # |F| in natural (ny, nx) layout
+        fabs_shift = ef.FourierShift().run_device(fabs)                    # FourierInitial, custom_filters.py:859-877
+        keep = cf.FourierProcessQuarters(fabs_shift).run_device(fabs_shift, invert=True, out_dtype=_lib.F32)   # 1 - mask
+        keep = ef.FourierIShift().run_device(keep)                         # back to the unshifted layout of F
+        keep_t = dev.empty(spec_t.ny, spec_t.nx, _lib.F32, np.float32)
+        keep_t.tensor().copy_(keep.tensor()[:, c0:c1].t())                 # this rank's columns, transposed
+        masked = dev.empty(spec_t.ny, spec_t.nx, _lib.C64, np.complex64)
+        dev.elementwise(_lib.OP_MUL, spec_t, keep_t, 0.0, masked)          # ProductFilter(factor=F), (1 - mask) * F
+        back = self.ifft2(masked)                                          # (r1 - r0, nx) complex
+        out = dev.empty(back.ny, back.nx, _lib.F32, np.float64)
+        dev.elementwise(_lib.OP_ABS, back, None, 0.0, out)
+        return out
+
+    # -- the whole chain on row bands (BASELINE.json configs[4]: one mosaic over the GPUs of a box)
+    def conditioning_chain(self, srtm, groves_class, hsheds, groves_iterations=3, with_hydrology=True):
+        """HydroDEMProcess.start (hydro_dem_process.py:122-153) on this rank's rows of a mosaic: every windowed stage
+        runs the single-GPU kernel on [halo | band | halo] after a halo exchange with the two neighbours (h rows:
+        closing 2, quadratic 7, nanfix 1, majority 5, erosion x2 2, expand 3, max 7x7 3, mean3 1), the Fourier stage
+        uses the distributed transforms, the sink-fill iterates to the global fixed point.  Inputs: device rasters of
+        the band (F32, U8 0/1, F32).  Returns {"final": F64-ref raster, "filled", "d8"} for the band's rows."""
+        from .filters import custom_filters as cf, extension_filters as ef
+        lib = _lib.load()
+        ny_b, nx = srtm.ny, srtm.nx
+        dem = self.detect_apply_fourier(srtm)                                        # image_srtm.py:125-126
+        groves = self.apply(ef.BinaryClosing(structure=np.ones((3, 3))), groves_class, 2)    # image_srtm.py:177-178
+        g_ext, g_up = self.extend(dev.convert(groves, _lib.U8), 7)
+        gc = cf.GrovesCorrection(g_ext)
+        for _ in range(groves_iterations):                                           # image_srtm.py:199
+            ext, n_up = self.extend(dem, 7)
+            assert n_up == g_up
+            dem = gc.run_device(ext, out_dtype=_lib.F32).sub(n_up, n_up + ny_b, 0, nx)
+        fixed = self.apply(cf.CorrectNANValues(), hsheds, 1)                         # LagoonsDetection, :633-661
+        majority = self.apply(cf.MajorityFilter(window_size=11), fixed, 5)
+        eroded = self.apply(ef.BinaryErosion(iterations=2), majority, 2)
+        expanded = self.apply(cf.ExpandFilter(window_size=7), eroded, 3)
+        prod = dev.empty(ny_b, nx, _lib.F32, np.float64)
+        dev.elementwise(_lib.OP_MUL, expanded, majority, 0.0, prod)                  # ProductFilter(factor=majority), :607
+        tidy = self.apply(ef.GreyDilation(size=(7, 7)), prod, 3)
+        fixed32 = dev.convert(fixed, _lib.F32)
+        complete = dev.empty(ny_b, nx, _lib.F64, np.float64)
+        _lib.check(lib.hd_final_terms(dem.ptr, dem.dtype, dem.pitch, tidy.ptr, tidy.pitch, fixed32.ptr, fixed32.pitch,
+                                      None, 0, complete.ptr, complete.dtype, complete.pitch, ny_b, nx, dev.stream_ptr()))
+        final = self.apply(cf.PostProcessingFinal(), complete, 1)                    # hydro_dem_process.py:149
+        out = {"final": final, "dem_complete": complete}
+        if with_hydrology:
+            out["filled"], out["d8"] = self.sinkfill(dev.convert(final, _lib.F32, np.float32))
+        return out
+
     # -- sink-fill + D8
     def sinkfill(self, z, max_rounds=10000):
         """Banded Planchon-Darboux fixed point (bit-identical to the single-GPU result)."""

@@ -25,6 +25,7 @@
 namespace {
 
 constexpr int FT = 64;                    // tile edge
+constexpr int CB = 8;                     // block edge between two levels of the multigrid start of the fill (4: no fewer fine visits, one more level of latency)
 constexpr int FNT = 256;
 constexpr int WHX = 4;                    // x halo of the W box (16-byte TMA rule), 1 needed
 constexpr int WBOX_W = FT + 2 * WHX;      // 72
@@ -38,20 +39,24 @@ struct FillCounters { int changed_tiles; int pad[3]; };
 __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
                                                         int64_t w_pitch, int64_t ny, int64_t nx, int top_is_halo = 0,
                                                         int bottom_is_halo = 0, int* __restrict__ tile_has_nodata = nullptr,
-                                                        int tiles_x = 0, int* __restrict__ any_nodata = nullptr)
+                                                        int tiles_x = 0, int* __restrict__ any_nodata = nullptr,
+                                                        const float* __restrict__ wc = nullptr, int64_t c_pitch = 0)
 {
     const int64_t nxq = (nx + 3) / 4;                                            // four consecutive cells per thread
     for (CellIter it(nxq); it.y < ny; it.next()) {
         const int64_t y = it.y, x0 = 4 * it.x;
         float v4[4], r4[4];
         gload4(z + y * z_pitch + x0, x0, nx, v4);
+        // interior cells start from the coarse-level fill of their block (an upper bound of the answer, see
+        // fill_pool_kernel) instead of +inf; a quad never straddles two blocks (CB is a multiple of 4)
+        const float start = wc ? __ldg(wc + (y / CB) * c_pitch + x0 / CB) : __int_as_float(0x7f800000);
         const bool yframe = (y == 0 && !top_is_halo) || (y == ny - 1 && !bottom_is_halo);
         bool nodata = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t x = x0 + j;
             const float v = v4[j];
-            float r = __int_as_float(0x7f800000);                                // +inf inside
+            float r = start;                                                     // +inf (or the coarse bound) inside
             if (v != v) {
                 r = __int_as_float(0xff800000);                                  // nodata: outlet at -inf
                 nodata |= x < nx;
@@ -200,12 +205,65 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(int tiles_x, int tiles_y
     for (int tile = blockIdx.x * blockDim.x + threadIdx.x; tile < ntiles; tile += gridDim.x * blockDim.x) {
         const int ty = tile / tiles_x, tx = tile % tiles_x;
         bool seed;
-        if (edge_rows_only)
+        if (edge_rows_only < 0)
+            seed = true;                                           // multigrid start: every tile has cells to lower
+        else if (edge_rows_only)
             seed = ((edge_rows_only & 2) && ty == 0) || ((edge_rows_only & 4) && ty >= (int)((ny - 2) / FT));
         else
             seed = ty == 0 || tx == 0 || ty == tiles_y - 1 || tx == tiles_x - 1 || queued[tile] != 0;
         queued[tile] = seed ? T_QUEUED : T_IDLE;
         if (seed) fill_push(ctl, slots, ctl->qcap, tile);
+    }
+}
+
+// ---- coarse level of the fill -------------------------------------------------------------------------------------
+// z_c(block) = max of the block's cells.  Every cell of a block can reach every other cell of it without exceeding
+// z_c, blocks that touch are 8-connected at cell level, so the fill of the coarse DEM is an UPPER BOUND of the fill of
+// the fine DEM on each block.  A block that holds an outlet (a frame cell or a nodata cell) is an outlet of the coarse
+// problem at level z_c.  Starting the fine iteration from that bound instead of +inf changes nothing in the result
+// (the fixed point is unique) but removes the long dependency chain of the tile wave: the global drainage structure
+// is solved on 1/64 of the cells, the fine level only relaxes locally and all its tiles are busy from the start.
+// w_in (levels >= 1): the finer level's own start -- a finite value marks an outlet cell of that level.
+__global__ void __launch_bounds__(256) fill_pool_kernel(const float* __restrict__ z, int64_t z_pitch, int64_t ny, int64_t nx,
+                                                        float* __restrict__ zc, float* __restrict__ wc, int64_t c_pitch,
+                                                        int64_t nyc, int64_t nxc, int* __restrict__ tile_flags, int tiles_x_c,
+                                                        const float* __restrict__ w_in)
+{
+    for (CellIter it(nxc); it.y < nyc; it.next()) {
+        const int64_t by = it.y, bx = it.x, y0 = by * CB, x0 = bx * CB;
+        float m = __int_as_float(0xff800000);
+        bool has_nan = false, any_valid = false;
+        for (int dy = 0; dy < CB && y0 + dy < ny; ++dy) {
+            const float* row = z + (y0 + dy) * z_pitch + x0;
+#pragma unroll
+            for (int q = 0; q < CB; q += 4) {
+                float v[4], wv[4] = {0.f, 0.f, 0.f, 0.f};
+                gload4(row + q, x0 + q, nx, v);
+                if (w_in) gload4(w_in + (y0 + dy) * z_pitch + x0 + q, x0 + q, nx, wv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (x0 + q + j >= nx) continue;
+                    if (v[j] != v[j]) has_nan = true;
+                    else { m = fmaxf(m, v[j]); any_valid = true; }
+                    if (w_in && wv[j] != __int_as_float(0x7f800000)) has_nan = true;      // an outlet of the finer level
+                }
+            }
+        }
+        const bool frame = y0 == 0 || x0 == 0 || y0 + CB >= ny || x0 + CB >= nx;
+        const bool seed = has_nan || frame;
+        zc[by * c_pitch + bx] = any_valid ? m : __int_as_float(0x7fc00000);
+        wc[by * c_pitch + bx] = !any_valid ? __int_as_float(0xff800000) : (seed ? m : __int_as_float(0x7f800000));
+        if (seed) tile_flags[(by / FT) * tiles_x_c + bx / FT] = 1;        // benign race: every writer stores 1
+    }
+}
+
+// non-outlet cells of a coarse level start from the (solved) next coarser level instead of +inf
+__global__ void __launch_bounds__(256) fill_refine_kernel(float* __restrict__ w, int64_t pitch, int64_t ny, int64_t nx,
+                                                          const float* __restrict__ wc, int64_t c_pitch)
+{
+    for (CellIter it(nx); it.y < ny; it.next()) {
+        float* p = w + it.y * pitch + it.x;
+        if (*p == __int_as_float(0x7f800000)) *p = __ldg(wc + (it.y / CB) * c_pitch + it.x / CB);
     }
 }
 
@@ -549,8 +607,15 @@ int stream_grid(int64_t total)
 
 // flags: 1 = W already initialised (continue a banded fill), 2 / 4 = the top / bottom raster row is a halo row of a
 // neighbouring band (not frame); finish = restore NaN at nodata cells afterwards
+struct FillOpts {
+    bool preinit = false;         // W and the per-tile flags are already set up (coarse level)
+    bool seed_all = false;        // every tile starts queued (fine level of the multigrid start)
+    const float* wc = nullptr;    // coarse-level fill used as the starting W of interior cells
+    int64_t c_pitch = 0;
+};
+
 static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
-                        int* visits_out, cudaStream_t s, int flags = 0, bool finish = true)
+                        int* visits_out, cudaStream_t s, int flags = 0, bool finish = true, FillOpts opt = FillOpts())
 {
     const int tiles_x = hd_cdiv(nx, FT), tiles_y = hd_cdiv(ny, FT), ntiles = tiles_x * tiles_y;
     FillCtl* ctl = (FillCtl*)workspace;
@@ -570,18 +635,18 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     // (no host-to-device copy of a stack object here: the whole call must be capturable in a CUDA graph)
     HD_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(FillCtl), s));
     HD_CUDA_OK(cudaMemsetAsync(slots, 0xff, (size_t)qcap * sizeof(int), s));        // SLOT_EMPTY = -1
-    HD_CUDA_OK(cudaMemsetAsync(queued, 0, (size_t)ntiles * sizeof(int), s));
+    if (!opt.preinit) HD_CUDA_OK(cudaMemsetAsync(queued, 0, (size_t)ntiles * sizeof(int), s));
     fill_ctl_init_kernel<<<1, 1, 0, s>>>(ctl, qcap);
     HD_LAUNCH_CHECK();
-    if (!(flags & 1)) {
+    if (!(flags & 1) && !opt.preinit) {
         hd_prof_begin("fill_init_kernel", s);
         fill_init_kernel<<<stream_grid(ny * ((nx + 3) / 4)), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, flags & 2,
-                                                             flags & 4, queued, tiles_x, &ctl->any_nodata);
+                                                             flags & 4, queued, tiles_x, &ctl->any_nodata, opt.wc, opt.c_pitch);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
     hd_prof_begin("fill_seed_kernel", s);
     fill_seed_kernel<<<hd_cdiv(ntiles, 256) < 1184 ? hd_cdiv(ntiles, 256) : 1184, 256, 0, s>>>(
-        tiles_x, tiles_y, ny, ctl, slots, queued, (flags & 1) ? (flags & 6) : 0);
+        tiles_x, tiles_y, ny, ctl, slots, queued, opt.seed_all ? -1 : ((flags & 1) ? (flags & 6) : 0));
     HD_LAUNCH_CHECK(); hd_count_launch();
     hd_prof_begin("fill_async_kernel", s);
     fill_async_kernel<<<grid, FNT, smem, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, tiles_x, tiles_y, ctl,
@@ -611,11 +676,88 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     return HD_OK;
 }
 
-extern "C" int64_t hd_pdfill_workspace_bytes(int64_t ny, int64_t nx)
+static int64_t fill_level_bytes(int64_t ny, int64_t nx)
 {
     const int64_t ntiles = (int64_t)hd_cdiv(ny, FT) * hd_cdiv(nx, FT);
     // control block + FIFO ring (ntiles + slack) + per-tile flags; the sweep variant uses two flag arrays
-    return 256 + (2 * ntiles + 8192) * (int64_t)sizeof(int) + 2 * ntiles * (int64_t)sizeof(int);
+    const int64_t b = 256 + (2 * ntiles + 8192) * (int64_t)sizeof(int) + 2 * ntiles * (int64_t)sizeof(int);
+    return (b + 255) / 256 * 256;
+}
+static int64_t coarse_pitch(int64_t nxc) { return (nxc + 31) / 32 * 32; }
+constexpr int MAX_LEVELS = 8;
+// coarse levels exist while the next one still has a few tiles
+static bool level_worth_it(int64_t nyc, int64_t nxc) { return (int64_t)hd_cdiv(nyc, FT) * hd_cdiv(nxc, FT) >= 4; }
+
+extern "C" int64_t hd_pdfill_workspace_bytes(int64_t ny, int64_t nx)
+{
+    // fine level control block, then per coarse level: control block + that level's z and W rasters
+    int64_t total = fill_level_bytes(ny, nx);
+    for (int l = 1; l < MAX_LEVELS; ++l) {
+        const int64_t nyc = hd_cdiv(ny, CB), nxc = hd_cdiv(nx, CB);
+        if (!level_worth_it(nyc, nxc)) break;
+        total += fill_level_bytes(nyc, nxc) + 2 * nyc * coarse_pitch(nxc) * (int64_t)sizeof(float);
+        ny = nyc; nx = nxc;
+    }
+    return total;
+}
+
+// Multigrid start (see fill_pool_kernel): DEM -> coarser DEMs by block maxima; the coarsest level is filled from
+// scratch, every finer level starts from the fill of the level above it.
+static int pdfill_multilevel(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
+                             int* visits_out, cudaStream_t s)
+{
+    struct Level { int64_t ny, nx, pitch; float* z; float* w; char* ctl; };
+    Level lv[MAX_LEVELS];
+    int nlev = 0;
+    const char* off = getenv("HD_FILL_MULTILEVEL");
+    char* cur = (char*)workspace + fill_level_bytes(ny, nx);
+    int64_t lny = ny, lnx = nx;
+    if (!(off && off[0] == '0')) {
+        for (int l = 1; l < MAX_LEVELS; ++l) {
+            const int64_t nyc = hd_cdiv(lny, CB), nxc = hd_cdiv(lnx, CB);
+            if (!level_worth_it(nyc, nxc)) break;
+            Level& L = lv[nlev++];
+            L.ny = nyc; L.nx = nxc; L.pitch = coarse_pitch(nxc);
+            L.ctl = cur;
+            L.z = (float*)(cur + fill_level_bytes(nyc, nxc));
+            L.w = L.z + nyc * L.pitch;
+            cur = (char*)(L.w + nyc * L.pitch);
+            lny = nyc; lnx = nxc;
+        }
+    }
+    if (nlev == 0) return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, s);
+    // downward: block maxima + outlet marks of every level
+    for (int l = 0; l < nlev; ++l) {
+        const Level& L = lv[l];
+        const float* zin = l == 0 ? (const float*)z : lv[l - 1].z;
+        const float* win = l == 0 ? nullptr : lv[l - 1].w;
+        const int64_t pin = l == 0 ? z_pitch : lv[l - 1].pitch, iny = l == 0 ? ny : lv[l - 1].ny, inx = l == 0 ? nx : lv[l - 1].nx;
+        const int tiles_x_c = hd_cdiv(L.nx, FT), ntiles_c = tiles_x_c * hd_cdiv(L.ny, FT);
+        int* queued_c = (int*)(L.ctl + 256) + (ntiles_c + 8192);
+        HD_CUDA_OK(cudaMemsetAsync(queued_c, 0, (size_t)ntiles_c * sizeof(int), s));
+        hd_prof_begin("fill_pool_kernel", s);
+        fill_pool_kernel<<<stream_grid(L.ny * L.nx), 256, 0, s>>>(zin, pin, iny, inx, L.z, L.w, L.pitch, L.ny, L.nx, queued_c,
+                                                                  tiles_x_c, win);
+        HD_LAUNCH_CHECK(); hd_count_launch();
+    }
+    // upward: coarsest level from scratch, every finer one from the level above
+    for (int l = nlev - 1; l >= 0; --l) {
+        const Level& L = lv[l];
+        FillOpts o;
+        o.preinit = true;
+        if (l < nlev - 1) {
+            hd_prof_begin("fill_refine_kernel", s);
+            fill_refine_kernel<<<stream_grid(L.ny * L.nx), 256, 0, s>>>(L.w, L.pitch, L.ny, L.nx, lv[l + 1].w, lv[l + 1].pitch);
+            HD_LAUNCH_CHECK(); hd_count_launch();
+            o.seed_all = true;
+        }
+        if (int e = pdfill_async(L.z, L.pitch, L.w, L.pitch, L.ny, L.nx, L.ctl, nullptr, s, 0, false, o)) return e;
+    }
+    FillOpts fine;
+    fine.seed_all = true;
+    fine.wc = lv[0].w;
+    fine.c_pitch = lv[0].pitch;
+    return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, s, 0, true, fine);
 }
 
 extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
@@ -628,7 +770,7 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
     const int tiles_x = hd_cdiv(nx, FT), tiles_y = hd_cdiv(ny, FT), ntiles = tiles_x * tiles_y;
     const char* mode = getenv("HD_FILL_MODE");
     if (!(mode && mode[0] == 's') && max_sweeps <= 0)
-        return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, sweeps_out, s);
+        return pdfill_multilevel(z, z_pitch, w, w_pitch, ny, nx, workspace, sweeps_out, s);
     FillCounters* counters = (FillCounters*)workspace;
     int* flags_a = (int*)((char*)workspace + 256);
     int* flags_b = flags_a + ntiles;

@@ -247,7 +247,7 @@ class _StreamSlot:
                     # not int16-representable: fetch the float32 raster itself (still intact: the slot is not reused
                     # before this tile has been collected)
                     arr = dev.download(raster.with_ref(np_dtype))
-                elif arr.dtype != np_dtype:                           # int16 -> float32 / float64 on host threads
+                elif arr.dtype != np_dtype and not os.environ.get("HD_STREAM_NO_WIDEN"):   # int16 -> float32 / float64 on host threads (the switch is for bandwidth experiments only)
                     wide = dev.pinned_empty(arr.shape, np_dtype)
                     _lib.check(lib.hd_host_widen_i16(ctypes.c_void_p(wide.ctypes.data), dev.hd_dtype_of(np_dtype),
                                                      ctypes.c_void_p(arr.ctypes.data), arr.size, self.host_threads))
@@ -386,8 +386,17 @@ class ConditioningChain:
         rasters and the chain captured as four CUDA-graph segments; tile i+1 uploads while tile i computes and tile
         i-1 downloads, so the steady-state cost per tile is max(kernels, H2D, D2H) instead of their sum."""
         import collections
+        import torch
         rings = self.__dict__.setdefault("_slot_rings", {})
+        # Waiting for a tile's downloads and widening its int16 results (2 ms of host threads per 3601^2 tile) happens on
+        # a helper thread, so that this thread is free to enqueue the following tiles; both release the GIL.
+        pool = self._collector(torch.cuda.current_device()) if depth > 1 else None
         inflight = collections.deque()
+
+        def launch(slot, arrays):
+            collect = slot.submit(arrays)
+            return pool.submit(collect).result if pool is not None else collect
+
         for k, item in enumerate(items):
             arrays = self._check_inputs(*item)
             # one tile at a time (depth 1) is a latency call: the filled DEM then travels as float32, because widening it
@@ -403,15 +412,29 @@ class ConditioningChain:
             while any(s is slot for s, _ in inflight):               # the slot's previous tile must be collected first
                 yield inflight.popleft()[1]()
             self.last_transfer_bytes = slot.transfer_bytes           # (H2D, D2H) PCIe bytes of one tile
-            inflight.append((slot, slot.submit(arrays)))
+            inflight.append((slot, launch(slot, arrays)))
             while len(inflight) >= depth:
                 yield inflight.popleft()[1]()
         while inflight:
             yield inflight.popleft()[1]()
 
+    def _collector(self, device_index):
+        """One helper thread per chain (results come back in order), bound to this process's device."""
+        pool = self.__dict__.get("_collect_pool")
+        if pool is None:
+            import concurrent.futures
+            import torch
+            pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="hydrodem-collect",
+                                                         initializer=torch.cuda.set_device, initargs=(device_index,))
+            self._collect_pool = pool
+        return pool
+
     def release(self):
         """Drop the captured slots of ``stream`` / ``apply_to_host`` (their device memory returns to the allocator)."""
         self.__dict__.pop("_slot_rings", None)
+        pool = self.__dict__.pop("_collect_pool", None)
+        if pool is not None:
+            pool.shutdown(wait=True)
 
     def _check_inputs(self, srtm_raw, groves_class_raw, hsheds, rivers=None):
         arrays = dict(srtm=srtm_raw, groves=groves_class_raw, hsheds=hsheds)

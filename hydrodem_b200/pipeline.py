@@ -136,6 +136,8 @@ class _StreamSlot:
         self.transfer_bytes = (sum(size(t) for t in self.dense_in.values()), sum(size(t) for t in self.dense_out.values()))
         local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
         self.host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(local, 1)))
+        if os.environ.get("HD_HOST_THREADS"):
+            self.host_threads = max(1, int(os.environ["HD_HOST_THREADS"]))
         self.ev_compute = self.ev_down = None
         self.keep = None
 

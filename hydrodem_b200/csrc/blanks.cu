@@ -8,8 +8,10 @@
 // takes np.nanmean of what is left and flags the cell when centre > 4 * mean.
 //
 // Kernel: a 64x64 tile with a 27-cell halo is staged by TMA (zero fill outside the quarter = "not counted"),
-// a float64 integral image of the 118x120 box is built in shared memory (one serial pass down the columns, one
-// along the rows -- both conflict free), and each output needs 8 integral-image reads: big box minus inner box.  The number of valid
+// a float64 integral image of the 118x120 box is built in shared memory (column sums as 4 row segments x 120
+// columns with segment offsets, then one thread per row along the columns -- both conflict free), and each output
+// needs 8 integral-image reads: big box minus inner box.  The tile's own cells are copied aside first, so the TMA
+// load of the next tile overlaps the row pass and the outputs.  The number of valid
 // cells is analytic (clipped 55x55 minus clipped 5x5).  float64 sums of float32 data are exact to ~1e-16, the
 // reference's float32 pairwise nanmean to ~1e-7: the stage is tolerance class, the mask is expected to be
 // identical (mismatch count reported by the tests).  NaN cells INSIDE the quarter are not skipped (they

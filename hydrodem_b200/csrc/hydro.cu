@@ -8,14 +8,17 @@
 // the racy, in-place one used here -- converges to the same bits: the result does not depend on the
 // schedule, the tile size or the number of GPUs.
 //
-// Kernel: one CTA per ACTIVE 64x64 tile.  z (no halo) and W (one-cell halo, NaN fill outside the raster so
-// that fminf ignores it) are staged by TMA; four groups of 64 threads march down / up / right / left through
-// the tile simultaneously (a marching sweep carries a level across the whole tile in one pass) until a
-// __syncthreads_or sees no change.  A changed tile writes W back and re-activates itself and its 8
-// neighbours for the next global sweep; the host stops when a sweep changes nothing.  Warp-aggregated: one
-// vote per thread group, one atomic per changed tile.
+// Kernels:
+//   fill_async_kernel   the default on one GPU and per band: persistent CTAs pull 64x64 tiles from a device-side FIFO,
+//                       relax each to its local fixed point (check pass + four simultaneous marching sweeps) and poke
+//                       exactly the neighbours whose cells can still be lowered;
+//   fill_pool_kernel /  multigrid start: block maxima give coarse DEMs whose fill is an upper bound of the fine fill, so
+//   fill_refine_kernel  every level starts from the level above instead of +inf (same result, no raster-crossing wave);
+//   fill_sweep_kernel   the simple variant (HD_FILL_MODE=sweep): one launch per global sweep over the active tiles, z and
+//                       W staged by TMA; kept as an independent cross-check of the worklist kernel;
+//   d8_kernel           flow directions of the filled surface.
 //
-// Algorithmic HBM traffic: 4 B (z) + 4 B (W) read + 4 B (W) written per cell of an active tile per sweep.
+// Algorithmic HBM traffic: 4 B (z) + 4 B (W) read + 4 B (W) written per cell of a visited tile.
 #include <cstdio>
 #include <cstdlib>
 

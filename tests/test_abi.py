@@ -70,3 +70,32 @@ def test_no_cpu_fallback(lib):
         ExpandFilter(window_size=3).apply(np.zeros((8, 8), dtype=np.float32))
     p = ctypes.c_void_p(1 << 20)
     assert lib.hd_expand(p, _lib.F32, 64, p, _lib.U8, 64, 64, 64, 7, None) == _lib.HD_ERR_CUDA
+
+
+def test_host_widen_helpers_are_exact():
+    """hd_host_widen_*: HOST functions of the C ABI (no device needed): int16 / float32 results widened to the
+    reference dtypes on several threads, any alignment, every value exact."""
+    import ctypes
+    import numpy as np
+    from hydrodem_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    n = 200_003
+    src16 = rng.integers(-32768, 32768, n + 9).astype(np.int16)
+    src32 = rng.standard_normal(n + 9).astype(np.float32) * 1e3
+    for off in (0, 1, 3):
+        for threads in (1, 5):
+            for dt, code in ((np.float32, _lib.F32), (np.float64, _lib.F64)):
+                dst = np.full(n + 8, -7, dtype=dt)
+                rc = lib.hd_host_widen_i16(ctypes.c_void_p(dst.ctypes.data + dst.itemsize * off), code,
+                                           ctypes.c_void_p(src16.ctypes.data + 2 * off), n, threads)
+                assert rc == 0
+                np.testing.assert_array_equal(dst[off:off + n], src16[off:off + n].astype(dt))
+                assert (dst[:off] == -7).all() and (dst[off + n:] == -7).all()
+            dst = np.full(n + 8, -7.0)
+            rc = lib.hd_host_widen_f32_f64(ctypes.c_void_p(dst.ctypes.data + 8 * off),
+                                           ctypes.c_void_p(src32.ctypes.data + 4 * off), n, threads)
+            assert rc == 0
+            np.testing.assert_array_equal(dst[off:off + n], src32[off:off + n].astype(np.float64))
+            assert (dst[:off] == -7).all() and (dst[off + n:] == -7).all()
+    assert lib.hd_host_widen_i16(None, _lib.F32, None, 4, 1) != 0

@@ -121,7 +121,9 @@ def test_banded_chain_matches_single_gpu(world):
     got = {k: np.concatenate([r[k] for r in res]) for k in res[0]}
     np.testing.assert_allclose(got["dem_complete"], want_complete, rtol=1e-5)
     flips = got["final"] != want_final
-    frac = np.abs(want_complete - np.floor(want_complete) - 0.5)
-    assert flips.mean() < 1e-3
+    from scipy import ndimage
+    mean = ndimage.convolve(want_complete, np.ones((3, 3)), mode="reflect") / 9.0
+    frac = np.abs(mean - np.floor(mean) - 0.5)
+    assert flips.mean() < 1e-3 and (frac[flips] < 5e-3).all()          # only where the mean sits on a half-integer
     np.testing.assert_array_equal(got["filled"], hydrology.sinkfill(got["final"]))
     np.testing.assert_array_equal(got["d8"], hydrology.d8(got["filled"]))

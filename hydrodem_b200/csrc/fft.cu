@@ -264,6 +264,15 @@ __device__ __forceinline__ void pass_twiddles(float2 (&w)[1 << K], const float2*
     }
 }
 
+// Which group a thread takes.  With a group stride of 8 elements and radix 8 the 32 lanes of a warp touch four
+// clusters of 8 consecutive elements, 64 elements (+4 of padding) apart: 8 banks.  The two clusters of a half-warp
+// (64-bit accesses are served per half-warp) then overlap in 8 banks -- a 2-way conflict on two of the seven
+// shared-memory sweeps.  Swapping lane bits 3 and 4 pairs clusters 0/2 and 1/3, which are 16 banks apart.
+__device__ __forceinline__ int lane_group(int g, int lgst, int k)
+{
+    return (lgst == 3 && k == 3) ? ((g & ~24) | ((g & 8) << 1) | ((g & 16) >> 1)) : g;
+}
+
 // One DIF pass over sub-transforms of length L (log2 = lgL); tw = full-circle table exp(-2 pi i k / m).
 // MULB: multiply the outputs by bhat[position] on the way out (the Bluestein pointwise product, fused).
 template <int K, bool MULB>
@@ -272,7 +281,8 @@ __device__ __forceinline__ void dif_pass(float2* s, int m, int lgm, int lgL, con
 {
     constexpr int R = 1 << K;
     const int lgst = lgL - K, st = 1 << lgst, tshift = lgm - lgL;
-    for (int g = threadIdx.x; g < (m >> K); g += FNT) {
+    for (int g0 = threadIdx.x; g0 < (m >> K); g0 += FNT) {
+        const int g = lane_group(g0, lgst, K);
         const int r = g & (st - 1);
         const int base = ((g - r) << K) + r;
         float2 x[R];
@@ -300,7 +310,8 @@ __device__ __forceinline__ void dit_pass(float2* s, int m, int lgm, int lgL, con
 {
     constexpr int R = 1 << K;
     const int lgst = lgL - K, st = 1 << lgst, tshift = lgm - lgL;
-    for (int g = threadIdx.x; g < (m >> K); g += FNT) {
+    for (int g0 = threadIdx.x; g0 < (m >> K); g0 += FNT) {
+        const int g = lane_group(g0, lgst, K);
         const int r = g & (st - 1);
         const int base = ((g - r) << K) + r;
         float2 x[R], w[R];

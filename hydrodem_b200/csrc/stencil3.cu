@@ -125,28 +125,33 @@ __global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUten
     const uint32_t stage_bytes = (uint32_t)((in_w * IN_H3 * sizeof(T) + 127) / 128 * 128);
     constexpr int HX = hd_halo_x(1, sizeof(T));
     const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(in_w * IN_H3 * sizeof(T)), HX, 1}};
+    // V consecutive cells per thread = one 16-byte shared-memory read per window row: lanes 16 bytes apart are
+    // conflict free (four float64 cells per thread, 32 bytes apart, made every LDS.128 a 2-way conflict)
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int TPR = TW / V;                                  // threads per tile row
     tile_loop<1>(smem, stage_bytes, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         T* tile = reinterpret_cast<T*>(st);
         patch_reflect<T>(tile, in_w, IN_H3, ty0 - 1, tx0 - HX, ny, nx);
 #pragma unroll
-        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+        for (int rep = 0; rep < TH * TW / V / NT; ++rep) {
             const int idx = rep * NT + threadIdx.x;
-            const int ro = idx >> 5, c4 = idx & 31;
-            const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+            const int ro = idx / TPR, cv = idx % TPR;
+            const int64_t y = ty0 + ro, x = tx0 + V * cv;
             if (y >= ny || x >= nx) continue;
-            const T* c = tile + ro * in_w + 4 * c4 + HX;      // first of the 4 centre columns, top window row
-            T win[3][6];                                      // 3 window rows x (4 centres + left and right neighbour)
+            const T* c = tile + ro * in_w + V * cv + HX;      // first of the V centre columns, top window row
+            T win[3][V + 2];                                  // 3 window rows x (V centres + left and right neighbour)
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-                T q[4];
-                load_quad<T>(c + dy * in_w, q);
+                const int4 raw = *reinterpret_cast<const int4*>(c + dy * in_w);
+                const T* q = reinterpret_cast<const T*>(&raw);
                 win[dy][0] = c[dy * in_w - 1];
-                win[dy][1] = q[0]; win[dy][2] = q[1]; win[dy][3] = q[2]; win[dy][4] = q[3];
-                win[dy][5] = c[dy * in_w + 4];
-            }
-            T v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < V; ++j) win[dy][j + 1] = q[j];
+                win[dy][V + 1] = c[dy * in_w + V];
+            }
+            T v[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
                 double acc = 0.0;                             // NI_Correlate: tmp = 0; tmp += in * w, row-major
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy)
@@ -157,10 +162,23 @@ __global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUten
                     }
                 v[j] = div_round<T>((T)acc, p.divisor, p.do_round);
             }
-            store4v<T>(out, out_pitch, y, x, nx, v);
+            T* po = out + y * out_pitch + x;
+            if (x + V - 1 < nx && ((reinterpret_cast<uintptr_t>(po) & 15) == 0)) {
+                int4 packed;
+                T* pv = reinterpret_cast<T*>(&packed);
+#pragma unroll
+                for (int j = 0; j < V; ++j) pv[j] = v[j];
+                *reinterpret_cast<int4*>(po) = packed;
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (x + j < nx) po[j] = v[j];
+            }
             if (out32) {                                      // optional float32 copy of the result (feeds the sink-fill)
-                const float f[4] = {(float)v[0], (float)v[1], (float)v[2], (float)v[3]};
-                store4<float>(out32, out32_pitch, y, x, nx, f);
+                float* p32 = out32 + y * out32_pitch + x;
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (x + j < nx) p32[j] = (float)v[j];
             }
         }
     });

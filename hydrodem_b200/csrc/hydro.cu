@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(int tiles_x, int tiles_y
 __global__ void __launch_bounds__(256) fill_pool_kernel(const float* __restrict__ z, int64_t z_pitch, int64_t ny, int64_t nx,
                                                         float* __restrict__ zc, float* __restrict__ wc, int64_t c_pitch,
                                                         int64_t nyc, int64_t nxc, int* __restrict__ tile_flags, int tiles_x_c,
-                                                        const float* __restrict__ w_in)
+                                                        const float* __restrict__ w_in, int top_is_halo, int bottom_is_halo)
 {
     for (CellIter it(nxc); it.y < nyc; it.next()) {
         const int64_t by = it.y, bx = it.x, y0 = by * CB, x0 = bx * CB;
@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(256) fill_pool_kernel(const float* __restrict_
                 }
             }
         }
-        const bool frame = y0 == 0 || x0 == 0 || y0 + CB >= ny || x0 + CB >= nx;
+        // (the first / last row of a band that continues on another GPU is a halo row, not raster frame)
+        const bool frame = (y0 == 0 && !top_is_halo) || x0 == 0 || (y0 + CB >= ny && !bottom_is_halo) || x0 + CB >= nx;
         const bool seed = has_nan || frame;
         zc[by * c_pitch + bx] = any_valid ? m : __int_as_float(0x7fc00000);
         wc[by * c_pitch + bx] = !any_valid ? __int_as_float(0xff800000) : (seed ? m : __int_as_float(0x7f800000));
@@ -707,7 +708,7 @@ extern "C" int64_t hd_pdfill_workspace_bytes(int64_t ny, int64_t nx)
 // Multigrid start (see fill_pool_kernel): DEM -> coarser DEMs by block maxima; the coarsest level is filled from
 // scratch, every finer level starts from the fill of the level above it.
 static int pdfill_multilevel(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
-                             int* visits_out, cudaStream_t s)
+                             int* visits_out, cudaStream_t s, int flags = 0, bool finish = true)
 {
     struct Level { int64_t ny, nx, pitch; float* z; float* w; char* ctl; };
     Level lv[MAX_LEVELS];
@@ -728,7 +729,7 @@ static int pdfill_multilevel(const void* z, int64_t z_pitch, void* w, int64_t w_
             lny = nyc; lnx = nxc;
         }
     }
-    if (nlev == 0) return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, s);
+    if (nlev == 0) return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, s, flags, finish);
     // downward: block maxima + outlet marks of every level
     for (int l = 0; l < nlev; ++l) {
         const Level& L = lv[l];
@@ -740,7 +741,7 @@ static int pdfill_multilevel(const void* z, int64_t z_pitch, void* w, int64_t w_
         HD_CUDA_OK(cudaMemsetAsync(queued_c, 0, (size_t)ntiles_c * sizeof(int), s));
         hd_prof_begin("fill_pool_kernel", s);
         fill_pool_kernel<<<stream_grid(L.ny * L.nx), 256, 0, s>>>(zin, pin, iny, inx, L.z, L.w, L.pitch, L.ny, L.nx, queued_c,
-                                                                  tiles_x_c, win);
+                                                                  tiles_x_c, win, flags & 2, flags & 4);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
     // upward: coarsest level from scratch, every finer one from the level above
@@ -754,13 +755,13 @@ static int pdfill_multilevel(const void* z, int64_t z_pitch, void* w, int64_t w_
             HD_LAUNCH_CHECK(); hd_count_launch();
             o.seed_all = true;
         }
-        if (int e = pdfill_async(L.z, L.pitch, L.w, L.pitch, L.ny, L.nx, L.ctl, nullptr, s, 0, false, o)) return e;
+        if (int e = pdfill_async(L.z, L.pitch, L.w, L.pitch, L.ny, L.nx, L.ctl, nullptr, s, flags & 6, false, o)) return e;
     }
     FillOpts fine;
     fine.seed_all = true;
     fine.wc = lv[0].w;
     fine.c_pitch = lv[0].pitch;
-    return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, s, 0, true, fine);
+    return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, s, flags, finish, fine);
 }
 
 extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
@@ -830,6 +831,8 @@ extern "C" int hd_pdfill_band(const void* z, int64_t z_pitch, void* w, int64_t w
     if (!z || !w || !workspace) return HD_ERR_NULL;
     if (ny < 1 || nx < 1 || z_pitch < nx || w_pitch < nx || (flags & ~7)) return HD_ERR_ARG;
     if (workspace_bytes < hd_pdfill_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
+    if (!(flags & 1))       // first round of a band: multigrid start (halo rows are not outlets); later rounds continue
+        return pdfill_multilevel(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, (cudaStream_t)stream, flags, false);
     return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, (cudaStream_t)stream, flags, false);
 }
 

@@ -433,7 +433,9 @@ class FourierProcessQuarters(Filter):
         self.pair_mid = self._mid_y, self._mid_x
         self._margin = FOURIER_MARGIN
 
-    def run_device(self, fabs=None, invert=False, out_dtype=None):
+    def run_device(self, fabs=None, invert=False, out_dtype=None, mask_fn=None):
+        """``mask_fn(quarter) -> U8 mask``: MaskFourier by default; the row-band sharded chain passes a version that
+        computes each rank's rows of the quarter only (hydrodem_b200/sharding.py)."""
         fabs = fabs if fabs is not None else self.fft_transform_abs
         if isinstance(fabs, np.ndarray):
             fabs = dev.upload(fabs)
@@ -447,9 +449,9 @@ class FourierProcessQuarters(Filter):
         x0 = self._mid_x + m + self._x_odd
         q2 = dev.empty(qh, qw, _lib.F32)                                     # [:my-m, mx+m+x_odd:nx]  (:945-947)
         dev.elementwise(_lib.OP_COPY, fabs.sub(0, qh, x0, self._nx), None, 0.0, q2)
-        mf = MaskFourier()
-        m1 = mf.run_device(q1)
-        m2 = mf.run_device(q2)
+        mask_fn = mask_fn or MaskFourier().run_device
+        m1 = mask_fn(q1)
+        m2 = mask_fn(q2)
         out_dtype = _lib.U8 if out_dtype is None else out_dtype
         out = dev.empty(self._ny, self._nx, out_dtype, np.float64)
         _lib.check(_lib.load().hd_fourier_mask_assemble(m1.ptr, m1.pitch, m2.ptr, m2.pitch, out.ptr, out.dtype, out.pitch,

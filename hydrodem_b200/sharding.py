@@ -259,10 +259,34 @@ class Band:
         rows = self._exchange_transposed(t, cols_b, rows_b)               # (my rows, nx)
         return self._rows_fft(rows, self.nx, True, False)
 
+    # rows of context a cell of MaskFourier depends on: two hollow-mean passes (27 each), IsolatedPoints (1), Expand 13 (6)
+    _MASK_HALO = 2 * 27 + 1 + 6
+
+    def _quarter_mask(self, quarter):
+        """MaskFourier (custom_filters.py:537-561) of one spectrum quarter with the COMPUTE split over the ranks: every
+        rank holds the whole |F| (all-gathered), runs the detector on its rows of the quarter plus 61 rows of context
+        cut from its own copy -- windows are clipped only at the true edges of the quarter, rows near a cut are
+        discarded -- and the U8 mask slabs are all-gathered."""
+        from .filters import custom_filters as cf
+        comm = self.comm
+        qh, qw = quarter.shape
+        bounds = band_bounds(qh, comm.world)
+        if min(b - a for a, b in bounds) < 16:                     # tiny quarters: not worth cutting
+            return cf.MaskFourier().run_device(quarter)
+        a, b = bounds[comm.rank]
+        lo, hi = max(0, a - self._MASK_HALO), min(qh, b + self._MASK_HALO)
+        m = cf.MaskFourier().run_device(quarter.sub(lo, hi, 0, qw))
+        mine = dev.convert(m, _lib.U8).tensor()[a - lo:b - lo].contiguous()
+        parts = comm.all_to_all_shaped([mine] * comm.world, [(bb - aa, qw) for (aa, bb) in bounds])
+        full = dev.empty(qh, qw, _lib.U8, np.float64)
+        full.tensor().copy_(torch.cat(parts, dim=0))
+        return full
+
     def detect_apply_fourier(self, band):
         """DetectApplyFourier (custom_filters.py:1053-1101) on a banded mosaic: distributed forward transform, the
-        |F| bands all-gathered so that every rank runs the (cheap, window-55) peak detector and the point-mirrored
-        mask assembly on the whole spectrum, mask applied to the local spectrum band, distributed inverse, abs.
+        |F| bands all-gathered (every rank holds the whole magnitude spectrum), the window-55 peak detector computed in
+        row slabs of the quarters split over the ranks and its masks all-gathered, point-mirrored mask assembly, mask
+        applied to the local spectrum band, distributed inverse, abs.
         Returns this rank's rows of the stripe-free DEM (F32 storage, float64 reference dtype)."""
         from .filters import custom_filters as cf, extension_filters as ef
         comm = self.comm
@@ -276,7 +300,8 @@ class Band:
         fabs = dev.empty(self.ny, self.nx, _lib.F32, np.float32)
         fabs.tensor().copy_(torch.cat(parts, dim=0).t())                   # |F| in natural (ny, nx) layout
         fabs_shift = ef.FourierShift().run_device(fabs)                    # FourierInitial, custom_filters.py:859-877
-        keep = cf.FourierProcessQuarters(fabs_shift).run_device(fabs_shift, invert=True, out_dtype=_lib.F32)   # 1 - mask
+        keep = cf.FourierProcessQuarters(fabs_shift).run_device(fabs_shift, invert=True, out_dtype=_lib.F32,
+                                                                mask_fn=self._quarter_mask)            # 1 - mask
         keep = ef.FourierIShift().run_device(keep)                         # back to the unshifted layout of F
         keep_t = dev.empty(spec_t.ny, spec_t.nx, _lib.F32, np.float32)
         keep_t.tensor().copy_(keep.tensor()[:, c0:c1].t())                 # this rank's columns, transposed

@@ -11,8 +11,10 @@ sink-fill, D8.  A "step" is one pass of the chain over one tile.  At N > 1 every
 
 Numbers on the JSON line
   value     whole-job Mcells/s with the inputs resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e       the same through the public API with HOST buffers: ConditioningChain.apply(ndarrays) -> host arrays,
-            pinned H2D of the three input rasters and D2H of final DEM / filled DEM / D8 inside the timed region
+  e2e       the same through the public API with HOST buffers: `for out in ConditioningChain.stream(tiles)` -- every
+            step uploads its three input rasters from pinned host memory and hands back final DEM / filled DEM / D8
+            as host arrays, all inside the timed region; copies of neighbouring steps overlap the kernels.  The
+            latency of ONE tile through ConditioningChain.apply_to_host is reported next to it.
   roofline  dominant kernel of the step: algorithmic bytes per launch / average launch time, measured live with a
             CUDA event pair around every launch (hd_profile_*), against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle port (oracle/chain.py) timed on rank 0, one core, on a bounded sample tile

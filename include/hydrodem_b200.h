@@ -206,8 +206,10 @@ int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch,
 
 /* ---- NEW hydrology stages (not in the reference) ----------------------------------- */
 /* Sink-fill: Planchon-Darboux fixed point with eps = 0, 8-connectivity; frame cells and NaN cells are outlets.
- * z, w: F32.  Default (max_sweeps <= 0): one persistent worklist kernel; asynchronous unless sweeps_out is given
- * (then the stream is synchronised once and *sweeps_out = tile visits).  max_sweeps > 0 or HD_FILL_MODE=sweep:
+ * z, w: F32.  Default (max_sweeps <= 0): persistent worklist kernels with a multigrid start (coarse DEMs of 8x8 block
+ * maxima are filled first: their fill is an upper bound of the answer and replaces +inf as the starting surface;
+ * the result is the same unique fixed point); asynchronous and capturable in a CUDA graph unless sweeps_out is
+ * given (then the stream is synchronised once and *sweeps_out = tile visits of the finest level).  max_sweeps > 0 or HD_FILL_MODE=sweep:
  * level-synchronous tile sweeps, the stream is synchronised every few sweeps, *sweeps_out = sweeps executed. */
 int64_t hd_pdfill_workspace_bytes(int64_t ny, int64_t nx);
 int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,

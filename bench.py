@@ -158,7 +158,7 @@ def run_reference(args):
     import multiprocessing as mp
     from oracle import clib
     clib.build()
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1          # the cores this process may actually use
     size = args.cpu_sample
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
@@ -174,7 +174,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"full conditioning chain, synthetic {TILE}x{TILE} SRTM tile per GPU",
+        "config": {"workload": f"full conditioning chain, synthetic {TILE}x{TILE} SRTM 1-arcsec tile per GPU "
+                               "(BASELINE.json configs[1])",
                    "sample": f"{cores} x {size}x{size} tiles per step (cost is linear in cells)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"oracle/chain.py on {cores} processes x {size}x{size} synthetic tiles per step"},

@@ -144,3 +144,24 @@ def test_stream_falls_back_to_float32_transport():
     np.testing.assert_array_equal(got[1]["final"], want_ok.final)
     np.testing.assert_array_equal(got[1]["filled"], want_ok.filled)
     assert got[1]["final"].dtype == np.float64 and got[1]["filled"].dtype == np.float32
+
+
+def test_stream_errors_propagate_and_chain_stays_usable():
+    """A tile the Fourier stage cannot take (a spectrum quarter smaller than the 55-cell detector window,
+    custom_filters.py:395-427 via sliding_window.py:151-156) raises the reference's WindowSizeHighError out of
+    ``stream``; wrong argument types raise NumpyArrayExpectedError; the chain object keeps working afterwards."""
+    from hydrodem_b200.exceptions import NumpyArrayExpectedError, WindowSizeHighError
+    chain = ConditioningChain()
+    small = SynthScene(120, 120, 5)
+    with pytest.raises(WindowSizeHighError):
+        list(chain.stream([(small.srtm(), small.groves(), small.hsheds())]))
+    with pytest.raises(NumpyArrayExpectedError):
+        list(chain.stream([(small.srtm().tolist(), small.groves(), small.hsheds())]))
+    with pytest.raises(ValueError):
+        list(chain.stream([(small.srtm()[:100], small.groves(), small.hsheds())]))
+    ok = SynthScene(200, 260, 6)
+    want = chain.apply(ok.srtm(), ok.groves(), ok.hsheds())
+    got = list(chain.stream([(ok.srtm(), ok.groves(), ok.hsheds())] * 2))
+    for g in got:
+        np.testing.assert_array_equal(g["final"], want.final)
+        np.testing.assert_array_equal(g["d8"], want.d8)

@@ -98,21 +98,34 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
                 if (NWIN + b.n >= 2 * min_count) {
                     const float* w = tile + ro * IN_W + xo + XOFF;     // top-left of the window
                     int count = 0;
-                    float first = b.c;
-                    bool found = false;
+                    if (b.c == 0.f) {
+                        // Counter keeps the first-inserted key of an == class: +0.0 and -0.0 need the scan order
+                        float first = b.c;
+                        bool found = false;
 #pragma unroll
-                    for (int dy = 0; dy < WS; ++dy) {
+                        for (int dy = 0; dy < WS; ++dy) {
 #pragma unroll
-                        for (int dx = 0; dx < WS; ++dx) {
-                            if ((dy == 0 || dy == WS - 1) && (dx == 0 || dx == WS - 1)) continue;   // NaN corners
-                            const float v = w[dy * IN_W + dx];
-                            const bool eq = (v == b.c);
-                            // Counter keeps the first-inserted key of an == class (0.0 vs -0.0)
-                            if (eq && !found) { first = v; found = true; }
-                            count += eq;
+                            for (int dx = 0; dx < WS; ++dx) {
+                                if ((dy == 0 || dy == WS - 1) && (dx == 0 || dx == WS - 1)) continue;   // NaN corners
+                                const float v = w[dy * IN_W + dx];
+                                const bool eq = (v == b.c);
+                                if (eq && !found) { first = v; found = true; }
+                                count += eq;
+                            }
                         }
+                        if (count >= min_count) result = first;        // count > (ws^2-1)*0.7  (:71-72)
+                    } else {
+                        // any other value: equal floats are the same bits, the candidate itself is the first key
+#pragma unroll
+                        for (int dy = 0; dy < WS; ++dy) {
+#pragma unroll
+                            for (int dx = 0; dx < WS; ++dx) {
+                                if ((dy == 0 || dy == WS - 1) && (dx == 0 || dx == WS - 1)) continue;   // NaN corners
+                                count += (w[dy * IN_W + dx] == b.c);
+                            }
+                        }
+                        if (count >= min_count) result = b.c;
                     }
-                    if (count >= min_count) result = first;            // count > (ws^2-1)*0.7  (:71-72)
                 }
             }
             out[y * out_pitch + x] = (OutT)result;

@@ -198,10 +198,21 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (the conditioning path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its banner ("NCCL version ...") and any NCCL_DEBUG output to stdout by default: stdout carries
-        # exactly one JSON line, so send NCCL's log to stderr
+        # NCCL writes its banner ("NCCL version ...") and any NCCL_DEBUG output to stdout (NCCL_DEBUG_FILE is ignored at
+        # NCCL_DEBUG=VERSION): stdout carries exactly one JSON line, so file descriptor 1 points at stderr while the
+        # communicator is created and the first collective runs
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     lib = _lib.load()
     ny = nx = args.size
 

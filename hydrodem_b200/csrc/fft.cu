@@ -18,13 +18,16 @@
 // The 2-D transform is rows -> tiled transpose -> rows -> tiled transpose; fftshift / ifftshift, |.|, and
 // the (1 - mask) product are folded into the load / store index arithmetic of those passes, so the shifted
 // spectrum is never materialised separately.
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <complex>
 #include <utility>
 #include <vector>
 
 #include "common.cuh"
+#include "fft_radix.cuh"
 
 namespace {
 
@@ -33,20 +36,26 @@ constexpr int MAX_M = 16384;             // 136 KB of (padded) complex64 in shar
 constexpr double PI = 3.14159265358979323846;
 
 // Rows longer than one shared-memory transform are split once, Cooley-Tukey style: N = n1 * n2 with a SMALL n1
-// (3, 5, 7 ...) and n2 <= 8192.  For each k1 < n1 one CTA transforms the length-n2 sequence
-//     y_k1[j] = W_N^(j k1) * sum_a x[a n2 + j] W_n1^(a k1)          (n1-point DFT + twiddle, done while loading)
+// (3, 5, 7 ... <= 8) and n2 <= 8192.  For each k1 < n1 one CTA of a thread-block cluster transforms the sequence
+//     y_k1[j] = W_N^(j k1) * sum_a x[a n2 + j] W_n1^(a k1)          (n1-point DFT + twiddle: long_row_stage, via DSMEM)
 // and X[k1 + n1 k2] = FFT_n2(y_k1)[k2].  The result is STORED as [k1][k2] (contiguous writes); the transposes
 // that follow every row pass undo this permutation in their index arithmetic, so it costs no extra pass.
 struct Plan1D {
     int n_total = 0, n1 = 1;             // n_total = n1 * n   (n = length transformed in shared memory)
-    float2* d_w1 = nullptr;              // [n1 * n1]  exp(-2 pi i a b / n1)
-    float2* d_wn = nullptr;              // [n_total]  exp(-2 pi i j / n_total)
+    float2* d_wn = nullptr;              // [n1][n]    exp(-2 pi i j k1 / n_total)
     int n = 0, m = 0, log2m = 0;
     bool bluestein = false;
     int npass = 0, k[4] = {0, 0, 0, 0};  // radix-2^k passes (DIF order)
     float2* d_tw = nullptr;              // [m]    exp(-2 pi i k / m), full circle
     float2* d_w = nullptr;               // [n]    chirp exp(-i pi k^2 / n)                  (Bluestein only)
     float2* d_bhat = nullptr;            // [m]    FFT_m(conj chirp) / m, bit-reversed order (Bluestein only)
+    // lengths 2^a 3^b 5^c that are not powers of two (6000, 7200: the sub-rows of the 18000 / 36000 mosaics) run as
+    // plain mixed-radix transforms: no chirp, no padding to 2^k
+    bool mixed = false;
+    int nrad = 0, rad[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // DIF pass radices, first pass first
+    int padsh = 4;                       // shared-memory index padding: i + (i >> padsh)   (31 = none)
+    uint16_t* d_pos = nullptr;           // [n]    position of X[k] after the last DIF pass (digit reversal)
+    uint16_t* d_ipos = nullptr;          // [n]    inverse: position p holds X[ipos[p]]
 };
 
 struct Plan2D {
@@ -92,12 +101,150 @@ int upload(float2** dst, const std::vector<float2>& src)
 
 void destroy1d(Plan1D& p)
 {
-    cudaFree(p.d_tw); cudaFree(p.d_w); cudaFree(p.d_bhat); cudaFree(p.d_w1); cudaFree(p.d_wn);
+    cudaFree(p.d_tw); cudaFree(p.d_w); cudaFree(p.d_bhat); cudaFree(p.d_wn); cudaFree(p.d_pos); cudaFree(p.d_ipos);
     p = Plan1D{};
 }
 
-constexpr int MAX_N1 = 16;
+constexpr int MAX_N1 = 8;              // = portable thread-block cluster size (one CTA per k1)
 constexpr int MAX_INNER = 8192;
+constexpr int FNT_HOST = 256;            // = FNT below (threads per FFT CTA)
+
+// ---- mixed-radix planner ------------------------------------------------------------------------------------------
+// Radices with a generated in-register butterfly (fft_radix.cuh).  The planner takes the factorisations of n with the
+// fewest passes, every order of their radices and a few index paddings, and keeps the one whose shared-memory
+// accesses need the fewest wavefronts under the bank model below (64-bit accesses are served per half-warp: 16 lanes,
+// conflict-free iff their padded indices differ mod 16); ties go to the smaller largest radix (registers).
+// Prototype + the same model in NumPy: tools/proto/fft_mixed.py.
+constexpr int kRadices[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
+constexpr int MAX_PASSES = 8;
+
+bool smooth235(int64_t n)
+{
+    for (int p : {2, 3, 5}) while (n % p == 0) n /= p;
+    return n == 1;
+}
+
+void enum_factorizations(int rem, int start, std::vector<int>& cur, std::vector<std::vector<int>>& out)
+{
+    if (rem == 1) { out.push_back(cur); return; }
+    if ((int)cur.size() >= MAX_PASSES) return;
+    for (int i = start; i < (int)(sizeof kRadices / sizeof kRadices[0]); ++i) {
+        const int r = kRadices[i];
+        if (rem % r == 0) {
+            cur.push_back(r);
+            enum_factorizations(rem / r, i, cur, out);
+            cur.pop_back();
+        }
+    }
+}
+
+double dif_wavefronts(const std::vector<int>& order, int padsh, int n, int nthreads)
+{
+    double total = 0.0;
+    int L = n;
+    for (int r : order) {
+        const int stride = L / r, ngroups = n / r, lanes = ngroups < nthreads ? ngroups : nthreads;
+        long long tot = 0, cnt = 0;
+        for (int q = 0; q < r; ++q)
+            for (int w0 = 0; w0 < lanes; w0 += 16) {
+                int words[16][16], nw[16] = {0};
+                for (int l = w0; l < w0 + 16 && l < lanes; ++l) {
+                    const int blk = l / stride, j = l - blk * stride;
+                    const int a0 = blk * L + j + q * stride, a = a0 + (a0 >> padsh), b = a & 15;
+                    bool seen = false;
+                    for (int t = 0; t < nw[b]; ++t) seen |= words[b][t] == a;
+                    if (!seen) words[b][nw[b]++] = a;
+                }
+                int worst = 0;
+                for (int b = 0; b < 16; ++b) worst = nw[b] > worst ? nw[b] : worst;
+                tot += worst; ++cnt;
+            }
+        total += 2.0 * (double)tot / (double)cnt;
+        L = stride;
+    }
+    return total;
+}
+
+// position of X[k] after DIF passes with these radices (first pass first)
+int dif_position(int k, const int* rad, int nrad, int L)
+{
+    int pos = 0;
+    for (int s = 0; s < nrad; ++s) {
+        const int stride = L / rad[s];
+        pos += (k % rad[s]) * stride;
+        k /= rad[s];
+        L = stride;
+    }
+    return pos;
+}
+
+int plan_mixed(Plan1D& p, int n, int nthreads)
+{
+    std::vector<std::vector<int>> facs;
+    std::vector<int> cur;
+    enum_factorizations(n, 0, cur, facs);
+    if (facs.empty()) return HD_ERR_UNSUPPORTED;
+    size_t fewest = facs[0].size();
+    for (auto& f : facs) fewest = f.size() < fewest ? f.size() : fewest;
+    std::vector<int> best;
+    int best_pad = 31, best_max = 1 << 30;
+    double best_cost = 1e30;
+    if (const char* e = getenv("HD_FFT_RADICES")) {            // experiments: "8,9,10,10[:padsh]"
+        std::vector<int> forced;
+        int prod = 1, pad_forced = -1;
+        for (const char* c = e; *c;) {
+            if (*c == ':') { pad_forced = atoi(c + 1); break; }
+            const int v = atoi(c);
+            if (v > 1) { forced.push_back(v); prod *= v; }
+            while (*c && *c != ',' && *c != ':') ++c;
+            if (*c == ',') ++c;
+        }
+        if (prod == n && !forced.empty() && (int)forced.size() <= MAX_PASSES) {
+            best = forced;
+            best_pad = pad_forced > 0 ? pad_forced : 31;
+            if (pad_forced <= 0) {
+                for (int pad : {31, 3, 4, 5}) {
+                    const double c = dif_wavefronts(forced, pad, n, nthreads);
+                    if (c < best_cost) { best_cost = c; best_pad = pad; }
+                }
+            }
+        }
+    }
+    if (best.empty()) {
+        for (auto f : facs) {
+            if (f.size() != fewest) continue;
+            std::sort(f.begin(), f.end());
+            do {
+                int mx = 0;
+                for (int r : f) mx = r > mx ? r : mx;
+                for (int pad : {31, 3, 4, 5}) {
+                    const double c = dif_wavefronts(f, pad, n, nthreads);
+                    if (c < best_cost - 1e-9 || (c < best_cost + 1e-9 && mx < best_max)) {
+                        best_cost = c; best = f; best_pad = pad; best_max = mx;
+                    }
+                }
+            } while (std::next_permutation(f.begin(), f.end()));
+        }
+    }
+    p.mixed = true;
+    p.nrad = (int)best.size();
+    for (int i = 0; i < p.nrad; ++i) p.rad[i] = best[i];
+    p.padsh = best_pad;
+    std::vector<uint16_t> pos((size_t)n);
+    for (int k = 0; k < n; ++k) pos[k] = (uint16_t)dif_position(k, p.rad, p.nrad, n);
+    std::vector<uint16_t> ipos((size_t)n);
+    for (int k = 0; k < n; ++k) ipos[pos[k]] = (uint16_t)k;
+    HD_CUDA_OK(cudaMalloc((void**)&p.d_pos, pos.size() * sizeof(uint16_t)));
+    HD_CUDA_OK(cudaMemcpy(p.d_pos, pos.data(), pos.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    HD_CUDA_OK(cudaMalloc((void**)&p.d_ipos, ipos.size() * sizeof(uint16_t)));
+    HD_CUDA_OK(cudaMemcpy(p.d_ipos, ipos.data(), ipos.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if (getenv("HD_FFT_TRACE")) {
+        fprintf(stderr, "fft plan n=%d: mixed radix", n);
+        for (int i = 0; i < p.nrad; ++i) fprintf(stderr, " %d", p.rad[i]);
+        fprintf(stderr, "  pad i+(i>>%d)  %.2f wavefronts per element pair\n", p.padsh, best_cost);
+    }
+    return HD_OK;
+}
 
 int build1d(Plan1D& p, int64_t n_total)
 {
@@ -113,25 +260,24 @@ int build1d(Plan1D& p, int64_t n_total)
         if (!n1) return HD_ERR_UNSUPPORTED;          // e.g. a prime length above 8192
         p.n1 = n1;
         n = n_total / n1;
-        std::vector<float2> w1((size_t)n1 * n1), wn((size_t)n_total);
-        for (int a = 0; a < n1; ++a)
-            for (int b = 0; b < n1; ++b) {
-                const double ang = -2.0 * PI * (double)((a * b) % n1) / (double)n1;
-                w1[(size_t)a * n1 + b] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        // wn[k1 * n + j] = W_N^(j k1): contiguous in j for each k1 (coalesced loads in long_row_stage)
+        std::vector<float2> wn((size_t)n_total);
+        for (int k1 = 0; k1 < n1; ++k1)
+            for (int64_t j = 0; j < n; ++j) {
+                const double ang = -2.0 * PI * (double)((j * k1) % n_total) / (double)n_total;
+                wn[(size_t)k1 * n + j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
             }
-        for (int64_t j = 0; j < n_total; ++j) {
-            const double ang = -2.0 * PI * (double)j / (double)n_total;
-            wn[j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
-        }
-        if (int e = upload(&p.d_w1, w1)) return e;
         if (int e = upload(&p.d_wn, wn)) return e;
     }
     const bool pow2 = (n & (n - 1)) == 0;
+    const bool mixed = !pow2 && smooth235(n) && n <= MAX_INNER && !getenv("HD_FFT_NO_MIXED");
     int64_t m = 1;
-    if (pow2) m = n;
+    if (pow2 || mixed) m = n;
     else while (m < 2 * n - 1) m <<= 1;
     if (m > MAX_M) return HD_ERR_UNSUPPORTED;       // longer rows need a multi-pass (four-step) FFT: not built yet
-    p.n = (int)n; p.m = (int)m; p.bluestein = !pow2;
+    p.n = (int)n; p.m = (int)m; p.bluestein = !pow2 && !mixed;
+    if (mixed)
+        if (int e = plan_mixed(p, (int)n, FNT_HOST)) return e;
     p.log2m = 0;
     while ((1 << p.log2m) < m) ++p.log2m;
     p.npass = p.log2m ? (p.log2m + 3) / 4 : 0;
@@ -388,7 +534,76 @@ __device__ __forceinline__ void fft_dit_all(float2* s, int m, int lgm, const Pas
     }
 }
 
+
+// ---- mixed-radix DIF passes (lengths 2^a 3^b 5^c) ----------------------------------------------------------------------
+// In place, natural order in, digit-reversed order out (Plan1D::d_pos says where X[k] ends up).  A pass of radix R on
+// sub-transforms of length L works on groups {base + j + q * (L/R)}, q = 0..R-1, held in registers by one thread:
+//   y = DFT_R(x)   (generated straight-line butterflies, fft_radix.cuh),   y[q] *= W_L^(j q),   stored back in place.
+struct MixPlan { int nrad; unsigned long long rad8; int padsh; const uint16_t* pos; };   // radices packed 8 bits each
+
+__device__ __forceinline__ int padv(int i, int sh) { return i + (i >> sh); }
+
+// W^(j q) for q = 1 .. R-1 from the table entries q = 1, 2, 4, 8 (correctly rounded) and at most three products
+template <int R>
+__device__ __forceinline__ void mix_twiddles(float2 (&w)[R], const float2* __restrict__ tw, int jt)
+{
+#pragma unroll
+    for (int b = 1; b < R; b <<= 1) w[b] = __ldg(&tw[jt * b]);
+#pragma unroll
+    for (int q = 3; q < R; ++q) {
+        const int hi = 1 << (31 - __builtin_clz(q));
+        if (q != hi) w[q] = cmul(w[hi], w[q - hi]);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void mix_dif_pass(float2* s, int n, int L, const float2* __restrict__ tw, int sh)
+{
+    const int stride = L / R, ngroups = n / R, tstep = n / L;
+    for (int g = threadIdx.x; g < ngroups; g += FNT) {
+        const int blk = g / stride, j = g - blk * stride;
+        const int base = blk * L + j;
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = s[padv(base + q * stride, sh)];
+        dft_fwd<R>(x);
+        if (stride > 1) {
+            float2 w[R];
+            mix_twiddles<R>(w, tw, j * tstep);
+#pragma unroll
+            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], w[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[padv(base + q * stride, sh)] = x[q];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void fft_mixed_all(float2* s, int n, const MixPlan& mp, const float2* tw)
+{
+    int L = n;
+    for (int i = 0; i < mp.nrad; ++i) {
+        const int r = (int)((mp.rad8 >> (8 * i)) & 0xffull);
+        switch (r) {
+            case 2: mix_dif_pass<2>(s, n, L, tw, mp.padsh); break;
+            case 3: mix_dif_pass<3>(s, n, L, tw, mp.padsh); break;
+            case 4: mix_dif_pass<4>(s, n, L, tw, mp.padsh); break;
+            case 5: mix_dif_pass<5>(s, n, L, tw, mp.padsh); break;
+            case 6: mix_dif_pass<6>(s, n, L, tw, mp.padsh); break;
+            case 8: mix_dif_pass<8>(s, n, L, tw, mp.padsh); break;
+            case 9: mix_dif_pass<9>(s, n, L, tw, mp.padsh); break;
+            case 10: mix_dif_pass<10>(s, n, L, tw, mp.padsh); break;
+            case 12: mix_dif_pass<12>(s, n, L, tw, mp.padsh); break;
+            case 15: mix_dif_pass<15>(s, n, L, tw, mp.padsh); break;
+            default: mix_dif_pass<16>(s, n, L, tw, mp.padsh); break;
+        }
+        L /= r;
+    }
+}
+
+
 enum LoadMode { LOAD_REAL = 0, LOAD_C64 = 1, LOAD_MASKED_SHIFTED = 2, LOAD_C64_HPAIR = 3 };
+enum Algo { ALG_POW2 = 0, ALG_BLUESTEIN = 1, ALG_MIXED = 2 };
 
 struct RowsArgs {
     const void* in;          // f32 (LOAD_REAL) or float2 rows
@@ -404,91 +619,199 @@ struct RowsArgs {
     int rows_total;          // LOAD_MASKED_SHIFTED: modulus of the row shift when only the first nrows rows are transformed
     int n1;                  // outer factor of a long row (1 = the whole row fits one transform)
     int n_total;             // n1 * n
-    const float2* w1;        // [n1 * n1]
-    const float2* wn;        // [n_total]
+    const float2* wn;        // [n1][n]  W_N^(j k1)
+    int permuted;            // mixed radix: leave X in digit-reversed order (position p holds X[ipos[p]]); the transpose
+                             // that consumes the rows un-permutes them in its index arithmetic
 };
 
-template <int LOAD, bool BLUE>
+// one element of the (virtual) input row, natural column index `col`
+template <int LOAD>
+__device__ __forceinline__ float2 load_elem(const RowsArgs& a, int row, int col)
+{
+    float2 v = make_float2(0.f, 0.f);
+    if (LOAD == LOAD_REAL) {
+        v.x = reinterpret_cast<const float*>(a.in)[(int64_t)row * a.in_pitch + col];
+    } else if (LOAD == LOAD_C64) {
+        v = reinterpret_cast<const float2*>(a.in)[(int64_t)row * a.in_pitch + col];
+    } else if (LOAD == LOAD_C64_HPAIR) {
+        // two Hermitian rows (real inverse transforms) packed as a + i b: the real / imaginary parts of the result
+        // are the two real output rows
+        const float2* src = reinterpret_cast<const float2*>(a.in) + (int64_t)row * a.in_pitch + col;
+        const float2 ra = src[0];
+        v = ra;
+        if (row + 1 < a.nrows) { const float2 rb = src[a.in_pitch]; v.x = ra.x - rb.y; v.y = ra.y + rb.x; }
+    } else {
+        int sr = row + a.shift_rows; if (sr >= a.rows_total) sr -= a.rows_total;
+        int sc = col + a.shift_cols; if (sc >= a.n_total) sc -= a.n_total;
+        v = reinterpret_cast<const float2*>(a.in)[(int64_t)sr * a.in_pitch + sc];
+        const float keep = 1.0f - (float)a.mask[(int64_t)sr * a.mask_pitch + sc];   // SubtractionFilter(minuend=1)
+        v.x *= keep; v.y *= keep;                                                     // ProductFilter(factor=F_shift)
+    }
+    if (a.inverse) v.y = -v.y;          // ifft(x) = conj(fft(conj x)) / N
+    return v;
+}
+
+// ---- long rows: thread-block cluster + distributed shared memory ---------------------------------------------------
+// A row longer than one shared-memory transform is split once, N = n1 * n (n1 <= 8 = the portable cluster size), and
+// handled by a CLUSTER of n1 CTAs:
+//   load      the cluster's threads share the columns j; the thread that owns j loads x[a n + j] for all a from global
+//             memory (each element of the row is read exactly once, coalesced), takes the n1-point DFT in registers,
+//             applies W_N^(j k1) and stores y_k1[j] into the shared memory of CTA k1 through DSMEM (long_row_load);
+//   transform CTA k1 transforms y_k1 (length n) on its own and stores X[k1 + n1 k2] at position k1 * n + k2.
+// Two cluster barriers per row: "all y have landed" and "my shared memory is free again" -- the second one is split
+// (arrive after the store phase, wait under the next row's first global loads).
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait()
+{
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st(uint32_t addr, float2 v)
+{
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// Load stage of a long row for this CTA's share of the columns j: x[a n + j] for all a straight from global memory
+// (n1 coalesced streams, every element of the row read once by the cluster), n1-point DFT in registers, W_N^(j k1)
+// (and the Bluestein chirp), then y_k1[j] is stored into CTA k1's shared memory at slot(j) -- remote stores only, no
+// remote loads.  The cluster barrier that says "everybody is done with the previous row's shared memory" is waited for
+// after the first batch of global loads has been issued, i.e. under their latency.
+// (not inlined: with the seven n1 cases inlined side by side ptxas spills hundreds of bytes in every one of them)
+template <int N1, int LOAD, int ALG>
+__device__ __noinline__ void long_row_load(float2* s, int n, uint32_t rank, int row, const RowsArgs& a,
+                                           const float2* __restrict__ chirp, int padsh)
+{
+    constexpr bool BLUE = ALG == ALG_BLUESTEIN;
+    const float2* __restrict__ wn2 = a.wn;
+    auto elem = [&](int r, int c) { return load_elem<LOAD>(a, r, c); };
+    auto slot = [&](int k) { return ALG == ALG_MIXED ? padv(k, padsh) : pad(k); };
+    const int chunk = (n + N1 - 1) / N1;
+    const int j_end = min(n, (int)(rank + 1) * chunk);
+    const uint32_t local = smem_u32(s);
+    // software pipelined: the global loads of the next j are issued right after the remote stores of this one
+    int j = (int)rank * chunk + (int)threadIdx.x;
+    bool live = j < j_end;
+    float2 x[N1];
+    if (live) {
+#pragma unroll
+        for (int a = 0; a < N1; ++a) x[a] = elem(row, a * n + j);
+    }
+    cluster_wait();                                     // the previous row's shared memory is free everywhere
+    while (live) {
+        dft_fwd<N1>(x);
+#pragma unroll
+        for (int k1 = 1; k1 < N1; ++k1) x[k1] = cmul(x[k1], __ldg(&wn2[(size_t)k1 * n + j]));     // W_N^(j k1)
+        if (BLUE) {
+            const float2 c = __ldg(&chirp[j]);
+#pragma unroll
+            for (int k1 = 0; k1 < N1; ++k1) x[k1] = cmul(x[k1], c);
+        }
+        const uint32_t addr = local + (uint32_t)slot(j) * (uint32_t)sizeof(float2);
+#pragma unroll
+        for (int k1 = 0; k1 < N1; ++k1) dsmem_st(dsmem_addr(addr, (uint32_t)k1), x[k1]);
+        j += FNT;
+        live = j < j_end;
+        if (live) {
+#pragma unroll
+            for (int a = 0; a < N1; ++a) x[a] = elem(row, a * n + j);
+        }
+    }
+}
+
+template <int LOAD, int ALG, bool LONG>
 __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int m, int log2m, PassPlan plan,
                                                        const float2* __restrict__ tw, const float2* __restrict__ chirp,
-                                                       const float2* __restrict__ bhat)
+                                                       const float2* __restrict__ bhat, MixPlan mix)
 {
+    constexpr bool BLUE = ALG == ALG_BLUESTEIN;
+    constexpr bool MIXED = ALG == ALG_MIXED;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
+    // Every variant takes its input in natural order (DIF passes) and finds X[k] in a permuted slot afterwards:
+    // digit-reversed for the mixed-radix passes, bit-reversed for the radix-2^k ones; Bluestein ends in natural order.
+    auto in_slot = [&](int k) -> int { return MIXED ? padv(k, mix.padsh) : pad(k); };
+    auto out_slot = [&](int k) -> int {
+        if (MIXED) return padv(a.permuted ? k : (int)__ldg(&mix.pos[k]), mix.padsh);
+        if (BLUE) return pad(k);
+        return pad(log2m ? (int)(__brev((unsigned)k) >> (32 - log2m)) : 0);
+    };
     const float scale = a.inverse ? 1.0f / (float)a.n_total : 1.0f;
-    const int n1 = a.n1;
+    const int n1 = LONG ? a.n1 : 1;
+    const uint32_t crank = LONG ? cluster_rank() : 0u;
+    const int nworkers = LONG ? (int)gridDim.x / n1 : (int)gridDim.x;          // clusters (LONG) or CTAs
+    const int worker = LONG ? (int)blockIdx.x / n1 : (int)blockIdx.x;
     // LOAD_REAL with n1 == 1 packs TWO real rows into one complex transform (x = row_a + i row_b) and separates the
     // two spectra afterwards: A[k] = (X[k] + conj X[n-k]) / 2, B[k] = (X[k] - conj X[n-k]) / 2i.
-    const bool pair = (LOAD == LOAD_REAL) && n1 == 1;
+    const bool pair = (LOAD == LOAD_REAL) && !LONG;
     const bool hpair = (LOAD == LOAD_C64_HPAIR);
-    const int nwork = pair ? (a.nrows + 1) / 2 : (hpair ? (a.nrows + 1) / 2 : a.nrows) * n1;
-    // one element of the (virtual) input row, natural column index `col`
-    auto elem = [&](int row, int col) -> float2 {
-        float2 v = make_float2(0.f, 0.f);
-        if (LOAD == LOAD_REAL) {
-            v.x = reinterpret_cast<const float*>(a.in)[(int64_t)row * a.in_pitch + col];
-        } else if (LOAD == LOAD_C64) {
-            v = reinterpret_cast<const float2*>(a.in)[(int64_t)row * a.in_pitch + col];
-        } else if (LOAD == LOAD_C64_HPAIR) {
-            // two Hermitian rows (real inverse transforms) packed as a + i b: the real / imaginary parts of the result
-            // are the two real output rows
-            const float2* src = reinterpret_cast<const float2*>(a.in) + (int64_t)row * a.in_pitch + col;
-            const float2 ra = src[0];
-            v = ra;
-            if (row + 1 < a.nrows) { const float2 rb = src[a.in_pitch]; v.x = ra.x - rb.y; v.y = ra.y + rb.x; }
-        } else {
-            int sr = row + a.shift_rows; if (sr >= a.rows_total) sr -= a.rows_total;
-            int sc = col + a.shift_cols; if (sc >= a.n_total) sc -= a.n_total;
-            v = reinterpret_cast<const float2*>(a.in)[(int64_t)sr * a.in_pitch + sc];
-            const float keep = 1.0f - (float)a.mask[(int64_t)sr * a.mask_pitch + sc];   // SubtractionFilter(minuend=1)
-            v.x *= keep; v.y *= keep;                                                     // ProductFilter(factor=F_shift)
-        }
-        if (a.inverse) v.y = -v.y;          // ifft(x) = conj(fft(conj x)) / N
-        return v;
-    };
-    for (int item = blockIdx.x; item < nwork; item += gridDim.x) {
-        const int row = pair ? 2 * item : (hpair ? 2 * (item / n1) : item / n1);
-        const int k1 = pair ? 0 : item % n1;
+    const int nwork = (pair || hpair) ? (a.nrows + 1) / 2 : a.nrows;
+    auto elem = [&](int row, int col) -> float2 { return load_elem<LOAD>(a, row, col); };
+    if (LONG) cluster_arrive();                         // "my shared memory is free" (matched by the wait in long_row_load)
+    for (int item = worker; item < nwork; item += nworkers) {
+        const int row = (pair || hpair) ? 2 * item : item;
+        const int k1 = (int)crank;
         const bool has_b = pair && (row + 1 < a.nrows);
-        // ---- load (+ n1-point DFT and twiddle for long rows, + chirp for Bluestein) --------------------------
-        // batches of LB elements per thread: all global loads of a batch are issued before the first is used
-        constexpr int LB = 8;
-        for (int k0 = threadIdx.x; k0 < m; k0 += LB * FNT) {
-            float2 v[LB], ch[LB];
+        // ---- load (+ chirp for Bluestein) ------------------------------------------------------------------------
+        if (LONG) {
+            if (BLUE)                                   // zero tail of the Bluestein buffer (own shared memory)
+                for (int k = n + (int)threadIdx.x; k < m; k += FNT) s[in_slot(k)] = make_float2(0.f, 0.f);
+            switch (n1) {
+                case 2: long_row_load<2, LOAD, ALG>(s, n, crank, row, a, chirp, mix.padsh); break;
+                case 3: long_row_load<3, LOAD, ALG>(s, n, crank, row, a, chirp, mix.padsh); break;
+                case 4: long_row_load<4, LOAD, ALG>(s, n, crank, row, a, chirp, mix.padsh); break;
+                case 5: long_row_load<5, LOAD, ALG>(s, n, crank, row, a, chirp, mix.padsh); break;
+                case 6: long_row_load<6, LOAD, ALG>(s, n, crank, row, a, chirp, mix.padsh); break;
+                case 7: long_row_load<7, LOAD, ALG>(s, n, crank, row, a, chirp, mix.padsh); break;
+                default: long_row_load<8, LOAD, ALG>(s, n, crank, row, a, chirp, mix.padsh); break;
+            }
+            cluster_sync_all();                         // every y_k1[j] of this row has landed
+        } else {
+            // batches of LB elements per thread: all global loads of a batch are issued before the first is used
+            constexpr int LB = 8;
+            for (int k0 = threadIdx.x; k0 < m; k0 += LB * FNT) {
+                float2 v[LB], ch[LB];
 #pragma unroll
-            for (int j = 0; j < LB; ++j) {
-                const int k = k0 + j * FNT;
-                v[j] = make_float2(0.f, 0.f);
-                ch[j] = make_float2(1.f, 0.f);
-                if (k < n) {
-                    if (pair) {
-                        const float* src = reinterpret_cast<const float*>(a.in) + (int64_t)row * a.in_pitch + k;
-                        v[j].x = src[0];
-                        if (has_b) v[j].y = src[a.in_pitch];     // real rows: the inverse conj is applied after the split
-                    } else if (n1 == 1) {
-                        v[j] = elem(row, k);
-                    } else {
-                        for (int aa = 0; aa < n1; ++aa) {
-                            const float2 x = elem(row, aa * n + k), w = __ldg(&a.w1[aa * n1 + k1]);
-                            v[j].x = fmaf(x.x, w.x, fmaf(-x.y, w.y, v[j].x));
-                            v[j].y = fmaf(x.x, w.y, fmaf(x.y, w.x, v[j].y));
+                for (int j = 0; j < LB; ++j) {
+                    const int k = k0 + j * FNT;
+                    v[j] = make_float2(0.f, 0.f);
+                    ch[j] = make_float2(1.f, 0.f);
+                    if (k < n) {
+                        if (pair) {
+                            const float* src = reinterpret_cast<const float*>(a.in) + (int64_t)row * a.in_pitch + k;
+                            v[j].x = src[0];
+                            if (has_b) v[j].y = src[a.in_pitch];     // real rows: the inverse conj is applied after the split
+                        } else {
+                            v[j] = elem(row, k);
                         }
-                        v[j] = cmul(v[j], __ldg(&a.wn[k * k1]));
+                        if (BLUE) ch[j] = __ldg(&chirp[k]);
                     }
-                    if (BLUE) ch[j] = __ldg(&chirp[k]);
+                }
+#pragma unroll
+                for (int j = 0; j < LB; ++j) {
+                    const int k = k0 + j * FNT;
+                    if (k >= m) continue;
+                    float2 u = v[j];
+                    if (BLUE && k < n) u = cmul(u, ch[j]);
+                    s[in_slot(k)] = u;
                 }
             }
-#pragma unroll
-            for (int j = 0; j < LB; ++j) {
-                const int k = k0 + j * FNT;
-                if (k >= m) continue;
-                float2 u = v[j];
-                if (BLUE && k < n) u = cmul(u, ch[j]);
-                if (BLUE) s[pad(k)] = u;
-                else s[pad(log2m ? (int)(__brev((unsigned)k) >> (32 - log2m)) : 0)] = u;   // DIT wants bit-reversed input
-            }
+            __syncthreads();
         }
-        __syncthreads();
         if (BLUE) {
             // DIF passes, the fused middle (last DIF pass x FFT(conj chirp) / m x first inverse DIT pass), DIT passes
             fft_dif_all<false>(s, m, log2m, plan, tw, bhat, 1);
@@ -499,18 +822,20 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
                 default: bluestein_mid_pass<4>(s, m, bhat); break;
             }
             fft_dit_all<true>(s, m, log2m, plan, tw, 1);
+        } else if (MIXED) {
+            fft_mixed_all(s, n, mix, tw);
         } else if (m > 1) {
-            fft_dit_all<false>(s, m, log2m, plan, tw);
+            fft_dif_all<false>(s, m, log2m, plan, tw, bhat);
         }
         // ---- store: X[k1 + n1 * k] goes to position k1 * n + k (see Plan1D) ------------------------------------
         const int64_t obase = (int64_t)row * a.out_pitch + (int64_t)k1 * n;
 #pragma unroll 4
         for (int k = threadIdx.x; k < n; k += FNT) {                       // unrolled: the chirp loads of four steps overlap
-            float2 v = s[pad(k)];
+            float2 v = s[out_slot(k)];
             if (BLUE) v = cmul(v, __ldg(&chirp[k]));
             if (pair) {
                 const int kn = k ? n - k : 0;
-                float2 u = s[pad(kn)];
+                float2 u = s[out_slot(kn)];
                 if (BLUE) u = cmul(u, __ldg(&chirp[kn]));
                 float2 fa = make_float2(0.5f * (v.x + u.x), 0.5f * (v.y - u.y));
                 float2 fb = make_float2(0.5f * (v.y + u.y), 0.5f * (u.x - v.x));
@@ -538,19 +863,29 @@ __global__ void __launch_bounds__(FNT, 3) fft_rows_kernel(RowsArgs a, int n, int
             }
         }
         __syncthreads();
+        if (LONG) cluster_arrive();                     // this row is stored: my shared memory is free again
     }
+    if (LONG) cluster_wait();                           // closes the last arrive; nobody writes to a CTA that has left
 }
 
 // ---- tiled transposes ---------------------------------------------------------------------------------------------
 // out[(x + sx) % nx_out_rows ...]: generic "transpose + cyclic shift" of a (rows x cols) array into (cols x rows).
 // Element in[r][c] lands at out[(c + shift_c) % cols][(r + shift_r) % rows].
-// pn1 > 1: the input columns are stored permuted by a long-row pass -- position c holds index c / pn2 + pn1 * (c % pn2)
-__device__ __forceinline__ int unpermute(int c, int pn1, int pn2) { return pn1 > 1 ? c / pn2 + pn1 * (c % pn2) : c; }
+// How the row pass that produced the input stored its columns: position c = k1 * n2 + p holds the frequency index
+// k1 + n1 * k2, with k2 = p, or k2 = ipos[p] when the mixed-radix passes left their output digit-reversed.
+struct RowPerm { int n1, n2; const uint16_t* ipos; };
+__device__ __forceinline__ int unpermute(int c, const RowPerm& pm)
+{
+    if (pm.n1 == 1 && !pm.ipos) return c;
+    const int k1 = c / pm.n2, p = c - k1 * pm.n2;
+    const int k2 = pm.ipos ? (int)__ldg(&pm.ipos[p]) : p;
+    return k1 + pm.n1 * k2;
+}
 
 template <typename T, bool WITH_ABS>
 __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int64_t in_pitch, T* __restrict__ out,
                                                         int64_t out_pitch, float* __restrict__ out_abs, int64_t abs_pitch,
-                                                        int rows, int cols, int shift_r, int shift_c, int pn1, int pn2,
+                                                        int rows, int cols, int shift_r, int shift_c, RowPerm pm,
                                                         int keep_max = -1, int mirror_rows = 0, int mirror_cols = 1)
 {
     // keep_max >= 0: only input columns whose (unpermuted) index is <= keep_max are written (half spectrum of a real
@@ -574,7 +909,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k, r = r0 + tx;            // out row = c, out col = r
             if (r < rows && c < cols) {
-                const int kc = unpermute(c, pn1, pn2);
+                const int kc = unpermute(c, pm);
                 if (keep_max >= 0 && kc > keep_max) continue;
                 const int full_rows = mirror_rows > 0 ? mirror_rows : rows;     // extent of the output's column axis
                 int orow = kc + shift_c; if (orow >= cols) orow -= cols;
@@ -608,7 +943,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
 template <typename OutT>
 __global__ void __launch_bounds__(256) transpose_real_kernel(const float* __restrict__ in, int64_t in_pitch,
                                                              OutT* __restrict__ out, int64_t out_pitch, int rows, int cols,
-                                                             int pn1, int pn2)
+                                                             RowPerm pm)
 {
     __shared__ float tile[32][33];
     const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
@@ -625,7 +960,7 @@ __global__ void __launch_bounds__(256) transpose_real_kernel(const float* __rest
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k, r = r0 + tx;
-            if (r < rows && c < cols) out[(int64_t)unpermute(c, pn1, pn2) * out_pitch + r] = (OutT)tile[tx][ty + 8 * k];
+            if (r < rows && c < cols) out[(int64_t)unpermute(c, pm) * out_pitch + r] = (OutT)tile[tx][ty + 8 * k];
         }
         __syncthreads();
     }
@@ -646,41 +981,82 @@ __global__ void __launch_bounds__(256) shift_kernel(const T* __restrict__ in, in
 }
 
 // ---- host launch helpers -----------------------------------------------------------------------------------------
-int launch_rows(const Plan1D& p, const RowsArgs& a_in, int load, cudaStream_t s)
+// Does a row pass with this plan / load mode leave its output digit-reversed when the consumer allows it?  (Not when
+// two real rows share a transform: separating their spectra needs X[k] and X[n-k] side by side.)
+bool leaves_permuted(const Plan1D& p, int load) { return p.mixed && !(load == LOAD_REAL && p.n1 == 1); }
+RowPerm perm_of(const Plan1D& p, int load, bool allow_permuted = true)
+{
+    return RowPerm{p.n1, p.n, (allow_permuted && leaves_permuted(p, load)) ? p.d_ipos : nullptr};
+}
+
+int launch_rows(const Plan1D& p, const RowsArgs& a_in, int load, cudaStream_t s, bool allow_permuted = true)
 {
     RowsArgs a = a_in;
+    a.permuted = (allow_permuted && leaves_permuted(p, load)) ? 1 : 0;
     a.n1 = p.n1;
     if (a.rows_total == 0) a.rows_total = a.nrows;
     a.n_total = p.n_total;
-    a.w1 = p.d_w1;
     a.wn = p.d_wn;
-    const size_t smem = (size_t)(p.m + (p.m >> 4) + 1) * sizeof(float2);
+    const size_t smem = (size_t)(p.m + (p.m >> (p.mixed ? p.padsh : 4)) + 1) * sizeof(float2);
     PassPlan plan{p.npass, {p.k[0], p.k[1], p.k[2], p.k[3]}};
+    unsigned long long rad8 = 0;
+    for (int i = 0; i < p.nrad; ++i) rad8 |= (unsigned long long)p.rad[i] << (8 * i);
+    MixPlan mix{p.nrad, rad8, p.padsh, p.d_pos};
     if (a.nrows < 1) return HD_OK;
-#define HD_ROWS(LOADV, BLUEV)                                                                          \
-    {                                                                                                  \
-        auto kern = fft_rows_kernel<LOADV, BLUEV>;                                                     \
-        HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        int per_sm = 1;                                                                                \
-        HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FNT, smem));            \
-        int grid = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);                                           \
-        const int nwork = (LOADV == LOAD_REAL && p.n1 == 1) ? (a.nrows + 1) / 2                       \
-                          : (LOADV == LOAD_C64_HPAIR ? (a.nrows + 1) / 2 : a.nrows) * p.n1;            \
-        if (grid > nwork) grid = nwork;                                                                \
-        hd_prof_begin("fft_rows_kernel", s);                                                           \
-        kern<<<grid, FNT, smem, s>>>(a, p.n, p.m, p.log2m, plan, p.d_tw, p.d_w, p.d_bhat);              \
+#define HD_ROWS_L(LOADV, ALGV, LONGV)                                                                     \
+    {                                                                                                    \
+        auto kern = fft_rows_kernel<LOADV, ALGV, LONGV>;                                                 \
+        HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        const int nwork = ((LOADV == LOAD_REAL && !LONGV) || LOADV == LOAD_C64_HPAIR) ? (a.nrows + 1) / 2 : a.nrows; \
+        cudaLaunchConfig_t cfg = {};                                                                     \
+        cfg.blockDim = dim3(FNT);                                                                        \
+        cfg.dynamicSmemBytes = smem;                                                                     \
+        cfg.stream = s;                                                                                  \
+        cudaLaunchAttribute attr[1];                                                                     \
+        int workers = 1;                                                                                 \
+        if (LONGV) {                                                                                     \
+            attr[0].id = cudaLaunchAttributeClusterDimension;                                            \
+            attr[0].val.clusterDim.x = (unsigned)p.n1;                                                   \
+            attr[0].val.clusterDim.y = 1;                                                                \
+            attr[0].val.clusterDim.z = 1;                                                                \
+            cfg.attrs = attr;                                                                            \
+            cfg.numAttrs = 1;                                                                            \
+            cfg.gridDim = dim3((unsigned)p.n1);                                                          \
+            HD_CUDA_OK(cudaOccupancyMaxActiveClusters(&workers, kern, &cfg));   /* co-resident clusters */ \
+        } else {                                                                                         \
+            int per_sm = 1;                                                                              \
+            HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FNT, smem));          \
+            workers = hd_num_sms() * (per_sm < 1 ? 1 : per_sm);                                          \
+        }                                                                                                \
+        if (workers < 1) workers = 1;                                                                    \
+        if (workers > nwork) workers = nwork;                                                            \
+        cfg.gridDim = dim3((unsigned)(workers * (LONGV ? p.n1 : 1)));                                    \
+        hd_prof_begin("fft_rows_kernel", s);                                                             \
+        HD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, p.n, p.m, p.log2m, plan, (const float2*)p.d_tw,     \
+                                      (const float2*)p.d_w, (const float2*)p.d_bhat, mix));              \
+    }
+#define HD_ROWS(LOADV, ALGV)                                        \
+    {                                                               \
+        if (p.n1 > 1) HD_ROWS_L(LOADV, ALGV, true)                  \
+        else HD_ROWS_L(LOADV, ALGV, false)                          \
     }
     if (p.bluestein) {
-        if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, true)
-        else if (load == LOAD_C64) HD_ROWS(LOAD_C64, true)
-        else if (load == LOAD_C64_HPAIR) HD_ROWS(LOAD_C64_HPAIR, true)
-        else HD_ROWS(LOAD_MASKED_SHIFTED, true)
+        if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, ALG_BLUESTEIN)
+        else if (load == LOAD_C64) HD_ROWS(LOAD_C64, ALG_BLUESTEIN)
+        else if (load == LOAD_C64_HPAIR) HD_ROWS(LOAD_C64_HPAIR, ALG_BLUESTEIN)
+        else HD_ROWS(LOAD_MASKED_SHIFTED, ALG_BLUESTEIN)
+    } else if (p.mixed) {
+        if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, ALG_MIXED)
+        else if (load == LOAD_C64) HD_ROWS(LOAD_C64, ALG_MIXED)
+        else if (load == LOAD_C64_HPAIR) HD_ROWS(LOAD_C64_HPAIR, ALG_MIXED)
+        else HD_ROWS(LOAD_MASKED_SHIFTED, ALG_MIXED)
     } else {
-        if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, false)
-        else if (load == LOAD_C64) HD_ROWS(LOAD_C64, false)
-        else if (load == LOAD_C64_HPAIR) HD_ROWS(LOAD_C64_HPAIR, false)
-        else HD_ROWS(LOAD_MASKED_SHIFTED, false)
+        if (load == LOAD_REAL) HD_ROWS(LOAD_REAL, ALG_POW2)
+        else if (load == LOAD_C64) HD_ROWS(LOAD_C64, ALG_POW2)
+        else if (load == LOAD_C64_HPAIR) HD_ROWS(LOAD_C64_HPAIR, ALG_POW2)
+        else HD_ROWS(LOAD_MASKED_SHIFTED, ALG_POW2)
     }
+#undef HD_ROWS_L
 #undef HD_ROWS
     HD_LAUNCH_CHECK();
     hd_count_launch();
@@ -741,8 +1117,8 @@ int hd_fft2_forward_shift_abs(void* plan, const void* in, int64_t in_pitch, void
     RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, 0, 0};
     if (int e = launch_rows(p->px, r1, LOAD_REAL, s)) return e;
     hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0, p->px.n1,
-                                                                          p->px.n, nh - 1, 0);
+    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0,
+                                                                          perm_of(p->px, LOAD_REAL), nh - 1, 0);
     HD_LAUNCH_CHECK(); hd_count_launch();
     RowsArgs r2{At, ny, A, ny, nullptr, 0, nh, 0, 0, 0, 0};              // out of place: long rows read the whole row
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
@@ -751,7 +1127,7 @@ int hd_fft2_forward_shift_abs(void* plan, const void* in, int64_t in_pitch, void
     hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, true><<<transpose_grid(nh, ny), 256, 0, s>>>(A, ny, (float2*)fshift, fshift_pitch,
                                                                          (float*)fabs_out, fabs_pitch, nh, ny, nx / 2, ny / 2,
-                                                                         p->py.n1, p->py.n, -1, nx);
+                                                                         perm_of(p->py, LOAD_C64), -1, nx);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }
@@ -782,7 +1158,7 @@ int hd_fft2_masked_inverse_abs(void* plan, const void* fshift, int64_t fshift_pi
         if (int e = launch_rows(p->px, r1, LOAD_MASKED_SHIFTED, s)) return e;
         hd_prof_begin("transpose_kernel", s);
         transpose_kernel<float2, false><<<transpose_grid(nyh, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, nyh, nx, 0, 0,
-                                                                               p->px.n1, p->px.n, -1, ny, 0);
+                                                                               perm_of(p->px, LOAD_MASKED_SHIFTED), -1, ny, 0);
         HD_LAUNCH_CHECK(); hd_count_launch();
         RowsArgs r2{At, ny, (float2*)absT, ny, nullptr, 0, nx, 0, 0, 1, 1};
         if (int e = launch_rows(p->py, r2, LOAD_C64_HPAIR, s)) return e;
@@ -791,18 +1167,17 @@ int hd_fft2_masked_inverse_abs(void* plan, const void* fshift, int64_t fshift_pi
         if (int e = launch_rows(p->px, r1, LOAD_MASKED_SHIFTED, s)) return e;
         hd_prof_begin("transpose_kernel", s);
         transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0,
-                                                                              p->px.n1, p->px.n);
+                                                                              perm_of(p->px, LOAD_MASKED_SHIFTED));
         HD_LAUNCH_CHECK(); hd_count_launch();
         RowsArgs r2{At, ny, (float2*)absT, ny, nullptr, 0, nx, 0, 0, 1, 1};
         if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
     }
+    const RowPerm pm2 = perm_of(p->py, ((ny & 1) && (nx & 1) && !getenv("HD_FFT_NO_HERMITIAN")) ? LOAD_C64_HPAIR : LOAD_C64);
     hd_prof_begin("transpose_real_kernel", s);
     if (out_dtype == HD_F32)
-        transpose_real_kernel<float><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (float*)out, out_pitch, nx, ny,
-                                                                           p->py.n1, p->py.n);
+        transpose_real_kernel<float><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (float*)out, out_pitch, nx, ny, pm2);
     else
-        transpose_real_kernel<double><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (double*)out, out_pitch, nx, ny,
-                                                                            p->py.n1, p->py.n);
+        transpose_real_kernel<double><<<transpose_grid(nx, ny), 256, 0, s>>>(absT, ny, (double*)out, out_pitch, nx, ny, pm2);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }
@@ -820,16 +1195,17 @@ int hd_fft2_c2c(void* plan, const void* in, int in_dtype, int64_t in_pitch, void
     float2* A = (float2*)workspace;
     float2* At = A + (int64_t)ny * nx;
     RowsArgs r1{in, in_pitch, A, nx, nullptr, 0, ny, 0, 0, inverse ? 1 : 0, 0};
-    if (int e = launch_rows(p->px, r1, in_dtype == HD_F32 ? LOAD_REAL : LOAD_C64, s)) return e;
+    const int load1 = in_dtype == HD_F32 ? LOAD_REAL : LOAD_C64;
+    if (int e = launch_rows(p->px, r1, load1, s)) return e;
     hd_prof_begin("transpose_kernel", s);
-    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0, p->px.n1,
-                                                                          p->px.n);
+    transpose_kernel<float2, false><<<transpose_grid(ny, nx), 256, 0, s>>>(A, nx, At, ny, nullptr, 0, ny, nx, 0, 0,
+                                                                          perm_of(p->px, load1));
     HD_LAUNCH_CHECK(); hd_count_launch();
     RowsArgs r2{At, ny, A, ny, nullptr, 0, nx, 0, 0, inverse ? 1 : 0, 0};
     if (int e = launch_rows(p->py, r2, LOAD_C64, s)) return e;
     hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, false><<<transpose_grid(nx, ny), 256, 0, s>>>(A, ny, (float2*)out, out_pitch, nullptr, 0, nx, ny,
-                                                                          0, 0, p->py.n1, p->py.n);
+                                                                          0, 0, perm_of(p->py, LOAD_C64));
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }
@@ -855,18 +1231,19 @@ int hd_fft_rows(void* plan, const void* in, int in_dtype, int64_t in_pitch, void
     // LOAD_REAL would pack two real rows per transform and emit both spectra: fine here (full spectra are stored)
     RowsArgs r1{in, in_pitch, direct ? (float2*)out : A, direct ? out_pitch : (int64_t)nx, nullptr, 0, (int)nrows, 0, 0,
                 inverse ? 1 : 0, 0};
-    if (int e = launch_rows(p->px, r1, in_dtype == HD_F32 ? LOAD_REAL : LOAD_C64, s)) return e;
+    const int load1 = in_dtype == HD_F32 ? LOAD_REAL : LOAD_C64;
+    if (int e = launch_rows(p->px, r1, load1, s, !direct)) return e;
     if (direct) return HD_OK;
     float2* t_out = transpose_out ? (float2*)out : At;
     const int64_t t_pitch = transpose_out ? out_pitch : nrows;
     hd_prof_begin("transpose_kernel", s);
     transpose_kernel<float2, false><<<transpose_grid((int)nrows, nx), 256, 0, s>>>(A, nx, t_out, t_pitch, nullptr, 0,
-                                                                                  (int)nrows, nx, 0, 0, p->px.n1, p->px.n);
+                                                                                  (int)nrows, nx, 0, 0, perm_of(p->px, load1));
     HD_LAUNCH_CHECK(); hd_count_launch();
     if (transpose_out) return HD_OK;
     hd_prof_begin("transpose_kernel", s);                         // long rows, row layout wanted: transpose back
     transpose_kernel<float2, false><<<transpose_grid(nx, (int)nrows), 256, 0, s>>>(At, nrows, (float2*)out, out_pitch, nullptr,
-                                                                                  0, nx, (int)nrows, 0, 0, 1, nx);
+                                                                                  0, nx, (int)nrows, 0, 0, RowPerm{1, nx, nullptr});
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }

@@ -165,6 +165,24 @@ def test_fft_long_rows_vs_scipy(shape):
     np.testing.assert_allclose(back.real, a, rtol=RTOL)
 
 
+@pytest.mark.parametrize("n,radices", [(120, "2,3,4,5"), (432, "6,8,9"), (1800, "10,12,15"), (240, "16,15"), (7200, None),
+                                       (6000, None), (3600, None), (4500, "9,10,10,5:31"), (3000, "5,10,10,6")])
+def test_fft_mixed_radix_vs_scipy(n, radices, monkeypatch):
+    """Lengths 2^a 3^b 5^c run as plain mixed-radix transforms (no Bluestein): every generated butterfly
+    (tools/gen_fft_radix.py) and the planner's own choice for the mosaic sub-row lengths, against scipy."""
+    from scipy import fftpack
+    if radices:
+        monkeypatch.setenv("HD_FFT_RADICES", radices)
+    rows = 7 if radices else 5                      # (plans are cached per shape: each case has its own)
+    rng = np.random.default_rng(n)
+    a = (rng.normal(100, 10, (rows, n))).astype(np.float32)
+    f = ef.FourierTransform().apply(a)
+    want = fftpack.fft2(a)
+    spectrum_close(f, want)
+    back = ef.FourierITransform().apply(want)
+    np.testing.assert_allclose(back.real, a, rtol=RTOL)
+
+
 def test_stripe_removal_long_rows():
     """The fused forward / masked inverse passes on a raster whose rows need the n1 * n2 split."""
     sc = SynthScene(200, 9000, 17)

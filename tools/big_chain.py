@@ -88,6 +88,19 @@ for rep in range(2):
     torch.cuda.synchronize()
     times.append(a.elapsed_time(b))
 cells = n * n
+if "--profile" in sys.argv:
+    import ctypes
+    lib = _lib.load()
+    lib.hd_profile_enable(1)
+    chain.run_device(d_srtm, d_gr, d_hs)
+    cbuf = ctypes.create_string_buffer(1 << 16)
+    lib.hd_profile_report(cbuf, 1 << 16)
+    lib.hd_profile_enable(0)
+    rows = [l.split() for l in cbuf.value.decode().splitlines()]
+    tot = sum(float(r[2]) for r in rows)
+    prof = {r[0]: {"launches": int(r[1]), "ms": round(float(r[2]), 3), "share": round(float(r[2]) / tot, 4)}
+            for r in sorted(rows, key=lambda r: -float(r[2]))}
+    print(json.dumps({"size": n, "profile_total_ms": tot, "kernels": prof}), flush=True)
 print(f"chain: {times[-1]:.2f} ms  -> {cells / times[-1] / 1e3:.0f} Mcells/s   (first run {times[0]:.2f} ms), "
       f"peak HBM in use {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
 

@@ -58,10 +58,20 @@ SIGNATURES = {
     "hd_fft2_masked_inverse_abs": (_i, [_p, _p, _i64, _p, _i64, _p, _i, _i64, _p, _i64, _p]),
     "hd_fft2_c2c": (_i, [_p, _p, _i, _i64, _p, _i64, _i, _p, _i64, _p]),
     "hd_fft_rows": (_i, [_p, _p, _i, _i64, _p, _i64, _i64, _i, _i, _p, _i64, _p]),
+    "hd_fft_band_pass": (_i, [_p, _i, _i, _p, _i64, _i64, _p, _i64, _i, _i, _i, _p, _i64, _i64, _p, _i64, _p]),
+    "hd_klayout_rows": (_i64, [_i64, _i64, _i64]),
+    "hd_klayout_ky": (_i64, [_i64, _i64, _i64, _i64]),
+    "hd_hermitian_complete": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p]),
+    "hd_conj_mirror_fill": (_i, [_p, _i64, _i64, _i64, _p]),
+    "hd_fourier_mask_assemble_rows": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p]),
     "hd_fftshift2": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
     "hd_pdfill_workspace_bytes": (_i64, [_i64, _i64]),
     "hd_pdfill": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _i, ctypes.POINTER(_i), _p]),
     "hd_pdfill_band": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _i, ctypes.POINTER(_i), _p]),
+    "hd_pdfill_d8": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p, _i64, ctypes.POINTER(_i), _p]),
+    "hd_pdfill_finish_d8": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _p]),
+    "hd_pdfill_status": (_i, [_p, ctypes.POINTER(_i), _p]),
+    "hd_halo_min_flag": (_i, [_p, _p, _i64, _p, _p]),
     "hd_pdfill_finish": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_d8": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_binary_morph": (_i, [_p, _i, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _p]),

@@ -154,21 +154,35 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
 // ---- mask assembly ------------------------------------------------------------------------------------------
 // quarters[0] -> top-left block [:my-m, :mx-m]; quarters[1] -> top-right block, shifted by the margin;
 // bottom blocks are the point mirrors; the middle row / column of odd sizes stays 0.  (:986-991, :1002-1049)
+// Row-band variant (hydrodem_b200/sharding.py): only the `out_rows` rows listed by the K layout (a, b) are produced --
+// local row t holds the spectrum row ky(t), i.e. the shifted row (ky + ny/2) % ny -- from quarter-mask slabs that start
+// at quarter row q0.  (out_rows == 0: the whole mask, row t = shifted row t.)
 template <typename OutT>
 __global__ void __launch_bounds__(256) assemble_kernel(const uint8_t* __restrict__ m1, int64_t p1,
                                                        const uint8_t* __restrict__ m2, int64_t p2, OutT* __restrict__ out,
-                                                       int64_t out_pitch, int ny, int nx, int margin, int invert)
+                                                       int64_t out_pitch, int ny, int nx, int margin, int invert,
+                                                       int out_rows = 0, int ka = 0, int kb = 0, int q0 = 0,
+                                                       int q_rows = 0x7fffffff)
 {
     const int my = ny / 2, y_odd = ny & 1, mx = nx / 2, x_odd = nx & 1;
     const int nxq = (nx + 3) / 4;                                  // four consecutive cells of a row per thread
-    for (CellIter it(nxq); it.y < ny; it.next()) {
-        const int y = (int)it.y, x4 = 4 * (int)it.x;
+    const int nrows = out_rows > 0 ? out_rows : ny;
+    // K layout (see csrc/fft.cu): rows ky in [ka, kb), then their mirrors ny - ky in ascending order
+    const int kmin = ka > 1 ? ka : 1, kmax = (kb - 1) < (ny - 1) / 2 ? (kb - 1) : (ny - 1) / 2, hlo = ny - kmax;
+    for (CellIter it(nxq); it.y < nrows; it.next()) {
+        const int t = (int)it.y, x4 = 4 * (int)it.x;
+        int y = t;
+        if (out_rows > 0) {
+            const int ky = t < kb - ka ? ka + t : hlo + (t - (kb - ka));
+            y = ky + ny / 2; if (y >= ny) y -= ny;
+        }
+        (void)kmin;
         // row part of the block lookup: position inside one of the (my, mx) blocks, or -1 on the odd middle row
         int by = -1, top = 0;
         if (y < my) { by = y; top = 1; } else if (y >= my + y_odd) { by = y - my - y_odd; }
         // bottom blocks: c3 = flip(c2) sits bottom-left, c4 = flip(c1) bottom-right
         const int qy = top ? by : my - 1 - by;
-        const bool row_ok = by >= 0 && qy < my - margin;
+        const bool row_ok = by >= 0 && qy < my - margin && qy >= q0 && qy - q0 < q_rows;
         OutT res[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -181,15 +195,15 @@ __global__ void __launch_bounds__(256) assemble_kernel(const uint8_t* __restrict
                     const int qx = top ? bx : mx - 1 - bx;
                     const bool use_first = top ? left : !left;
                     if (use_first) {
-                        if (qx < mx - margin) v = m1[(int64_t)qy * p1 + qx];
+                        if (qx < mx - margin) v = m1[(int64_t)(qy - q0) * p1 + qx];
                     } else {
-                        if (qx >= margin) v = m2[(int64_t)qy * p2 + (qx - margin)];
+                        if (qx >= margin) v = m2[(int64_t)(qy - q0) * p2 + (qx - margin)];
                     }
                 }
             }
             res[j] = invert ? (OutT)(1 - v) : (OutT)v;
         }
-        store4v<OutT>(out, out_pitch, y, x4, nx, res);
+        store4v<OutT>(out, out_pitch, t, x4, nx, res);
     }
 }
 
@@ -251,4 +265,26 @@ extern "C" int hd_fourier_mask_assemble(const void* q1, int64_t q1_pitch, const 
     HD_ASM(double, HD_F64)
 #undef HD_ASM
     return HD_ERR_UNSUPPORTED;
+}
+
+// The same assembly for the rows of one rank of the sharded Fourier stage: out (U8, rows x nx) holds the mask rows of
+// the K layout (a, b) (csrc/fft.cu); q1 / q2 are slabs of the quarter masks starting at quarter row q0 (q_rows rows).
+extern "C" int hd_fourier_mask_assemble_rows(const void* q1, int64_t q1_pitch, const void* q2, int64_t q2_pitch, int64_t q0,
+                                             int64_t q_rows, void* out, int64_t out_pitch, int64_t out_rows, int64_t a,
+                                             int64_t b, int64_t ny, int64_t nx, int margin, void* stream)
+{
+    if (!q1 || !q2 || !out) return HD_ERR_NULL;
+    if (ny < 2 || nx < 2 || ny > 0x7fffffff || nx > 0x7fffffff || out_pitch < nx || margin < 0 || out_rows < 1) return HD_ERR_ARG;
+    if (ny / 2 - margin < 1 || nx / 2 - margin < 1 || a < 0 || b <= a || b > ny / 2 + 1 || q0 < 0 || q_rows < 0) return HD_ERR_ARG;
+    if (q1_pitch < nx / 2 - margin || q2_pitch < nx / 2 - margin) return HD_ERR_ARG;
+    const int64_t total = out_rows * ((nx + 3) / 4);
+    const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    hd_prof_begin("assemble_kernel", s);
+    assemble_kernel<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)q1, q1_pitch, (const uint8_t*)q2, q2_pitch, (uint8_t*)out,
+                                                    out_pitch, (int)ny, (int)nx, margin, 0, (int)out_rows, (int)a, (int)b, (int)q0,
+                                                    (int)q_rows);
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
 }

@@ -980,6 +980,62 @@ __global__ void __launch_bounds__(256) shift_kernel(const T* __restrict__ in, in
     }
 }
 
+
+// ---- row-band building blocks (hydrodem_b200/sharding.py) ----------------------------------------------------------------
+// "K layout": a rank of the sharded Fourier stage holds the spectrum rows ky in [a, b) (0 <= a < b <= ny/2 + 1) followed
+// by their Hermitian mirrors {ny - ky} in ascending order -- a row set closed under ky -> -ky, so the conjugate half of
+// the spectrum of a real raster can be completed without talking to another GPU.
+struct KLayout {
+    int a, b, ny, hlo, nhi;
+    __host__ __device__ KLayout(int a_, int b_, int ny_) : a(a_), b(b_), ny(ny_)
+    {
+        const int kmin = a > 1 ? a : 1, kmax = (b - 1) < (ny - 1) / 2 ? (b - 1) : (ny - 1) / 2;
+        nhi = kmax >= kmin ? kmax - kmin + 1 : 0;
+        hlo = ny - kmax;
+    }
+    __host__ __device__ int rows() const { return (b - a) + nhi; }
+    __host__ __device__ int ky(int t) const { return t < b - a ? a + t : hlo + (t - (b - a)); }
+    __host__ __device__ int local(int k) const { return (k >= a && k < b) ? k - a : (b - a) + (k - hlo); }
+};
+
+// half (rows x nh) c64, rows in K layout  ->  fshift / fabs rows (rows x nx) with the COLUMNS fftshift-ed (the rows stay
+// in K layout).  Same values as the last transpose of hd_fft2_forward_shift_abs: direct copy for kx <= nx/2, conjugate
+// of the mirror row for the rest, |.| by hypotf.
+__global__ void __launch_bounds__(256) hermitian_complete_kernel(const float2* __restrict__ half, int64_t half_pitch,
+                                                                 float2* __restrict__ fshift, int64_t fs_pitch,
+                                                                 float* __restrict__ fabs_out, int64_t fa_pitch, KLayout kl,
+                                                                 int nx)
+{
+    const int nh = nx / 2 + 1, rows = kl.rows(), sx = nx / 2;
+    for (CellIter it(nx); it.y < rows; it.next()) {
+        const int t = (int)it.y, kx = (int)it.x;
+        float2 v;
+        if (kx < nh) {
+            v = half[(int64_t)t * half_pitch + kx];
+        } else {
+            const int km = (kl.ny - kl.ky(t)) % kl.ny;
+            v = half[(int64_t)kl.local(km) * half_pitch + (nx - kx)];
+            v.y = -v.y;
+        }
+        int oc = kx + sx; if (oc >= nx) oc -= nx;
+        if (fshift) fshift[(int64_t)t * fs_pitch + oc] = v;
+        fabs_out[(int64_t)t * fa_pitch + oc] = hypotf(v.x, v.y);
+    }
+}
+
+// bt (rows x ny) c64: bt[x][ny - k] = conj bt[x][k] for 0 < k, 2k != ny (what the Hermitian inverse's transpose writes)
+__global__ void __launch_bounds__(256) conj_mirror_kernel(float2* __restrict__ bt, int64_t pitch, int rows, int ny)
+{
+    const int nlo = ny / 2 + 1, nm = ny - nlo;                  // columns nlo .. ny-1 are mirrors
+    if (nm <= 0) return;
+    for (CellIter it(nm); it.y < rows; it.next()) {
+        const int k = nlo + (int)it.x;
+        float2 v = bt[it.y * pitch + (ny - k)];
+        v.y = -v.y;
+        bt[it.y * pitch + k] = v;
+    }
+}
+
 // ---- host launch helpers -----------------------------------------------------------------------------------------
 // Does a row pass with this plan / load mode leave its output digit-reversed when the consumer allows it?  (Not when
 // two real rows share a transform: separating their spectra needs X[k] and X[n-k] side by side.)
@@ -1244,6 +1300,76 @@ int hd_fft_rows(void* plan, const void* in, int in_dtype, int64_t in_pitch, void
     hd_prof_begin("transpose_kernel", s);                         // long rows, row layout wanted: transpose back
     transpose_kernel<float2, false><<<transpose_grid(nx, (int)nrows), 256, 0, s>>>(At, nrows, (float2*)out, out_pitch, nullptr,
                                                                                   0, nx, (int)nrows, 0, 0, RowPerm{1, nx, nullptr});
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+
+// One pass of the sharded Fourier stage: batched 1-D transforms along the rows of a local (nrows x n) block (n = the
+// plan's nx for axis 0, ny for axis 1), then the local transpose into out_t (kept_cols x nrows) in natural frequency
+// order -- the layout the all-to-all sends from.  `load` selects exactly the row pass the single-GPU functions run
+// (0 real rows [pairs], 1 complex, 2 (1 - mask) * shifted spectrum, 3 Hermitian row pairs), so every transform
+// performs the same arithmetic as on one GPU.  real_out: the pass stores |z| (load 1) or |re|, |im| (load 3) as float.
+int hd_fft_band_pass(void* plan, int axis, int load, const void* in, int64_t in_pitch, int64_t nrows, const void* mask,
+                     int64_t mask_pitch, int shift_cols, int inverse, int real_out, void* out_t, int64_t out_t_pitch,
+                     int64_t keep_cols, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    if (!plan || !in || !out_t || !workspace) return HD_ERR_NULL;
+    Plan2D* p = (Plan2D*)plan;
+    const Plan1D& pl = axis == 0 ? p->px : p->py;
+    const int n = pl.n_total;
+    if (nrows < 1 || nrows > 0x7fffffff || axis < 0 || axis > 1 || load < 0 || load > 3) return HD_ERR_ARG;
+    if (load == LOAD_MASKED_SHIFTED && !mask) return HD_ERR_NULL;
+    if (load == LOAD_C64_HPAIR && !real_out) return HD_ERR_ARG;
+    if (workspace_bytes < nrows * (int64_t)n * (int64_t)sizeof(float2)) return HD_ERR_WORKSPACE;
+    if (in_pitch < n || out_t_pitch < nrows) return HD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    float2* A = (float2*)workspace;
+    RowsArgs r{in, in_pitch, A, n, (const uint8_t*)mask, mask_pitch, (int)nrows, 0, shift_cols, inverse ? 1 : 0,
+               real_out ? 1 : 0, (int)nrows};
+    if (int e = launch_rows(pl, r, load, s)) return e;
+    const RowPerm pm = perm_of(pl, load);
+    if (real_out) {
+        hd_prof_begin("transpose_real_kernel", s);
+        transpose_real_kernel<float><<<transpose_grid((int)nrows, n), 256, 0, s>>>((const float*)A, n, (float*)out_t, out_t_pitch,
+                                                                                  (int)nrows, n, pm);
+    } else {
+        hd_prof_begin("transpose_kernel", s);
+        transpose_kernel<float2, false><<<transpose_grid((int)nrows, n), 256, 0, s>>>(
+            A, n, (float2*)out_t, out_t_pitch, nullptr, 0, (int)nrows, n, 0, 0, pm, keep_cols > 0 ? (int)keep_cols - 1 : -1, 0);
+    }
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+int64_t hd_klayout_rows(int64_t a, int64_t b, int64_t ny) { return KLayout((int)a, (int)b, (int)ny).rows(); }
+int64_t hd_klayout_ky(int64_t a, int64_t b, int64_t ny, int64_t t) { return KLayout((int)a, (int)b, (int)ny).ky((int)t); }
+
+int hd_hermitian_complete(const void* half, int64_t half_pitch, void* fshift, int64_t fshift_pitch, void* fabs_out,
+                          int64_t fabs_pitch, int64_t a, int64_t b, int64_t ny, int64_t nx, void* stream)
+{
+    if (!half || !fabs_out) return HD_ERR_NULL;
+    if (a < 0 || b <= a || b > ny / 2 + 1 || nx < 2 || half_pitch < nx / 2 + 1 || fabs_pitch < nx || (fshift && fshift_pitch < nx))
+        return HD_ERR_ARG;
+    const KLayout kl((int)a, (int)b, (int)ny);
+    const int64_t total = (int64_t)kl.rows() * nx;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    hd_prof_begin("hermitian_complete_kernel", (cudaStream_t)stream);
+    hermitian_complete_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float2*)half, half_pitch, (float2*)fshift,
+                                                                       fshift_pitch, (float*)fabs_out, fabs_pitch, kl, (int)nx);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+int hd_conj_mirror_fill(void* bt, int64_t pitch, int64_t rows, int64_t ny, void* stream)
+{
+    if (!bt) return HD_ERR_NULL;
+    if (rows < 1 || ny < 1 || pitch < ny) return HD_ERR_ARG;
+    const int64_t total = rows * (ny - (ny / 2 + 1));
+    if (total <= 0) return HD_OK;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+    hd_prof_begin("conj_mirror_kernel", (cudaStream_t)stream);
+    conj_mirror_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float2*)bt, pitch, (int)rows, (int)ny);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }

@@ -78,8 +78,13 @@ __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) fill_finish_kernel(const float* __restrict__ z, int64_t z_pitch,
                                                           float* __restrict__ w, int64_t w_pitch, int64_t ny, int64_t nx,
-                                                          const int* __restrict__ any_nodata = nullptr)
+                                                          const int* __restrict__ any_nodata = nullptr,
+                                                          const int* __restrict__ status = nullptr,
+                                                          const int* __restrict__ pending = nullptr)
 {
+    // a fill that stalled must not pass for a result: poison the first cell (see STATUS_OFF)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ((status && *status != 0) || (pending && *pending != 0)))
+        w[0] = __int_as_float(0x7fc00000);
     if (any_nodata && *any_nodata == 0) return;          // fill_init_kernel saw no nodata cell: nothing to restore
     for (CellIter it(nx); it.y < ny; it.next()) {
         const int64_t y = (int64_t)it.y, x = (int64_t)it.x;
@@ -178,6 +183,13 @@ struct FillCtl {
 };
 constexpr int SLOT_EMPTY = -1;
 constexpr int SPIN_LIMIT = 1 << 22;
+// Sticky status word of a fill, at byte STATUS_OFF of the workspace (inside the 256 bytes reserved for the finest level's
+// control block, cleared once per hd_pdfill / first hd_pdfill_band call): set by ANY level whose worklist stalled
+// (a waiting CTA ran out of patience: preemption, MPS, a debugger) or whose in-tile iteration hit its cap.  The finish
+// kernels poison W[0][0] with NaN when it is set, and hd_pdfill_status reads it back: a fill that did not reach the
+// fixed point can never pass silently, with or without statistics, inside or outside a CUDA graph.
+constexpr int STATUS_OFF = 192;
+enum { FILL_STALLED = 1, FILL_ITER_CAP = 2, FILL_PENDING = 4 };
 // per-tile state: a tile is never processed by two CTAs at once (a second writer could overwrite a lower W with a
 // higher one); a tile that is poked while running is marked dirty and re-queued by its own worker when it finishes
 enum { T_IDLE = 0, T_QUEUED = 1, T_RUNNING = 2, T_DIRTY = 3 };
@@ -341,7 +353,7 @@ __device__ __forceinline__ void fill_march(float* __restrict__ ws, const float* 
 
 __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restrict__ z, int64_t z_pitch, float* __restrict__ w,
                                                          int64_t w_pitch, int64_t ny, int64_t nx, int tiles_x, int tiles_y,
-                                                         FillCtl* ctl, int* slots, int* queued)
+                                                         FillCtl* ctl, int* slots, int* queued, int* status)
 {
     // This kernel does not use TMA: W must be read L2-coherently (ld.global.cg) while other CTAs update it, and both
     // boxes have to land in a padded (conflict-free) layout that a dense TMA box cannot produce.
@@ -368,7 +380,7 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
             const int v = *slot;
             if (v != SLOT_EMPTY) { *slot = SLOT_EMPTY; tile = v; break; }
             if (*(volatile int*)&ctl->pending <= 0 || *(volatile int*)&ctl->error) break;
-            if (spin > SPIN_LIMIT) { atomicExch(&ctl->error, 1); break; }
+            if (spin > SPIN_LIMIT) { atomicExch(&ctl->error, 1); atomicOr(status, FILL_STALLED); break; }
             __nanosleep(100);
         }
         if (tile >= 0) { atomicExch(&queued[tile], T_RUNNING); __threadfence(); }
@@ -455,7 +467,10 @@ __global__ void __launch_bounds__(FNT, 4) fill_async_kernel(const float* __restr
             else                 fill_march<-1, WS_STRIDE>(ws, zs, (lane64 + 1) * WS_STRIDE + FT);
             ++iters;
             __syncthreads();
-            if (iters > 4096) break;
+            if (iters > 4096) {                          // (unreachable on real terrain; never silently)
+                if (threadIdx.x == 0) atomicOr(status, FILL_ITER_CAP);
+                break;
+            }
         }
         if (threadIdx.x == 0) { atomicAdd(&ctl->iterations, (unsigned long long)iters); tc3 = clock64(); }
 
@@ -600,6 +615,87 @@ __global__ void __launch_bounds__(256) d8_kernel(const float* __restrict__ w, in
     }
 }
 
+
+// Last pass of the fill FUSED with the D8 pass: nodata cells (outlets at -inf while iterating) get their NaN back and
+// every cell's flow direction is written in the same sweep over W -- 4 B read + 1 B written per cell, W is not read
+// a second time by a separate D8 launch.  A fill that stalled (status word set, see FILL_*) poisons W[0][0] and the
+// first code with NaN / 255 so that it cannot pass for a result.
+__global__ void __launch_bounds__(256) fill_finish_d8_kernel(float* __restrict__ w, int64_t w_pitch, uint8_t* __restrict__ out,
+                                                             int64_t out_pitch, int64_t ny, int64_t nx,
+                                                             const FillCtl* __restrict__ ctl, const int* __restrict__ status)
+{
+    const float ninf = __int_as_float(0xff800000), qnan = __int_as_float(0x7fc00000);
+    const bool bad = (status && *status != 0) || (ctl && ctl->pending != 0);
+    const int64_t nxq = (nx + 3) / 4;
+    for (CellIter it(nxq); it.y < ny; it.next()) {
+        const int64_t y = it.y, x0 = 4 * it.x;
+        float win[3][6];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int64_t yy = y + dy - 1;
+            if (yy < 0 || yy >= ny) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) win[dy][j] = 0.f;
+                continue;
+            }
+            const float* p = w + yy * w_pitch + x0;
+            float q[4];
+            if (x0 + 3 < nx && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(p));       // (neighbours may be rewriting -inf as NaN)
+                q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q[j] = (x0 + j < nx) ? __ldcg(p + j) : 0.f;
+            }
+            win[dy][0] = x0 > 0 ? __ldcg(p - 1) : 0.f;
+            win[dy][1] = q[0]; win[dy][2] = q[1]; win[dy][3] = q[2]; win[dy][4] = q[3];
+            win[dy][5] = x0 + 4 < nx ? __ldcg(p + 4) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) win[dy][j] = win[dy][j] == ninf ? qnan : win[dy][j];   // nodata
+        }
+        uint8_t codes[4] = {0, 0, 0, 0};
+        bool restore = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t x = x0 + j;
+            const float c = win[1][j + 1];
+            restore |= (c != c) && x < nx;
+            if (y == 0 || y >= ny - 1 || x == 0 || x >= nx - 1) continue;
+            const float nb[8] = {win[1][j + 2], win[2][j + 2], win[2][j + 1], win[2][j], win[1][j], win[0][j],
+                                 win[0][j + 1], win[0][j + 2]};
+            float best = 0.f;
+            uint8_t code = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float drop = __fsub_rn(c, nb[k]);
+                if (k & 1) drop = __fmul_rn(drop, 0.70710678f);
+                if (drop > best) { best = drop; code = (uint8_t)(1u << k); }
+            }
+            codes[j] = code;
+        }
+        if (restore) {                                                    // rare: rewrite the quad with NaN at the nodata cells
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x0 + j < nx && win[1][j + 1] != win[1][j + 1]) w[y * w_pitch + x0 + j] = qnan;
+        }
+        if (bad && y == 0 && x0 == 0) { w[0] = qnan; codes[0] = 255; }
+        store4v<uint8_t>(out, out_pitch, y, x0, nx, codes);
+    }
+}
+
+// halo row of a band after an exchange: W = min(W, received); *lowered |= 1 when any cell went down (the banded fill
+// needs another round).  -inf (nodata) and NaN never count.
+__global__ void __launch_bounds__(256) halo_min_kernel(float* __restrict__ w, const float* __restrict__ recv, int64_t nx,
+                                                       int* __restrict__ lowered)
+{
+    bool any = false;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < nx; x += (int64_t)gridDim.x * blockDim.x) {
+        const float r = recv[x], c = w[x];
+        if (r < c) { w[x] = r; any = true; }
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) atomicExch(lowered, 1);
+}
+
 int stream_grid(int64_t total)
 {
     const int64_t b = (total + 255) / 256, cap = (int64_t)hd_num_sms() * 16;
@@ -616,11 +712,25 @@ struct FillOpts {
     bool seed_all = false;        // every tile starts queued (fine level of the multigrid start)
     const float* wc = nullptr;    // coarse-level fill used as the starting W of interior cells
     int64_t c_pitch = 0;
+    int* status = nullptr;        // sticky status word of the whole fill (root workspace + STATUS_OFF)
 };
+
+static int launch_finish_d8(void* w, int64_t w_pitch, void* d8, int64_t d8_pitch, int64_t ny, int64_t nx, const void* workspace,
+                            cudaStream_t s)
+{
+    const FillCtl* ctl = (const FillCtl*)workspace;
+    const int* status = workspace ? (const int*)((const char*)workspace + STATUS_OFF) : nullptr;
+    hd_prof_begin("fill_finish_d8_kernel", s);
+    fill_finish_d8_kernel<<<stream_grid(ny * ((nx + 3) / 4)), 256, 0, s>>>((float*)w, w_pitch, (uint8_t*)d8, d8_pitch, ny, nx, ctl,
+                                                                          status);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
 
 static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
                         int* visits_out, cudaStream_t s, int flags = 0, bool finish = true, FillOpts opt = FillOpts())
 {
+    if (!opt.status) opt.status = (int*)((char*)workspace + STATUS_OFF);
     const int tiles_x = hd_cdiv(nx, FT), tiles_y = hd_cdiv(ny, FT), ntiles = tiles_x * tiles_y;
     FillCtl* ctl = (FillCtl*)workspace;
     const int qcap = ntiles + 8192;
@@ -654,16 +764,17 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     HD_LAUNCH_CHECK(); hd_count_launch();
     hd_prof_begin("fill_async_kernel", s);
     fill_async_kernel<<<grid, FNT, smem, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, tiles_x, tiles_y, ctl,
-                                              slots, queued);
+                                              slots, queued, opt.status);
     HD_LAUNCH_CHECK(); hd_count_launch();
     if (finish) {
         hd_prof_begin("fill_finish_kernel", s);
         fill_finish_kernel<<<stream_grid(ny * nx), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx,
-                                                               (flags & 1) ? nullptr : &ctl->any_nodata);
+                                                               (flags & 1) ? nullptr : &ctl->any_nodata, opt.status,
+                                                               &ctl->pending);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
     if (!visits_out && !getenv("HD_FILL_TRACE")) return HD_OK;      // fully asynchronous when nobody asks for statistics
-    static FillCtl* h_ctl = nullptr;
+    static thread_local FillCtl* h_ctl = nullptr;          // per calling thread: concurrent fills never share it
     if (!h_ctl) HD_CUDA_OK(cudaHostAlloc((void**)&h_ctl, sizeof(FillCtl), cudaHostAllocDefault));
     HD_CUDA_OK(cudaMemcpyAsync(h_ctl, ctl, sizeof(FillCtl), cudaMemcpyDeviceToHost, s));
     HD_CUDA_OK(cudaStreamSynchronize(s));
@@ -749,6 +860,7 @@ static int pdfill_multilevel(const void* z, int64_t z_pitch, void* w, int64_t w_
         const Level& L = lv[l];
         FillOpts o;
         o.preinit = true;
+        o.status = (int*)((char*)workspace + STATUS_OFF);
         if (l < nlev - 1) {
             hd_prof_begin("fill_refine_kernel", s);
             fill_refine_kernel<<<stream_grid(L.ny * L.nx), 256, 0, s>>>(L.w, L.pitch, L.ny, L.nx, lv[l + 1].w, lv[l + 1].pitch);
@@ -758,6 +870,7 @@ static int pdfill_multilevel(const void* z, int64_t z_pitch, void* w, int64_t w_
         if (int e = pdfill_async(L.z, L.pitch, L.w, L.pitch, L.ny, L.nx, L.ctl, nullptr, s, flags & 6, false, o)) return e;
     }
     FillOpts fine;
+    fine.status = (int*)((char*)workspace + STATUS_OFF);
     fine.seed_all = true;
     fine.wc = lv[0].w;
     fine.c_pitch = lv[0].pitch;
@@ -771,6 +884,7 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
     if (ny < 1 || nx < 1 || z_pitch < nx || w_pitch < nx) return HD_ERR_ARG;
     if (workspace_bytes < hd_pdfill_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
+    HD_CUDA_OK(cudaMemsetAsync((char*)workspace + STATUS_OFF, 0, sizeof(int), s));
     const int tiles_x = hd_cdiv(nx, FT), tiles_y = hd_cdiv(ny, FT), ntiles = tiles_x * tiles_y;
     const char* mode = getenv("HD_FILL_MODE");
     if (!(mode && mode[0] == 's') && max_sweeps <= 0)
@@ -789,7 +903,7 @@ extern "C" int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitc
     HD_LAUNCH_CHECK(); hd_count_launch();
     // every tile starts active
     HD_CUDA_OK(cudaMemsetAsync(flags_a, 1, (size_t)ntiles * sizeof(int), s));   // any non-zero byte pattern = active
-    static int* h_changed = nullptr;
+    static thread_local int* h_changed = nullptr;
     if (!h_changed) HD_CUDA_OK(cudaHostAlloc((void**)&h_changed, sizeof(int), cudaHostAllocDefault));
     int sweeps = 0, rc = HD_OK;
     int* fin = flags_a;
@@ -831,6 +945,7 @@ extern "C" int hd_pdfill_band(const void* z, int64_t z_pitch, void* w, int64_t w
     if (!z || !w || !workspace) return HD_ERR_NULL;
     if (ny < 1 || nx < 1 || z_pitch < nx || w_pitch < nx || (flags & ~7)) return HD_ERR_ARG;
     if (workspace_bytes < hd_pdfill_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
+    if (!(flags & 1)) HD_CUDA_OK(cudaMemsetAsync((char*)workspace + STATUS_OFF, 0, sizeof(int), (cudaStream_t)stream));
     if (!(flags & 1))       // first round of a band: multigrid start (halo rows are not outlets); later rounds continue
         return pdfill_multilevel(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, (cudaStream_t)stream, flags, false);
     return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, (cudaStream_t)stream, flags, false);
@@ -855,6 +970,56 @@ extern "C" int hd_d8(const void* w, int64_t w_pitch, void* out, int64_t out_pitc
     hd_prof_begin("d8_kernel", (cudaStream_t)stream);
     d8_kernel<<<stream_grid(ny * ((nx + 3) / 4)), 256, 0, (cudaStream_t)stream>>>((const float*)w, w_pitch, (uint8_t*)out, out_pitch, ny,
                                                                     nx);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+// hd_pdfill + hd_d8 in one call: the fill, then ONE pass that restores NaN at the nodata cells and writes the flow
+// directions (fill_finish_d8_kernel).  Fully asynchronous, capturable in a CUDA graph.
+extern "C" int hd_pdfill_d8(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, void* d8, int64_t d8_pitch, int64_t ny,
+                            int64_t nx, void* workspace, int64_t workspace_bytes, int* visits_out, void* stream)
+{
+    if (!z || !w || !d8 || !workspace) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || z_pitch < nx || w_pitch < nx || d8_pitch < nx) return HD_ERR_ARG;
+    if (workspace_bytes < hd_pdfill_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    HD_CUDA_OK(cudaMemsetAsync((char*)workspace + STATUS_OFF, 0, sizeof(int), s));
+    if (int e = pdfill_multilevel(z, z_pitch, w, w_pitch, ny, nx, workspace, visits_out, s, 0, false)) return e;
+    return launch_finish_d8(w, w_pitch, d8, d8_pitch, ny, nx, workspace, s);
+}
+
+// The fused last pass on its own (row-band fill: after the last round and the final halo refresh).
+extern "C" int hd_pdfill_finish_d8(void* w, int64_t w_pitch, void* d8, int64_t d8_pitch, int64_t ny, int64_t nx,
+                                   const void* workspace, void* stream)
+{
+    if (!w || !d8) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || w_pitch < nx || d8_pitch < nx) return HD_ERR_ARG;
+    return launch_finish_d8(w, w_pitch, d8, d8_pitch, ny, nx, workspace, (cudaStream_t)stream);
+}
+
+// Sticky status of the last fill that used this workspace (synchronises the stream): 0 = reached the fixed point.
+extern "C" int hd_pdfill_status(const void* workspace, int* status_out, void* stream)
+{
+    if (!workspace || !status_out) return HD_ERR_NULL;
+    static thread_local int* h_word = nullptr;
+    if (!h_word) HD_CUDA_OK(cudaHostAlloc((void**)&h_word, 2 * sizeof(int), cudaHostAllocDefault));
+    cudaStream_t s = (cudaStream_t)stream;
+    HD_CUDA_OK(cudaMemcpyAsync(h_word, (const char*)workspace + STATUS_OFF, sizeof(int), cudaMemcpyDeviceToHost, s));
+    HD_CUDA_OK(cudaMemcpyAsync(h_word + 1, &((const FillCtl*)workspace)->pending, sizeof(int), cudaMemcpyDeviceToHost, s));
+    HD_CUDA_OK(cudaStreamSynchronize(s));
+    *status_out = h_word[0] | (h_word[1] != 0 ? FILL_PENDING : 0);
+    return HD_OK;
+}
+
+// Row-band fill, after a halo exchange: w_halo = min(w_halo, received row); *lowered (device int) is set to 1 when a
+// cell went down.  No host synchronisation: the ranks all-reduce the device flags and read ONE word per round.
+extern "C" int hd_halo_min_flag(void* w_halo, const void* received, int64_t nx, int* lowered, void* stream)
+{
+    if (!w_halo || !received || !lowered) return HD_ERR_NULL;
+    if (nx < 1) return HD_ERR_ARG;
+    hd_prof_begin("halo_min_kernel", (cudaStream_t)stream);
+    halo_min_kernel<<<(int)((nx + 255) / 256 < 64 ? (nx + 255) / 256 : 64), 256, 0, (cudaStream_t)stream>>>(
+        (float*)w_halo, (const float*)received, nx, lowered);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }

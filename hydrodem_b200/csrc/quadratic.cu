@@ -6,10 +6,12 @@
 // with x, y = linspace(-ws/2 + 1, ws/2, ws) (half-pixel asymmetric offsets).  All three sums are separable:
 //     column pass : V1[y][x] = sum_dy w,  Vyy[y][x] = sum_dy y^2 w        (one pass down each tile column)
 //     row pass    : s1 = sum_dx V1,  s3 = sum_dx Vyy,  s2 = sum_dx x^2 V1
-// i.e. 2*ws taps instead of ws^2 per sum.  The kernel weights sum to 1, so the sums are taken over (w - ref) with a
-// per-tile reference elevation: float32 partial sums then carry terrain relief, not absolute elevation, and the
-// final expression (evaluated in double) agrees with the reference to ~5e-7 relative -- inside the 1e-5
-// tolerance class of this stage.
+// i.e. 2*ws taps instead of ws^2 per sum.  The window values are cast to float32 like the reference's windows
+// (sliding_window.py:132) and every sum is accumulated in DOUBLE, tap by tap in a fixed order: a cell's result is a
+// fixed sequence of operations on its own window and nothing else -- it does not depend on where tile or band
+// boundaries fall, so a row-band sharded mosaic gives the same bits as one GPU (round 1 re-centred float32 sums on a
+// per-tile reference elevation, which made borderline `dem - smooth > 1.5` tests flip with the partition).  The
+// result agrees with the reference (float32 s1, float64 s2 / s3) to ~1e-7 relative: inside the 1e-5 tolerance class.
 //
 // Groves tail (one GrovesCorrection iteration, fused -- the six elementwise filters never touch HBM):
 //     hi = dem - smooth;  tall = hi > 1.5;  keep = 1 - groves * tall;  out = keep * hi + smooth
@@ -29,6 +31,8 @@ struct QuadParams {
     double thr;          // tall-groves threshold (1.5)
 };
 
+constexpr int HALF = TH / 2;          // partial sums are kept for half a tile at a time (shared memory: 2 CTAs per SM)
+
 template <int H, typename T, typename OutT, bool GROVES>
 __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                        const __grid_constant__ CUtensorMap tm_groves,
@@ -37,8 +41,7 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
 {
     constexpr int WS = 2 * H + 1;
     constexpr int CWU = TW + 2 * H;                 // window columns touched by a tile
-    constexpr int CW = (CWU + 3) / 4 * 4 + 4;       // row stride of the partial-sum arrays: 16-byte aligned rows, room for
-                                                    // whole float4 reads past the last used column
+    constexpr int CW = (CWU + 1) / 2 * 2 + 2;       // row stride of the partial-sum arrays (doubles): 16-byte aligned rows
     constexpr int HX = hd_halo_x(H, sizeof(T));
     constexpr int XOFF = HX - H;
     constexpr int IN_W = TW + 2 * HX;
@@ -48,12 +51,8 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
     constexpr int NP = GROVES ? 2 : 1;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
-    __shared__ float s_ref;
-    float* v1 = reinterpret_cast<float*>(smem + 2 * STAGE);     // [TH][CW]  sum_dy (w - ref)
-    float* vyy = v1 + TH * CW;                                   // [TH][CW]  sum_dy y^2 (w - ref)
-    float c2f[WS];
-#pragma unroll
-    for (int k = 0; k < WS; ++k) c2f[k] = (float)p.c2[k];        // squared half-integers: exact in float32
+    double* v1 = reinterpret_cast<double*>(smem + 2 * STAGE);   // [HALF][CW]  sum_dy w
+    double* vyy = v1 + HALF * CW;                                // [HALF][CW]  sum_dy y^2 w
 
     const TilePlane planes[2] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * sizeof(T)), HX, H},
                                  {&tm_groves, IN_BYTES, (uint32_t)(TH * TW), 0, 0}};
@@ -64,114 +63,95 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
         // Groves tail: where groves == 0 the reference evaluates smooth + 1 * (dem - smooth), i.e. dem to the last bit or
         // two -- those cells are copied, and a tile without a single groves cell (most of them: groves cover about one
         // per cent of a scene) skips both filter passes.
+        bool any_half[2] = {true, true};
         if (GROVES) {
-            bool any = false;
 #pragma unroll
-            for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
-                const int idx = rep * NT + threadIdx.x;
-                const int ro = idx >> 5, c4 = idx & 31;
-                const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
-                const uint32_t g = (y < ny && x < nx) ? gwords[idx] : 0u;
-                any |= g != 0u;
-            }
-            if (!__syncthreads_or(any)) {
+            for (int hf = 0; hf < 2; ++hf) {
+                bool any = false;
 #pragma unroll
-                for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
-                    const int idx = rep * NT + threadIdx.x;
+                for (int rep = 0; rep < HALF * TW / 4 / NT; ++rep) {
+                    const int idx = hf * (HALF * TW / 4) + rep * NT + threadIdx.x;
                     const int ro = idx >> 5, c4 = idx & 31;
                     const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
-                    if (y >= ny || x >= nx) continue;
-                    OutT res[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) res[j] = (OutT)tile[(ro + H) * IN_W + 4 * c4 + j + HX];
-                    store4v<OutT>(out, out_pitch, y, x, nx, res);
+                    const uint32_t g = (y < ny && x < nx) ? gwords[idx] : 0u;
+                    any |= g != 0u;
                 }
-                return;
+                any_half[hf] = __syncthreads_or(any);
             }
         }
-        // The kernel sums to 1, so smoothed = ref + K * (w - ref) for any constant ref.  Taking ref from the tile
-        // keeps the float32 partial sums small (terrain relief instead of absolute elevation): ~5e-7 relative.
-        if (threadIdx.x == 0) {
-            const float r = (float)tile[H * IN_W + HX];
-            s_ref = (r - r == 0.f) ? r : 0.f;                    // finite, else 0
-        }
-        __syncthreads();
-        const float ref = s_ref;
-        // ---- column pass ----------------------------------------------------------------------------
-        for (int item = threadIdx.x; item < CWU * (TH / STRIP); item += NT) {
-            const int c = item % CWU, s = item / CWU;
-            float v[STRIP + 2 * H];
-#pragma unroll
-            for (int r = 0; r < STRIP + 2 * H; ++r)
-                v[r] = (float)tile[(s * STRIP + r) * IN_W + c + XOFF] - ref;          // window cast to float32
-#pragma unroll
-            for (int o = 0; o < STRIP; ++o) {
-                float a = 0.f, b = 0.f;
-#pragma unroll
-                for (int r = 0; r < WS; ++r) {
-                    a += v[o + r];
-                    b = fmaf(c2f[r], v[o + r], b);
-                }
-                v1[(s * STRIP + o) * CW + c] = a;
-                vyy[(s * STRIP + o) * CW + c] = b;
-            }
-        }
-        __syncthreads();
-        // ---- row pass: 4 consecutive outputs per thread -------------------------------------------------
 #pragma unroll 1
-        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
-            const int idx = rep * NT + threadIdx.x;
-            const int ro = idx >> 5, c4 = idx & 31;
-            const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
-            if (y >= ny || x >= nx) continue;
-            const uint32_t gq = GROVES ? gwords[idx] : 0u;
-            if (GROVES && gq == 0u) {                     // no groves cell in this quad: copy
-                OutT cp[4];
+        for (int hf = 0; hf < 2; ++hf) {
+            const int r0 = hf * HALF;                               // first tile row of this half
+            if (any_half[hf]) {
+                // ---- column pass: fixed tap order, double accumulators ------------------------------------------
+                for (int item = threadIdx.x; item < CWU * (HALF / STRIP); item += NT) {
+                    const int c = item % CWU, sq = item / CWU;
+                    float v[STRIP + 2 * H];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cp[j] = (OutT)tile[(ro + H) * IN_W + 4 * c4 + j + HX];
-                store4v<OutT>(out, out_pitch, y, x, nx, cp);
-                continue;
-            }
-            constexpr int NQ = (WS + 3 + 3) / 4;        // float4 loads covering the WS + 3 columns of 4 windows
-            float a[4 * NQ], b[4 * NQ];
-            const float4* pa = reinterpret_cast<const float4*>(v1 + ro * CW + 4 * c4);    // lanes 16 B apart: conflict free
-            const float4* pb = reinterpret_cast<const float4*>(vyy + ro * CW + 4 * c4);
+                    for (int r = 0; r < STRIP + 2 * H; ++r)
+                        v[r] = (float)tile[(r0 + sq * STRIP + r) * IN_W + c + XOFF];          // window cast to float32
 #pragma unroll
-            for (int k = 0; k < NQ; ++k) {
-                const float4 qa = pa[k], qb = pb[k];
-                a[4 * k] = qa.x; a[4 * k + 1] = qa.y; a[4 * k + 2] = qa.z; a[4 * k + 3] = qa.w;
-                b[4 * k] = qb.x; b[4 * k + 1] = qb.y; b[4 * k + 2] = qb.z; b[4 * k + 3] = qb.w;
-            }
-            OutT res[4];
+                    for (int o = 0; o < STRIP; ++o) {
+                        double a = 0.0, b = 0.0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const T ctr = tile[(ro + H) * IN_W + 4 * c4 + j + HX];
-                const bool interior = y >= H && y < ny - H && x + j >= H && x + j < nx - H;
-                T smooth = ctr;                                    // smoothed = dem.copy()  (:249)
-                if (interior) {
-                    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                    for (int d = 0; d < WS; ++d) {
-                        s1 += a[j + d];
-                        s2 = fmaf(c2f[d], a[j + d], s2);
-                        s3 += b[j + d];
+                        for (int r = 0; r < WS; ++r) {
+                            a += (double)v[o + r];
+                            b = fma(p.c2[r], (double)v[o + r], b);
+                        }
+                        v1[(sq * STRIP + o) * CW + c] = a;
+                        vyy[(sq * STRIP + o) * CW + c] = b;
                     }
-                    // (:255-256) on the re-centred sums, in double; stored in dem's dtype
-                    smooth = (T)((double)ref + (((double)s2 + (double)s3) * p.r1 - (double)s1 * p.r23) / p.den);
                 }
-                if (GROVES) {
-                    const uint32_t gbyte = (gq >> (8 * j)) & 0xffu;
-                    if (gbyte == 0u) { res[j] = (OutT)ctr; continue; }
-                    const double g = (double)gbyte;
-                    const T hi = ctr - smooth;                                        // SubtractionFilter (:725)
-                    const double tall = (hi > (T)p.thr) ? 1.0 : 0.0;                  // MaskTallGroves
-                    const double keep = 1.0 - g * tall;                               // Product, 1 - .
-                    res[j] = (OutT)__dadd_rn(__dmul_rn(keep, (double)hi), (double)smooth);   // x hi, + smooth (:729-731)
-                } else {
-                    res[j] = (OutT)smooth;
-                }
+                __syncthreads();
             }
-            store4v<OutT>(out, out_pitch, y, x, nx, res);
+            // ---- row pass: 4 consecutive outputs per thread -----------------------------------------------------
+#pragma unroll 1
+            for (int rep = 0; rep < HALF * TW / 4 / NT; ++rep) {
+                const int idx = r0 * (TW / 4) + rep * NT + threadIdx.x;
+                const int ro = idx >> 5, c4 = idx & 31;
+                const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+                if (y >= ny || x >= nx) continue;
+                const uint32_t gq = GROVES ? gwords[idx] : 0u;
+                if (GROVES && gq == 0u) {                     // no groves cell in this quad: copy
+                    OutT cp[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cp[j] = (OutT)tile[(ro + H) * IN_W + 4 * c4 + j + HX];
+                    store4v<OutT>(out, out_pitch, y, x, nx, cp);
+                    continue;
+                }
+                const double* pa = v1 + (ro - r0) * CW + 4 * c4;
+                const double* pb = vyy + (ro - r0) * CW + 4 * c4;
+                OutT res[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const T ctr = tile[(ro + H) * IN_W + 4 * c4 + j + HX];
+                    const bool interior = y >= H && y < ny - H && x + j >= H && x + j < nx - H;
+                    const uint32_t gbyte = (gq >> (8 * j)) & 0xffu;
+                    if (GROVES && gbyte == 0u) { res[j] = (OutT)ctr; continue; }
+                    T smooth = ctr;                                    // smoothed = dem.copy()  (:249)
+                    if (interior) {
+                        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                        for (int d = 0; d < WS; ++d) {
+                            s1 += pa[j + d];
+                            s2 = fma(p.c2[d], pa[j + d], s2);
+                            s3 += pb[j + d];
+                        }
+                        smooth = (T)(((s2 + s3) * p.r1 - s1 * p.r23) / p.den);        // (:255-256), stored in dem's dtype
+                    }
+                    if (GROVES) {
+                        const double g = (double)gbyte;
+                        const T hi = ctr - smooth;                                        // SubtractionFilter (:725)
+                        const double tall = (hi > (T)p.thr) ? 1.0 : 0.0;                  // MaskTallGroves
+                        const double keep = 1.0 - g * tall;                               // Product, 1 - .
+                        res[j] = (OutT)__dadd_rn(__dmul_rn(keep, (double)hi), (double)smooth);   // x hi, + smooth (:729-731)
+                    } else {
+                        res[j] = (OutT)smooth;
+                    }
+                }
+                store4v<OutT>(out, out_pitch, y, x, nx, res);
+            }
+            if (any_half[hf] && hf == 0) __syncthreads();       // the partial sums are rewritten for the second half
         }
     });
 }
@@ -180,9 +160,9 @@ template <int H, typename T, typename OutT, bool GROVES>
 int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_pitch, const void* groves,
            int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t stream)
 {
-    constexpr int CW = (TW + 2 * H + 3) / 4 * 4 + 4, IN_W = TW + 2 * hd_halo_x(H, sizeof(T)), IN_H = TH + 2 * H;
+    constexpr int CW = (TW + 2 * H + 1) / 2 * 2 + 2, IN_W = TW + 2 * hd_halo_x(H, sizeof(T)), IN_H = TH + 2 * H;
     constexpr size_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128 + (GROVES ? TH * TW : 0);
-    constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * sizeof(float);
+    constexpr size_t SMEM = 2 * STAGE + 2 * HALF * CW * sizeof(double);
     CUtensorMap tm, tm_g;
     if (int e = hd_make_tmap_2d(&tm, in, dtype, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
     tm_g = tm;

@@ -58,12 +58,55 @@ class SinkFill(DeviceFilter):
         out = dev.empty(raster.ny, raster.nx, _lib.F32, np.float32)
         nbytes = lib.hd_pdfill_workspace_bytes(raster.ny, raster.nx)
         work = dev.scratch(nbytes)
+        import torch
+        # statistics need a host synchronisation inside the call: impossible while a CUDA graph is being captured
+        stats = self.want_stats and not torch.cuda.is_current_stream_capturing()
         sweeps = ctypes.c_int(-1)
+        self._work = work
         _lib.check(lib.hd_pdfill(src.ptr, src.pitch, out.ptr, out.pitch, src.ny, src.nx, ctypes.c_void_p(work.data_ptr()),
-                                 nbytes, int(self.max_sweeps), ctypes.byref(sweeps) if self.want_stats else None,
+                                 nbytes, int(self.max_sweeps), ctypes.byref(sweeps) if stats else None,
                                  dev.stream_ptr()))
-        self.sweeps = sweeps.value if self.want_stats else None
+        self.sweeps = sweeps.value if stats else None
         return out
+
+
+class SinkFillD8(DeviceFilter):
+    """SinkFill followed by D8FlowDirection as ONE launch group: the fill, then a single pass that restores NaN at the
+    nodata cells and writes the flow directions (``hd_pdfill_d8``).  ``run_device`` returns (filled, d8).
+    ``status()`` reads the fill's sticky status word (0 = fixed point reached) -- it synchronises the stream."""
+
+    def __init__(self, *, want_stats=False):
+        self.want_stats = want_stats
+        self.sweeps = None
+        self._work = None
+
+    def run_device(self, raster):
+        import torch
+        lib = _lib.load()
+        src = as_f32(raster)
+        filled = dev.empty(raster.ny, raster.nx, _lib.F32, np.float32)
+        d8 = dev.empty(raster.ny, raster.nx, _lib.U8, np.uint8)
+        nbytes = lib.hd_pdfill_workspace_bytes(raster.ny, raster.nx)
+        self._work = work = dev.scratch(nbytes)
+        # statistics need a host synchronisation inside the call: impossible while a CUDA graph is being captured
+        stats = self.want_stats and not torch.cuda.is_current_stream_capturing()
+        visits = ctypes.c_int(-1)
+        _lib.check(lib.hd_pdfill_d8(src.ptr, src.pitch, filled.ptr, filled.pitch, d8.ptr, d8.pitch, src.ny, src.nx,
+                                    ctypes.c_void_p(work.data_ptr()), nbytes, ctypes.byref(visits) if stats else None,
+                                    dev.stream_ptr()))
+        self.sweeps = visits.value if stats else None
+        return filled, d8
+
+    def status(self):
+        st = ctypes.c_int(-1)
+        _lib.check(_lib.load().hd_pdfill_status(ctypes.c_void_p(self._work.data_ptr()), ctypes.byref(st), dev.stream_ptr()))
+        return st.value
+
+    def apply(self, image_to_filter):
+        from . import Filter
+        Filter.apply(self, image_to_filter)
+        filled, d8 = self.run_device(dev.upload(image_to_filter))
+        return dev.download(filled), dev.download(d8)
 
 
 class D8FlowDirection(DeviceFilter):

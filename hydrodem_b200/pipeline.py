@@ -313,10 +313,9 @@ class ConditioningChain:
 
     def _stage_hydrology(self, st):
         """NEW stages: SinkFill + D8FlowDirection on the final DEM."""
-        fill = nf.SinkFill(want_stats=self.fill_stats)
-        st["filled"] = fill.run_device(st["final32"])
+        fill = nf.SinkFillD8(want_stats=self.fill_stats)             # fill + fused NaN restore / D8 pass
+        st["filled"], st["d8"] = fill.run_device(st["final32"])
         st["fill"] = fill
-        st["d8"] = nf.D8FlowDirection().run_device(st["filled"])
 
     def _result(self, st):
         out = {"final": st["final"]}

@@ -181,6 +181,34 @@ int hd_fft2_c2c(void* plan, const void* in, int in_dtype, int64_t in_pitch, void
  * transforms.  Workspace: hd_fft2_workspace_bytes(nrows, nx). */
 int hd_fft_rows(void* plan, const void* in, int in_dtype, int64_t in_pitch, void* out, int64_t out_pitch, int64_t nrows,
                 int inverse, int transpose_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- row-band sharded Fourier stage (DetectApplyFourier, custom_filters.py:1053-1101, on a mosaic cut into row bands
+ * over several GPUs: hydrodem_b200/sharding.py).  Every pass below runs EXACTLY the row transforms of the single-GPU
+ * entry points above on a rank's local rows, so the sharded stage reproduces the single-GPU result bit for bit; the
+ * transposes between the passes become all-to-all exchanges.
+ * hd_fft_band_pass: batched 1-D transforms along the rows of a local (nrows x n) block (axis 0: n = plan nx, axis 1:
+ * n = plan ny), then the local transpose into out_t (kept_cols x nrows, natural frequency order).  load: 0 real rows
+ * (two per transform), 1 complex, 2 (1 - mask) * column-shifted spectrum (mask U8), 3 Hermitian row pairs.  real_out:
+ * the pass stores |z| (load 1) or |re| / |im| (load 3) as F32.  keep_cols > 0: only the first keep_cols frequencies
+ * are written (half spectrum of real rows).  Workspace: nrows * n * 8 bytes. */
+int hd_fft_band_pass(void* plan, int axis, int load, const void* in, int64_t in_pitch, int64_t nrows, const void* mask,
+                     int64_t mask_pitch, int shift_cols, int inverse, int real_out, void* out_t, int64_t out_t_pitch,
+                     int64_t keep_cols, void* workspace, int64_t workspace_bytes, void* stream);
+/* "K layout" of a rank's spectrum rows: ky in [a, b) (b <= ny/2 + 1) followed by their mirrors ny - ky in ascending
+ * order -- closed under ky -> -ky, so the conjugate half of a real raster's spectrum is completed locally. */
+int64_t hd_klayout_rows(int64_t a, int64_t b, int64_t ny);
+int64_t hd_klayout_ky(int64_t a, int64_t b, int64_t ny, int64_t t);
+/* half spectrum (rows x (nx/2 + 1), C64, rows in K layout) -> column-shifted full rows: fshift (C64, may be NULL) and
+ * fabs (F32) = what FourierInitial leaves (custom_filters.py:859-877), for this rank's rows. */
+int hd_hermitian_complete(const void* half, int64_t half_pitch, void* fshift, int64_t fshift_pitch, void* fabs_out,
+                          int64_t fabs_pitch, int64_t a, int64_t b, int64_t ny, int64_t nx, void* stream);
+/* bt (rows x ny, C64): columns ny/2+1 .. ny-1 = conjugates of columns ny-k (the Hermitian inverse's intermediate). */
+int hd_conj_mirror_fill(void* bt, int64_t pitch, int64_t rows, int64_t ny, void* stream);
+/* hd_fourier_mask_assemble for the rows of one K layout: q1 / q2 are slabs of the quarter masks starting at quarter row
+ * q0 (q_rows rows); out: U8 (out_rows x nx). */
+int hd_fourier_mask_assemble_rows(const void* q1, int64_t q1_pitch, const void* q2, int64_t q2_pitch, int64_t q0,
+                                  int64_t q_rows, void* out, int64_t out_pitch, int64_t out_rows, int64_t a, int64_t b,
+                                  int64_t ny, int64_t nx, int margin, void* stream);
 int hd_fftshift2(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
                  int inverse, void* stream);
 
@@ -220,6 +248,18 @@ int hd_pdfill(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t 
  * raster frame.  Nodata cells stay at -inf until hd_pdfill_finish restores NaN.  *visits_out = tile visits. */
 int hd_pdfill_band(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
                    int64_t workspace_bytes, int flags, int* visits_out, void* stream);
+/* Fill + D8 fused: the fill, then ONE pass that restores NaN at the nodata cells and writes the D8 codes (W is not
+ * re-read by a separate D8 launch).  Asynchronous and capturable; *visits_out (may be NULL) synchronises once. */
+int hd_pdfill_d8(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, void* d8, int64_t d8_pitch, int64_t ny,
+                 int64_t nx, void* workspace, int64_t workspace_bytes, int* visits_out, void* stream);
+/* The fused last pass alone (row-band fill: after the last round).  workspace: the fill's (status word), may be NULL. */
+int hd_pdfill_finish_d8(void* w, int64_t w_pitch, void* d8, int64_t d8_pitch, int64_t ny, int64_t nx,
+                        const void* workspace, void* stream);
+/* Sticky status of the last fill run with this workspace (0 = fixed point reached; 1 worklist stalled, 2 in-tile
+ * iteration cap, 4 work left).  The finish passes also poison W[0][0] = NaN when it is non-zero.  Synchronises. */
+int hd_pdfill_status(const void* workspace, int* status_out, void* stream);
+/* Row-band fill after a halo exchange: w_halo = min(w_halo, received); *lowered (device int) = 1 if a cell went down. */
+int hd_halo_min_flag(void* w_halo, const void* received, int64_t nx, int* lowered, void* stream);
 int hd_pdfill_finish(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* stream);
 /* D8 flow direction on a (filled) F32 surface -> U8 ESRI codes (E=1, SE=2, S=4, SW=8, W=16, NW=32, N=64, NE=128);
  * steepest positive drop, diagonals scaled by 0.70710678f, ties -> first in that order, frame / NaN / flat -> 0. */

@@ -89,3 +89,22 @@ def test_sinkfill_full_tile():
     eq(w, clib.priority_flood(z))
     eq(nf.D8FlowDirection().apply(w), clib.d8(w))
     print("sweeps", fill.sweeps)
+
+
+def test_fused_fill_d8_equals_separate_passes():
+    """hd_pdfill_d8 (fill, then ONE pass restoring NaN and writing D8) against SinkFill -> D8FlowDirection and the
+    oracle; the sticky status word reads 0."""
+    from hydrodem_b200.filters import new_filters as nf
+    from oracle import hydrology
+    z = np.round(SynthScene(333, 517, 91).srtm())
+    z[40:44, 100:130] = np.nan
+    z[200, 0] = np.nan                                          # nodata on the frame
+    z[150:220, 300:420] -= 7
+    fused = nf.SinkFillD8(want_stats=True)
+    filled, d8 = fused.apply(z)
+    want = hydrology.sinkfill(z)
+    np.testing.assert_array_equal(filled, want)
+    np.testing.assert_array_equal(d8, hydrology.d8(want))
+    np.testing.assert_array_equal(filled, nf.SinkFill().apply(z))
+    np.testing.assert_array_equal(d8, nf.D8FlowDirection().apply(filled))
+    assert fused.status() == 0 and fused.sweeps >= 1

@@ -92,6 +92,11 @@ def test_band_bounds():
     for ny, w in ((3601, 8), (5, 5), (18000, 4)):
         bb = sharding.band_bounds(ny, w)
         assert bb[0][0] == 0 and bb[-1][1] == ny and all(a[1] == c[0] for a, c in zip(bb, bb[1:]))
+    # aligned starts (two rows share one transform on the device: the pairs must not straddle a cut)
+    for ny, w in ((3601, 8), (421, 3), (36000, 8), (10801, 4)):
+        bb = sharding.band_bounds(ny, w, 2)
+        assert bb[0][0] == 0 and bb[-1][1] == ny and all(a[1] == c[0] for a, c in zip(bb, bb[1:]))
+        assert all(a % 2 == 0 for a, _ in bb) and max(b - a for a, b in bb) - min(b - a for a, b in bb) <= 3
 
 
 def _free_port():
@@ -102,36 +107,57 @@ def _free_port():
     return p
 
 
-def _halo_worker(rank, world, port, ny, nx, h, out):
+def _check_exchanges(comm, ny=23, nx=17, h=3):
+    """Halo exchange (grouped send / recv into the margin rows), the transposing all-to-all of the sharded Fourier
+    stage and redistribute_rows between two row layouts, on CPU tensors."""
+    world, rank = comm.world, comm.rank
+    mosaic = torch.arange(ny * nx, dtype=torch.float32).reshape(ny, nx)
+    bounds = sharding.band_bounds(ny, world)
+    r0, r1 = bounds[rank]
+    up, down = (h if rank > 0 else 0), (h if rank < world - 1 else 0)
+    ext = torch.full((up + r1 - r0 + down, nx), -1.0)
+    ext[up:up + r1 - r0] = mosaic[r0:r1]
+    sends, recvs = [], []
+    if up:
+        sends.append((ext[up:up + h], rank - 1)); recvs.append((ext[:up], rank - 1))
+    if down:
+        sends.append((ext[up + r1 - r0 - h:up + r1 - r0], rank + 1)); recvs.append((ext[up + r1 - r0:], rank + 1))
+    comm.p2p(sends, recvs)
+    ok = bool(torch.equal(ext, mosaic[r0 - up:r1 + down]))
+    # transposing all-to-all: block (rows of rank i, columns of rank j) lands on rank j
+    cols_b = sharding.band_bounds(nx, world)
+    t = mosaic[r0:r1].t().contiguous()
+    c0, c1 = cols_b[rank]
+    bufs = [torch.empty((c1 - c0, b - a)) for a, b in bounds]
+    comm.p2p([(t[a:b], j) for j, (a, b) in enumerate(cols_b)], [(bufs[i], i) for i in range(world)])
+    ok &= bool(torch.equal(torch.cat(bufs, dim=1), mosaic[:, c0:c1].t()))
+    # row redistribution: contiguous bands -> overlapping slabs in another order
+    src_ids = [torch.arange(a, b).numpy() for a, b in bounds]
+    dst_ids = [((torch.arange(0, ny // 2 + 2) + 3 * k) % ny).numpy() for k in range(world)]
+    dst = torch.full((len(dst_ids[rank]), nx), -1.0)
+    sharding.redistribute_rows(comm, mosaic[r0:r1].clone(), src_ids, dst_ids, dst)
+    ok &= bool(torch.equal(dst, mosaic[torch.from_numpy(dst_ids[rank])]))
+    flag = torch.tensor([1 if rank == 1 else 0], dtype=torch.int32)
+    ok &= int(comm.allreduce_max_(flag)[0]) == 1
+    ok &= int(comm.allreduce_max_(torch.zeros(1, dtype=torch.int32))[0]) == 0
+    return ok
+
+
+def _gloo_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        comm = sharding.DistComm()
-        mosaic = torch.arange(ny * nx, dtype=torch.float32).reshape(ny, nx)
-        r0, r1 = sharding.band_bounds(ny, world)[rank]
-        band = mosaic[r0:r1].clone()
-        up, down = comm.exchange(band[:h], band[-h:], band[:h], band[-h:])
-        ok = True
-        if rank > 0:
-            ok &= bool(torch.equal(up, mosaic[r0 - h:r0]))
-        else:
-            ok &= up is None
-        if rank < world - 1:
-            ok &= bool(torch.equal(down, mosaic[r1:r1 + h]))
-        else:
-            ok &= down is None
-        ok &= comm.any(rank == 1) is True and comm.any(False) is False
-        out[rank] = int(ok)
+        out[rank] = int(_check_exchanges(sharding.DistComm()))
     finally:
         dist.destroy_process_group()
 
 
-def test_halo_exchange_gloo_world2():
+def test_exchanges_gloo_world2():
     world = 2
     out = mp.Array("i", [0] * world)
     port = _free_port()
-    procs = [mp.Process(target=_halo_worker, args=(r, world, port, 23, 17, 3, out)) for r in range(world)]
+    procs = [mp.Process(target=_gloo_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -140,54 +166,17 @@ def test_halo_exchange_gloo_world2():
     assert list(out) == [1, 1]
 
 
-def test_thread_comm_emulation():
+def test_exchanges_thread_comm():
+    assert sharding.ThreadComm.run(3, _check_exchanges) == [True, True, True]
+    assert sharding.ThreadComm.run(4, lambda c: _check_exchanges(c, 41, 9, 2)) == [True] * 4
+
+
+def test_band_rejects_thin_bands_on_every_rank():
+    """Bands thinner than the halo are refused before any collective, by a test that only depends on (ny, world)."""
     def fn(comm):
-        x = torch.full((2, 4), float(comm.rank))
-        up, down = comm.exchange(x[:1], x[-1:], x[:1], x[-1:])
-        return (None if up is None else float(up[0, 0]), None if down is None else float(down[0, 0]), comm.any(comm.rank == 2))
-    res = sharding.ThreadComm.run(3, fn)
-    assert res == [(None, 1.0, True), (0.0, 2.0, True), (1.0, None, True)]
-
-
-def _a2a_worker(rank, world, port, ny, nx, out):
-    """The all-to-all of the distributed fft2 over gloo: block (rows of rank i, columns of rank j) of a matrix must
-    land on rank j, i.e. the exchange of transposed blocks reassembles full columns."""
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        comm = sharding.DistComm()
-        mat = torch.arange(ny * nx, dtype=torch.float32).reshape(ny, nx)
-        rows_b, cols_b = sharding.band_bounds(ny, world), sharding.band_bounds(nx, world)
-        r0, r1 = rows_b[rank]
-        t = mat[r0:r1].t().contiguous()                              # (nx, my rows): the transposed local band
-        chunks = [t[a:b] for (a, b) in cols_b]
-        mine = cols_b[rank][1] - cols_b[rank][0]
-        got = comm.all_to_all_shaped(chunks, [(mine, b - a) for (a, b) in rows_b])
-        cols = torch.cat(got, dim=1)                                 # (my cols, ny)
-        c0, c1 = cols_b[rank]
-        out[rank] = int(torch.equal(cols, mat[:, c0:c1].t()))
-    finally:
-        dist.destroy_process_group()
-
-
-def test_all_to_all_gloo_world2():
-    world = 2
-    out = mp.Array("i", [0] * world)
-    port = _free_port()
-    procs = [mp.Process(target=_a2a_worker, args=(r, world, port, 11, 7, out)) for r in range(world)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(120)
-        assert p.exitcode == 0
-    assert list(out) == [1, 1]
-
-
-def test_thread_comm_all_to_all():
-    def fn(comm):
-        chunks = [torch.full((1, 2), float(10 * comm.rank + j)) for j in range(comm.world)]
-        got = comm.all_to_all_shaped(chunks, [(1, 2)] * comm.world)
-        return [float(g[0, 0]) for g in got]
-    res = sharding.ThreadComm.run(3, fn)
-    assert res == [[0.0, 10.0, 20.0], [1.0, 11.0, 21.0], [2.0, 12.0, 22.0]]
+        try:
+            sharding.Band(comm, 60, 50)
+        except ValueError:
+            return "refused"
+        return "ok"
+    assert sharding.ThreadComm.run(3, fn) == ["refused"] * 3

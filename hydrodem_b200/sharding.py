@@ -151,36 +151,37 @@ class ThreadComm:
 # ---- row redistribution between two layouts ----------------------------------------------------------------------------
 def _runs(src_ids, dst_ids):
     """Maximal runs that are contiguous in BOTH id lists: [(src_lo, dst_lo, length)], ordered by dst position."""
-    pos = {int(g): k for k, g in enumerate(src_ids)}
-    out, k = [], 0
-    n = len(dst_ids)
-    while k < n:
-        g = int(dst_ids[k])
-        if g not in pos:
-            k += 1
-            continue
-        s0, d0, ln = pos[g], k, 1
-        while k + 1 < n and int(dst_ids[k + 1]) in pos and pos[int(dst_ids[k + 1])] == s0 + ln:
-            k += 1
-            ln += 1
-        out.append((s0, d0, ln))
-        k += 1
-    return out
+    src_ids, dst_ids = np.asarray(src_ids, dtype=np.int64), np.asarray(dst_ids, dtype=np.int64)
+    if len(src_ids) == 0 or len(dst_ids) == 0:
+        return []
+    where = np.full(int(max(src_ids.max(), dst_ids.max())) + 2, -1, dtype=np.int64)
+    where[src_ids] = np.arange(len(src_ids))
+    p = where[dst_ids]                                   # source position of every wanted row, -1 = held elsewhere
+    k = np.nonzero(p >= 0)[0]
+    if len(k) == 0:
+        return []
+    brk = np.nonzero((np.diff(k) != 1) | (np.diff(p[k]) != 1))[0] + 1
+    starts = np.concatenate([[0], brk])
+    ends = np.concatenate([brk, [len(k)]])
+    return [(int(p[k[a]]), int(k[a]), int(b - a)) for a, b in zip(starts, ends)]
 
 
-def redistribute_rows(comm, src, src_ids, dst_ids, dst):
+_PLAN_CACHE = {}
+
+
+def redistribute_rows(comm, src, src_ids, dst_ids, dst, key=None):
     """Move rows between two layouts of the same global row set.  src / dst: 2-D tensors (local rows x cols, a row is
     contiguous); src_ids[r] / dst_ids[r]: the global row ids rank r holds / wants, in local order (the same lists on
-    every rank).  A global row may be wanted by several ranks (halos) but is held by exactly one."""
+    every rank).  A global row may be wanted by several ranks (halos) but is held by exactly one.  ``key``: caches the
+    message plan (the layouts of a mosaic shape do not change from step to step)."""
     me = comm.rank
-    sends, recvs = [], []
-    for j in range(comm.world):
-        for s0, _, ln in _runs(src_ids[me], dst_ids[j]):
-            sends.append((src[s0:s0 + ln], j))
-    for i in range(comm.world):
-        for _, d0, ln in _runs(src_ids[i], dst_ids[me]):
-            recvs.append((dst[d0:d0 + ln], i))
-    comm.p2p(sends, recvs)
+    plan = _PLAN_CACHE.get((key, me, comm.world)) if key is not None else None
+    if plan is None:
+        plan = ([(s0, ln, j) for j in range(comm.world) for s0, _, ln in _runs(src_ids[me], dst_ids[j])],
+                [(d0, ln, i) for i in range(comm.world) for _, d0, ln in _runs(src_ids[i], dst_ids[me])])
+        if key is not None:
+            _PLAN_CACHE[(key, me, comm.world)] = plan
+    comm.p2p([(src[s0:s0 + ln], j) for s0, ln, j in plan[0]], [(dst[d0:d0 + ln], i) for d0, ln, i in plan[1]])
     return dst
 
 
@@ -400,7 +401,7 @@ class Band:
             slab = self._dense(hi - lo, nx, _lib.F32)
         else:
             slab = self._dense(0, nx, _lib.F32)
-        redistribute_rows(comm, fabs.tensor(), shifted, slab_ids, slab.tensor()[:hi - lo])
+        redistribute_rows(comm, fabs.tensor(), shifted, slab_ids, slab.tensor()[:hi - lo], key=("fabs", ny, nx))
         x0 = mx + m + x_odd
         for (xa, xb) in ((0, qw), (x0, nx)):
             own = self._dense(s1 - s0, qw, _lib.U8)
@@ -425,7 +426,7 @@ class Band:
         loc = []
         for own in masks:
             mloc = self._dense(q1 - q0, qw, _lib.U8)
-            redistribute_rows(comm, own.tensor()[:s1 - s0], own_ids, need_ids, mloc.tensor()[:q1 - q0])
+            redistribute_rows(comm, own.tensor()[:s1 - s0], own_ids, need_ids, mloc.tensor()[:q1 - q0], key=("qmask", ny, nx))
             loc.append(mloc)
         mask = self._dense(nk, nx, _lib.U8)
         _lib.check(lib.hd_fourier_mask_assemble_rows(loc[0].ptr, loc[0].pitch, loc[1].ptr, loc[1].pitch, q0, q1 - q0,
@@ -542,3 +543,24 @@ class Band:
         _lib.check(_lib.load().hd_pdfill_status(ctypes.c_void_p(self._fill_work.data_ptr()), ctypes.byref(st),
                                                 dev.stream_ptr()))
         return st.value
+
+    # -- host API: one rank's rows in, one rank's rows out --------------------------------------------------------------
+    def apply_to_host(self, srtm_rows, groves_rows, hsheds_rows):
+        """The banded chain through host buffers: this rank's rows of the three input mosaics (ndarrays: float32,
+        uint8 / bool, float32; pinned memory is copied asynchronously) -> {"final" float64, "filled" float32, "d8" uint8}
+        ndarrays of the same rows.  What bench.py's e2e measures at N > 1."""
+        import torch
+        for a in (srtm_rows, groves_rows, hsheds_rows):
+            if not isinstance(a, np.ndarray):
+                from .exceptions import NumpyArrayExpectedError
+                raise NumpyArrayExpectedError(a)
+            if a.shape != (self.rows, self.nx):
+                raise ValueError(f"expected this rank's rows {(self.rows, self.nx)}, got {a.shape}")
+        cur = torch.cuda.current_stream()
+        srtm = dev.upload(np.ascontiguousarray(srtm_rows, dtype=np.float32))
+        g_ext, h_ext = self.alloc_ext(_lib.U8, np.uint8), self.alloc_ext(_lib.F32, np.float32)
+        g = np.ascontiguousarray(groves_rows)
+        dev.upload_into(g_ext.owned(), g.view(np.uint8) if g.dtype == np.bool_ else g.astype(np.uint8, copy=False), cur)
+        dev.upload_into(h_ext.owned(), np.ascontiguousarray(hsheds_rows, dtype=np.float32), cur)
+        out = self.conditioning_chain(srtm, g_ext, h_ext)
+        return {k: dev.download(out[k]) for k in ("final", "filled", "d8")}

@@ -59,6 +59,10 @@ SIGNATURES = {
     "hd_fft2_c2c": (_i, [_p, _p, _i, _i64, _p, _i64, _i, _p, _i64, _p]),
     "hd_fft_rows": (_i, [_p, _p, _i, _i64, _p, _i64, _i64, _i, _i, _p, _i64, _p]),
     "hd_fft_band_pass": (_i, [_p, _i, _i, _p, _i64, _i64, _p, _i64, _i, _i, _i, _p, _i64, _i64, _p, _i64, _p]),
+    "hd_fft_band_pass_scatter": (_i, [_p, _i, _i, _p, _i64, _i64, _p, _i64, _i, _i, _i, _p, _i64, _p, _i64, _p]),
+    "hd_ipc_export": (_i, [_p, _p, ctypes.POINTER(_i64)]),
+    "hd_ipc_import": (_i, [_p, ctypes.POINTER(_p)]),
+    "hd_ipc_close": (_i, [_p]),
     "hd_klayout_rows": (_i64, [_i64, _i64, _i64]),
     "hd_klayout_ky": (_i64, [_i64, _i64, _i64, _i64]),
     "hd_hermitian_complete": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p]),
@@ -72,12 +76,27 @@ SIGNATURES = {
     "hd_pdfill_finish_d8": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _p]),
     "hd_pdfill_status": (_i, [_p, ctypes.POINTER(_i), _p]),
     "hd_halo_min_flag": (_i, [_p, _p, _i64, _p, _p]),
+    "hd_fill_pool_band": (_i, [_p, _i64, _i64, _i64, _p, _p, _i64, _i, _p, _p]),
+    "hd_pdfill_coarse": (_i, [_p, _p, _i64, _i64, _i64, _p, _i64, _p]),
+    "hd_pdfill_band_start": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _i, _p, _i64, _i64, _p]),
     "hd_pdfill_finish": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_d8": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_binary_morph": (_i, [_p, _i, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _p]),
     "hd_max_filter": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
     "hd_convolve3": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, ctypes.POINTER(_d), _d, _i, _p, _i64, _p]),
 }
+
+
+
+class ScatterSeg(ctypes.Structure):
+    _fields_ = [("row0", _i64), ("row1", _i64), ("base", _p), ("pitch", _i64), ("dst_row0", _i64)]
+
+
+class Scatter(ctypes.Structure):
+    """hd_scatter of include/hydrodem_b200.h."""
+    _fields_ = [("nseg", ctypes.c_int32), ("ncolseg", ctypes.c_int32), ("seg", ScatterSeg * 16),
+                ("col_local0", _i64 * 2), ("col_dst0", _i64 * 2), ("col_len", _i64 * 2)]
+
 
 _lib = None
 

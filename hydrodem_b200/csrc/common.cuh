@@ -36,7 +36,8 @@ void hd_prof_begin(const char* name, cudaStream_t stream);
 int hd_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t ny, int64_t nx, int64_t pitch_elems,
                     int box_w, int box_h, bool nan_fill);
 
-int hd_num_sms();
+int hd_num_sms();          // SMs persistent grids are sized for (HD_SM_RESERVE leaves some to communication kernels)
+int hd_num_sms_total();
 size_t hd_dtype_size(int dtype);
 
 static inline int hd_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -966,6 +966,55 @@ __global__ void __launch_bounds__(256) transpose_real_kernel(const float* __rest
     }
 }
 
+
+// ---- transpose fused with the all-to-all: remote stores over NVLink --------------------------------------------------------
+// The sharded Fourier stage follows every row pass with "transpose, then send row range j of the result to rank j".
+// Here the transpose writes each element STRAIGHT INTO THE MEMORY OF THE RANK THAT OWNS IT (peer pointers obtained once
+// through CUDA IPC, hd_ipc_*): no send buffer, no NCCL call, no unpack copy -- the exchange is the transpose's own
+// stores, 256-byte row segments per warp.  hd_scatter describes where output row `orow` lives (which peer, which row
+// there) and at which column this rank's local rows land.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_scatter_kernel(const T* __restrict__ in, int64_t in_pitch, int rows, int cols,
+                                                                RowPerm pm, int keep_max, hd_scatter sc)
+{
+    __shared__ T tile[32][33];
+    const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    const int ntiles = tiles_c * tiles_r;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = r0 + ty + 8 * k, c = c0 + tx;
+            if (r < rows && c < cols) tile[ty + 8 * k][tx] = in[(int64_t)r * in_pitch + c];
+        }
+        __syncthreads();
+        // destination column of local row r (at most two segments: the K layout's lower / mirror rows)
+        const int r = r0 + tx;
+        int64_t ocol = -1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (q < sc.ncolseg && r >= sc.col_local0[q] && r < sc.col_local0[q] + sc.col_len[q])
+                ocol = sc.col_dst0[q] + (r - sc.col_local0[q]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + ty + 8 * k;
+            if (r < rows && c < cols && ocol >= 0) {
+                const int orow = unpermute(c, pm);
+                if (keep_max >= 0 && orow > keep_max) continue;
+                for (int q = 0; q < sc.nseg; ++q) {
+                    const hd_scatter_seg& sg = sc.seg[q];
+                    if (orow >= sg.row0 && orow < sg.row1) {
+                        reinterpret_cast<T*>(sg.base)[(orow - sg.row0 + sg.dst_row0) * sg.pitch + ocol] = tile[tx][ty + 8 * k];
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // cyclic shift without transpose (FourierShift / FourierIShift wrappers): out[(r+sr)%rows][(c+sc)%cols] = in[r][c]
 template <typename T>
 __global__ void __launch_bounds__(256) shift_kernel(const T* __restrict__ in, int64_t in_pitch, T* __restrict__ out,
@@ -1079,6 +1128,7 @@ int launch_rows(const Plan1D& p, const RowsArgs& a_in, int load, cudaStream_t s,
             cfg.numAttrs = 1;                                                                            \
             cfg.gridDim = dim3((unsigned)p.n1);                                                          \
             HD_CUDA_OK(cudaOccupancyMaxActiveClusters(&workers, kern, &cfg));   /* co-resident clusters */ \
+            workers = (int)((int64_t)workers * hd_num_sms() / hd_num_sms_total());                       \
         } else {                                                                                         \
             int per_sm = 1;                                                                              \
             HD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FNT, smem));          \
@@ -1338,6 +1388,40 @@ int hd_fft_band_pass(void* plan, int axis, int load, const void* in, int64_t in_
         transpose_kernel<float2, false><<<transpose_grid((int)nrows, n), 256, 0, s>>>(
             A, n, (float2*)out_t, out_t_pitch, nullptr, 0, (int)nrows, n, 0, 0, pm, keep_cols > 0 ? (int)keep_cols - 1 : -1, 0);
     }
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+
+// hd_fft_band_pass with the all-to-all fused into the transpose: the transposed result is scattered into peer memory as
+// described by `sc` (see transpose_scatter_kernel).  The caller synchronises the ranks around it (all peers done with the
+// destination buffers before, all writes landed after).
+int hd_fft_band_pass_scatter(void* plan, int axis, int load, const void* in, int64_t in_pitch, int64_t nrows, const void* mask,
+                             int64_t mask_pitch, int shift_cols, int inverse, int real_out, const hd_scatter* sc,
+                             int64_t keep_cols, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    if (!plan || !in || !sc || !workspace) return HD_ERR_NULL;
+    Plan2D* p = (Plan2D*)plan;
+    const Plan1D& pl = axis == 0 ? p->px : p->py;
+    const int n = pl.n_total;
+    if (nrows < 1 || nrows > 0x7fffffff || axis < 0 || axis > 1 || load < 0 || load > 3) return HD_ERR_ARG;
+    if (sc->nseg < 0 || sc->nseg > HD_SCATTER_MAX_SEGS || sc->ncolseg < 0 || sc->ncolseg > 2) return HD_ERR_ARG;
+    if (load == LOAD_MASKED_SHIFTED && !mask) return HD_ERR_NULL;
+    if (load == LOAD_C64_HPAIR && !real_out) return HD_ERR_ARG;
+    if (workspace_bytes < nrows * (int64_t)n * (int64_t)sizeof(float2)) return HD_ERR_WORKSPACE;
+    if (in_pitch < n) return HD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    float2* A = (float2*)workspace;
+    RowsArgs r{in, in_pitch, A, n, (const uint8_t*)mask, mask_pitch, (int)nrows, 0, shift_cols, inverse ? 1 : 0,
+               real_out ? 1 : 0, (int)nrows};
+    if (int e = launch_rows(pl, r, load, s)) return e;
+    const RowPerm pm = perm_of(pl, load);
+    hd_prof_begin("transpose_scatter_kernel", s);
+    if (real_out)
+        transpose_scatter_kernel<float><<<transpose_grid((int)nrows, n), 256, 0, s>>>((const float*)A, n, (int)nrows, n, pm, -1, *sc);
+    else
+        transpose_scatter_kernel<float2><<<transpose_grid((int)nrows, n), 256, 0, s>>>(A, n, (int)nrows, n, pm,
+                                                                                     keep_cols > 0 ? (int)keep_cols - 1 : -1, *sc);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
 }

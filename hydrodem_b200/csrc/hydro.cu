@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict_
                                                         int64_t w_pitch, int64_t ny, int64_t nx, int top_is_halo = 0,
                                                         int bottom_is_halo = 0, int* __restrict__ tile_has_nodata = nullptr,
                                                         int tiles_x = 0, int* __restrict__ any_nodata = nullptr,
-                                                        const float* __restrict__ wc = nullptr, int64_t c_pitch = 0)
+                                                        const float* __restrict__ wc = nullptr, int64_t c_pitch = 0,
+                                                        int64_t wc_y0 = 0)
 {
     const int64_t nxq = (nx + 3) / 4;                                            // four consecutive cells per thread
     for (CellIter it(nxq); it.y < ny; it.next()) {
@@ -52,7 +53,9 @@ __global__ void __launch_bounds__(256) fill_init_kernel(const float* __restrict_
         gload4(z + y * z_pitch + x0, x0, nx, v4);
         // interior cells start from the coarse-level fill of their block (an upper bound of the answer, see
         // fill_pool_kernel) instead of +inf; a quad never straddles two blocks (CB is a multiple of 4)
-        const float start = wc ? __ldg(wc + (y / CB) * c_pitch + x0 / CB) : __int_as_float(0x7f800000);
+        // (wc_y0: row of the coarse raster's frame of reference that local row 0 corresponds to -- a band of a mosaic
+        // looks up the GLOBAL coarse fill)
+        const float start = wc ? __ldg(wc + ((y + wc_y0) / CB) * c_pitch + x0 / CB) : __int_as_float(0x7f800000);
         const bool yframe = (y == 0 && !top_is_halo) || (y == ny - 1 && !bottom_is_halo);
         bool nodata = false;
 #pragma unroll
@@ -712,6 +715,7 @@ struct FillOpts {
     bool seed_all = false;        // every tile starts queued (fine level of the multigrid start)
     const float* wc = nullptr;    // coarse-level fill used as the starting W of interior cells
     int64_t c_pitch = 0;
+    int64_t wc_y0 = 0;            // local row 0 = row wc_y0 of the raster the coarse level was pooled from
     int* status = nullptr;        // sticky status word of the whole fill (root workspace + STATUS_OFF)
 };
 
@@ -755,7 +759,8 @@ static int pdfill_async(const void* z, int64_t z_pitch, void* w, int64_t w_pitch
     if (!(flags & 1) && !opt.preinit) {
         hd_prof_begin("fill_init_kernel", s);
         fill_init_kernel<<<stream_grid(ny * ((nx + 3) / 4)), 256, 0, s>>>((const float*)z, z_pitch, (float*)w, w_pitch, ny, nx, flags & 2,
-                                                             flags & 4, queued, tiles_x, &ctl->any_nodata, opt.wc, opt.c_pitch);
+                                                             flags & 4, queued, tiles_x, &ctl->any_nodata, opt.wc, opt.c_pitch,
+                                                             opt.wc_y0);
         HD_LAUNCH_CHECK(); hd_count_launch();
     }
     hd_prof_begin("fill_seed_kernel", s);
@@ -1022,4 +1027,114 @@ extern "C" int hd_halo_min_flag(void* w_halo, const void* received, int64_t nx, 
         (float*)w_halo, (const float*)received, nx, lowered);
     HD_LAUNCH_CHECK(); hd_count_launch();
     return HD_OK;
+}
+
+// ---- row-band fill with a GLOBAL multigrid start ---------------------------------------------------------------------
+// A band that starts from its own coarse levels solves the drainage structure with the cut rows closed: every later
+// round then has to carry corrections from the cut deep into the band, one dependent tile hop after the other (7 rounds
+// of ~2 ms on a 36000^2 mosaic over 8 GPUs).  Instead the ranks pool their bands (hd_fill_pool_band), all-gather the
+// coarse DEM (1/64 of the cells), every rank fills the WHOLE coarse mosaic (hd_pdfill_coarse: cheap, redundant) and each
+// band starts from that global upper bound (hd_pdfill_band_start): the rounds that follow only repair cells next to the
+// cuts.  The fixed point is unique, so the result is the same surface, bit for bit.
+
+// Block maxima + outlet marks of a band whose first row is a multiple of 8 in mosaic coordinates.  flags 2 / 4: the top /
+// bottom edge of the band is an interior cut, not mosaic frame.  zc, wc: (ceil(ny / 8) x ceil(nx / 8)), pitch c_pitch.
+extern "C" int hd_fill_pool_band(const void* z, int64_t z_pitch, int64_t ny, int64_t nx, void* zc, void* wc, int64_t c_pitch,
+                                 int flags, void* tile_flags_scratch, void* stream)
+{
+    if (!z || !zc || !wc || !tile_flags_scratch) return HD_ERR_NULL;
+    const int64_t nyc = hd_cdiv(ny, CB), nxc = hd_cdiv(nx, CB);
+    if (ny < 1 || nx < 1 || z_pitch < nx || c_pitch < nxc || (flags & ~6)) return HD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    hd_prof_begin("fill_pool_kernel", s);
+    fill_pool_kernel<<<stream_grid(nyc * nxc), 256, 0, s>>>((const float*)z, z_pitch, ny, nx, (float*)zc, (float*)wc, c_pitch, nyc,
+                                                            nxc, (int*)tile_flags_scratch, hd_cdiv(nxc, FT), nullptr, flags & 2,
+                                                            flags & 4);
+    HD_LAUNCH_CHECK(); hd_count_launch();
+    return HD_OK;
+}
+
+// Fill of a coarse DEM whose W already carries the outlet marks (finite = outlet at that level, +inf elsewhere), with
+// its own multigrid start.  Workspace: hd_pdfill_workspace_bytes(nyc, nxc).
+extern "C" int hd_pdfill_coarse(const void* zc, void* wc, int64_t c_pitch, int64_t nyc, int64_t nxc, void* workspace,
+                                int64_t workspace_bytes, void* stream)
+{
+    if (!zc || !wc || !workspace) return HD_ERR_NULL;
+    if (nyc < 1 || nxc < 1 || c_pitch < nxc) return HD_ERR_ARG;
+    if (workspace_bytes < hd_pdfill_workspace_bytes(nyc, nxc)) return HD_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    HD_CUDA_OK(cudaMemsetAsync((char*)workspace + STATUS_OFF, 0, sizeof(int), s));
+    int* status = (int*)((char*)workspace + STATUS_OFF);
+    struct Level { int64_t ny, nx, pitch; float* z; float* w; char* ctl; };
+    Level lv[MAX_LEVELS];
+    int nlev = 0;
+    char* cur = (char*)workspace + fill_level_bytes(nyc, nxc);
+    int64_t lny = nyc, lnx = nxc;
+    for (int l = 1; l < MAX_LEVELS; ++l) {
+        const int64_t ny2 = hd_cdiv(lny, CB), nx2 = hd_cdiv(lnx, CB);
+        if (!level_worth_it(ny2, nx2)) break;
+        Level& L = lv[nlev++];
+        L.ny = ny2; L.nx = nx2; L.pitch = coarse_pitch(nx2);
+        L.ctl = cur;
+        L.z = (float*)(cur + fill_level_bytes(ny2, nx2));
+        L.w = L.z + ny2 * L.pitch;
+        cur = (char*)(L.w + ny2 * L.pitch);
+        lny = ny2; lnx = nx2;
+    }
+    for (int l = 0; l < nlev; ++l) {                                  // downward: block maxima + outlet marks
+        const Level& L = lv[l];
+        const float* zin = l == 0 ? (const float*)zc : lv[l - 1].z;
+        const float* win = l == 0 ? (const float*)wc : lv[l - 1].w;
+        const int64_t pin = l == 0 ? c_pitch : lv[l - 1].pitch, iny = l == 0 ? nyc : lv[l - 1].ny, inx = l == 0 ? nxc : lv[l - 1].nx;
+        const int tiles_x_c = hd_cdiv(L.nx, FT), ntiles_c = tiles_x_c * hd_cdiv(L.ny, FT);
+        int* queued_c = (int*)(L.ctl + 256) + (ntiles_c + 8192);
+        HD_CUDA_OK(cudaMemsetAsync(queued_c, 0, (size_t)ntiles_c * sizeof(int), s));
+        hd_prof_begin("fill_pool_kernel", s);
+        fill_pool_kernel<<<stream_grid(L.ny * L.nx), 256, 0, s>>>(zin, pin, iny, inx, L.z, L.w, L.pitch, L.ny, L.nx, queued_c,
+                                                                  tiles_x_c, win, 0, 0);
+        HD_LAUNCH_CHECK(); hd_count_launch();
+    }
+    for (int l = nlev - 1; l >= 0; --l) {                              // upward
+        const Level& L = lv[l];
+        FillOpts o;
+        o.preinit = true;
+        o.status = status;
+        if (l < nlev - 1) {
+            hd_prof_begin("fill_refine_kernel", s);
+            fill_refine_kernel<<<stream_grid(L.ny * L.nx), 256, 0, s>>>(L.w, L.pitch, L.ny, L.nx, lv[l + 1].w, lv[l + 1].pitch);
+            HD_LAUNCH_CHECK(); hd_count_launch();
+            o.seed_all = true;
+        }
+        if (int e = pdfill_async(L.z, L.pitch, L.w, L.pitch, L.ny, L.nx, L.ctl, nullptr, s, 0, false, o)) return e;
+    }
+    FillOpts top;
+    top.preinit = true;
+    top.seed_all = true;
+    top.status = status;
+    if (nlev > 0) {
+        hd_prof_begin("fill_refine_kernel", s);
+        fill_refine_kernel<<<stream_grid(nyc * nxc), 256, 0, s>>>((float*)wc, c_pitch, nyc, nxc, lv[0].w, lv[0].pitch);
+        HD_LAUNCH_CHECK(); hd_count_launch();
+    }
+    return pdfill_async(zc, c_pitch, wc, c_pitch, nyc, nxc, workspace, nullptr, s, 0, false, top);
+}
+
+// First round of a band ([halo row | band | halo row], flags as hd_pdfill_band) from the filled GLOBAL coarse mosaic:
+// wc_global (pitch c_pitch) covers the whole mosaic, y_origin = mosaic row of the raster's row 0.
+extern "C" int hd_pdfill_band_start(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx,
+                                    void* workspace, int64_t workspace_bytes, int flags, const void* wc_global,
+                                    int64_t c_pitch, int64_t y_origin, void* stream)
+{
+    if (!z || !w || !workspace || !wc_global) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || z_pitch < nx || w_pitch < nx || (flags & ~6) || y_origin < 0) return HD_ERR_ARG;
+    if (workspace_bytes < hd_pdfill_workspace_bytes(ny, nx)) return HD_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    HD_CUDA_OK(cudaMemsetAsync((char*)workspace + STATUS_OFF, 0, sizeof(int), s));
+    FillOpts fine;
+    fine.status = (int*)((char*)workspace + STATUS_OFF);
+    fine.seed_all = true;
+    fine.wc = (const float*)wc_global;
+    fine.c_pitch = c_pitch;
+    fine.wc_y0 = y_origin;
+    return pdfill_async(z, z_pitch, w, w_pitch, ny, nx, workspace, nullptr, s, flags, false, fine);
 }

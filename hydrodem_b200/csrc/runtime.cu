@@ -71,6 +71,17 @@ size_t hd_dtype_size(int dtype)
     }
 }
 
+int hd_num_sms_total()
+{
+    static int total = 0;
+    if (total == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&total, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || total <= 0) total = 148;
+    }
+    return total;
+}
+
 int hd_num_sms()
 {
     static int sms = 0;
@@ -78,6 +89,12 @@ int hd_num_sms()
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 148;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        // HD_SM_RESERVE=k: persistent grids are sized for (SMs - k), leaving k SMs to the communication kernels that run
+        // beside them in the row-band sharded chain (NCCL send / recv cannot start while every SM is full)
+        if (const char* e = getenv("HD_SM_RESERVE")) {
+            const int k = atoi(e);
+            if (k > 0 && k < sms) sms -= k;
+        }
     }
     return sms;
 }
@@ -310,6 +327,51 @@ int hd_host_widen_i16(void* dst, int dst_dtype, const int16_t* src, int64_t n, i
             for (; i < b; ++i) d[i] = (double)src[i];
         });
     }
+    return HD_OK;
+}
+
+// ---- peer memory (row-band sharded chain: the transposes store straight into the other ranks' buffers) ---------------
+// One process per GPU: a rank exports the allocation that holds its exchange buffers (CUDA IPC), the others open it
+// once and keep the mapping.  handle64: 64 bytes (cudaIpcMemHandle_t); *offset = byte offset of ptr inside its
+// allocation (the opened mapping starts at the allocation's base).
+int hd_ipc_export(const void* ptr, void* handle64, int64_t* offset)
+{
+    if (!ptr || !handle64 || !offset) return HD_ERR_NULL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    HD_CUDA_OK(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    typedef CUresult (*PFN_range)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static PFN_range fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &q, cudaEnableDefault, &qr) != cudaSuccess || !q) {
+            hd_set_last_cuda_error((int)cudaErrorNotSupported);
+            return HD_ERR_CUDA;
+        }
+        fn = (PFN_range)q;
+    }
+    if (fn(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS) { hd_set_last_cuda_error((int)cudaErrorInvalidValue); return HD_ERR_CUDA; }
+    memcpy(handle64, &h, 64);
+    *offset = (int64_t)((CUdeviceptr)ptr - base);
+    return HD_OK;
+}
+
+int hd_ipc_import(const void* handle64, void** base)
+{
+    if (!handle64 || !base) return HD_ERR_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    HD_CUDA_OK(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess));
+    return HD_OK;
+}
+
+int hd_ipc_close(void* base)
+{
+    if (!base) return HD_OK;
+    HD_CUDA_OK(cudaIpcCloseMemHandle(base));
     return HD_OK;
 }
 

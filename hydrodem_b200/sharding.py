@@ -36,6 +36,33 @@ MASK_HALO = 2 * 27 + 1 + 6     # MaskFourier: two hollow-mean passes (27 each), 
 LOAD_REAL, LOAD_C64, LOAD_MASKED, LOAD_HPAIR = 0, 1, 2, 3
 
 
+class _Trace:
+    """HD_BAND_TRACE=1: per-phase host and device times of the banded chain (tools/band_phases.py prints them)."""
+
+    def __init__(self):
+        import os
+        self.on = bool(os.environ.get("HD_BAND_TRACE"))
+        self.marks = []
+
+    def mark(self, name):
+        if self.on:
+            import time
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, time.perf_counter(), ev))
+
+    def report(self):
+        torch.cuda.synchronize()
+        out = []
+        for (n0, t0, e0), (n1, t1, e1) in zip(self.marks, self.marks[1:]):
+            out.append((n1, (t1 - t0) * 1e3, e0.elapsed_time(e1)))
+        self.marks = []
+        return out
+
+
+TRACE = _Trace()
+
+
 def band_bounds(n, world, align=1):
     """Row range [r0, r1) of every rank; starts are multiples of ``align``; sizes differ by at most ``align``."""
     n, world, align = int(n), int(world), int(align)
@@ -60,9 +87,18 @@ class DistComm:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def p2p(self, sends, recvs):
+    class _Handle:
+        def __init__(self, works):
+            self.works = works
+
+        def wait(self):
+            for w in self.works:
+                w.wait()                        # NCCL: the current stream waits for the transfer, the host does not
+
+    def p2p_async(self, sends, recvs):
         """sends: [(contiguous tensor, dst rank)], recvs: [(contiguous tensor, src rank)].  Messages between one pair of
-        ranks are matched in posting order.  One grouped batch: NCCL fuses it into a single kernel over NVLink."""
+        ranks are matched in posting order.  One grouped batch: NCCL fuses it into a single kernel over NVLink, on its
+        own stream -- kernels launched before ``wait()`` overlap the transfer."""
         dist = self.dist
         local = [t for t, d in sends if d == self.rank]
         ops = []
@@ -74,13 +110,28 @@ class DistComm:
         for t, d in sends:
             if d != self.rank:
                 ops.append(dist.P2POp(dist.isend, t, d, self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        return self._Handle(dist.batch_isend_irecv(ops) if ops else [])
+
+    def p2p(self, sends, recvs):
+        self.p2p_async(sends, recvs).wait()
 
     def allreduce_max_(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t
+
+    same_process = False
+
+    def gather_objects(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def device_barrier(self):
+        """Stream-ordered barrier: kernels launched after it start only when every rank's earlier kernels are done."""
+        if not hasattr(self, "_bar"):
+            self._bar = torch.zeros(1, dtype=torch.int32,
+                                    device="cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu")
+        self.dist.all_reduce(self._bar, group=self.group)
 
 
 class ThreadComm:
@@ -111,6 +162,29 @@ class ThreadComm:
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         sh.barrier.wait()
+
+    class _Done:
+        def wait(self):
+            pass
+
+    same_process = True
+
+    def gather_objects(self, obj):
+        sh = self.shared
+        sh.vals[self.rank] = obj
+        sh.barrier.wait()
+        out = list(sh.vals)
+        sh.barrier.wait()
+        return out
+
+    def device_barrier(self):
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.shared.barrier.wait()
+
+    def p2p_async(self, sends, recvs):
+        self.p2p(sends, recvs)
+        return self._Done()
 
     def allreduce_max_(self, t):
         sh = self.shared
@@ -190,6 +264,67 @@ def _cview(t):
     return torch.view_as_real(t) if t.is_complex() else t
 
 
+# ---- peer memory: persistent exchange buffers every rank can store into ---------------------------------------------------
+class PeerBuffers:
+    """Named device buffers of this rank, living in ONE allocation that the other ranks have mapped (CUDA IPC; ranks that
+    are threads of one process simply share the pointers).  ``ptr(rank, name)`` is valid in this process's kernels."""
+
+    def __init__(self, comm, sizes):
+        lib = _lib.load()
+        self.comm = comm
+        self.offsets, total = {}, 0
+        for name, nbytes in sizes.items():
+            self.offsets[name] = total
+            total += (int(nbytes) + 255) // 256 * 256
+        self.arena = torch.empty(max(total, 256), dtype=torch.uint8, device=dev.device())
+        base = self.arena.data_ptr()
+        self.ok = True
+        if comm.same_process:
+            infos = comm.gather_objects((base, self.offsets))
+            self.bases = [b for b, _ in infos]
+        else:
+            # every rank runs the same sequence of collectives whatever fails locally; `ok` is agreed on at the end
+            handle = ctypes.create_string_buffer(64)
+            off = ctypes.c_int64(0)
+            mine = None
+            if lib.hd_ipc_export(ctypes.c_void_p(base), handle, ctypes.byref(off)) == _lib.HD_OK:
+                mine = (handle.raw, off.value, self.offsets)
+            infos = comm.gather_objects(mine if mine is not None else (None, 0, self.offsets))
+            self.bases, self._opened = [], []
+            good = mine is not None and all(i[0] is not None for i in infos)
+            for j, (raw, off_j, _) in enumerate(infos):
+                if j == comm.rank or not good:
+                    self.bases.append(base)
+                    continue
+                p = ctypes.c_void_p()
+                if lib.hd_ipc_import(ctypes.create_string_buffer(raw, 64), ctypes.byref(p)) != _lib.HD_OK:
+                    good = False
+                    self.bases.append(base)
+                    continue
+                self._opened.append(p)
+                self.bases.append(p.value + off_j)
+            self.ok = all(comm.gather_objects(bool(good)))
+        self.peer_offsets = [info[-1] for info in infos]
+
+    def ptr(self, rank, name):
+        return self.bases[rank] + self.peer_offsets[rank][name]
+
+    def view(self, name, rows, cols, dtype):
+        """This rank's buffer ``name`` as a dense DeviceRaster."""
+        tdt = {_lib.C64: torch.complex64, _lib.F32: torch.float32, _lib.U8: torch.uint8}[dtype]
+        n = int(rows) * int(cols) * torch.empty(0, dtype=tdt).element_size()
+        o = self.offsets[name]
+        t = self.arena[o:o + max(n, 0)].view(tdt).view(int(rows), int(cols)) if rows and cols else \
+            torch.empty((1, int(cols)), dtype=tdt, device=self.arena.device)
+        return dev.DeviceRaster(t, rows, cols, dtype)
+
+    def close(self):
+        lib = _lib.load()
+        for p in getattr(self, "_opened", []):
+            lib.hd_ipc_close(p)
+        self._opened = []
+
+
 # ---- one rank's view of the mosaic --------------------------------------------------------------------------------------
 class ExtRaster:
     """A band with its halo margins: ``raster`` has up + rows + down rows; rows [up, up + rows) are owned."""
@@ -213,11 +348,17 @@ class Band:
 
     def __init__(self, comm, ny, nx, halo=HALO):
         self.comm, self.ny, self.nx, self.halo = comm, int(ny), int(nx), int(halo)
-        self.bounds = band_bounds(ny, comm.world, 2)
+        # band starts are multiples of 8: even (two rows share one transform on the device) and aligned with the 8x8 blocks
+        # of the sink-fill's coarse level (a block never straddles a cut)
+        self.bounds = band_bounds(ny, comm.world, 8)
         self.r0, self.r1 = self.bounds[comm.rank]
         if comm.world > 1 and min(b - a for a, b in self.bounds) < self.halo:
             # the same test on every rank (it only depends on ny and world): nobody enters a collective alone
             raise ValueError(f"{ny} rows over {comm.world} ranks leave bands thinner than the {self.halo}-row halo")
+        import os
+        self.fill_overlap = max(8, int(os.environ.get("HD_FILL_OVERLAP", "64")) // 8 * 8)
+        if comm.world > 1 and min(b - a for a, b in self.bounds) < 2 * self.fill_overlap:
+            self.fill_overlap = max(8, min(b - a for a, b in self.bounds) // 16 * 8)
         self.up = self.halo if comm.rank > 0 else 0
         self.down = self.halo if comm.rank < comm.world - 1 else 0
         self.fill_rounds = None
@@ -281,32 +422,95 @@ class Band:
                                         int(inverse), int(real_out), out_t.ptr, out_t.pitch, int(keep_cols),
                                         ctypes.c_void_p(work.data_ptr()), nbytes, dev.stream_ptr()))
 
-    def _transpose_exchange(self, t, send_bounds, recv_cols, out):
-        """t: (N x my_len) local transposed block.  Rows [a, b) of it go to the rank that owns [a, b) (send_bounds);
-        what arrives from rank i is an (mine x len_i) block that lands in columns recv_cols[i] of ``out``
-        (recv_cols[i] = list of (col0, col1) ranges, in the order of rank i's local rows)."""
-        comm = self.comm
-        tt = t.tensor()
-        mine = out.ny
-        sends = [(_cview(tt[a:b]), j) for j, (a, b) in enumerate(send_bounds) if b > a and tt.shape[1] > 0]
-        bufs, recvs = [], []
-        for i in range(comm.world):
-            width = sum(c1 - c0 for c0, c1 in recv_cols[i])
-            if width == 0 or mine == 0:
-                bufs.append(None)
-                continue
-            b = torch.empty((mine, width), dtype=tt.dtype, device=tt.device)
-            bufs.append(b)
-            recvs.append((_cview(b), i))
-        comm.p2p(sends, recvs)
+    def _peer_setup(self, KL, CB, XB):
+        """Persistent exchange buffers of the Fourier stage in peer-mapped memory (once per Band).  None: the ranks could
+        not map each other's memory (or HD_BAND_DIRECT=0) -- the exchanges then go through NCCL send / recv."""
+        if not hasattr(self, "_peers"):
+            import os
+            self._peers = None
+            if self.comm.world > 1 and os.environ.get("HD_BAND_DIRECT", "1") != "0":
+                lib = _lib.load()
+                me = self.comm.rank
+                kl = KL[me]
+                pitch = int(lib.hd_pitch_elems(self.nx, _lib.F32))
+                sizes = {"at": (CB[me][1] - CB[me][0]) * self.ny * 8, "half": kl["rows"] * (self.nx // 2 + 1) * 8,
+                         "bt": (XB[me][1] - XB[me][0]) * self.ny * 8, "dem": (self.up + self.rows + self.down) * pitch * 4}
+                peers = PeerBuffers(self.comm, sizes)
+                if peers.ok:
+                    peers.dem_pitch = self.comm.gather_objects((pitch, self.up))
+                    self._peers = peers
+        return self._peers
+
+    def _pass_scatter(self, plan, axis, load, src, nrows, segs, colsegs, keep_cols=0, mask=None, shift_cols=0, inverse=0,
+                      real_out=0):
+        """Row pass + transpose whose stores go straight into the owning ranks' buffers (hd_fft_band_pass_scatter).
+        segs: [(row0, row1, device pointer, pitch in elements, dst_row0)]; colsegs: [(local row0, column0, length)]."""
+        lib = _lib.load()
+        n = self.nx if axis == 0 else self.ny
+        sc = _lib.Scatter()
+        segs = [g for g in segs if g[1] > g[0]]
+        sc.nseg, sc.ncolseg = len(segs), len(colsegs)
+        for k, (a, b, ptr, pitch, d0) in enumerate(segs):
+            sc.seg[k].row0, sc.seg[k].row1, sc.seg[k].base, sc.seg[k].pitch, sc.seg[k].dst_row0 = a, b, ptr, pitch, d0
+        for k, (l0, c0, ln) in enumerate(colsegs):
+            sc.col_local0[k], sc.col_dst0[k], sc.col_len[k] = l0, c0, ln
+        if nrows < 1:
+            return
+        nbytes = int(nrows) * n * 8
+        work = dev.scratch(nbytes)
+        mp, mpitch = (mask.ptr, mask.pitch) if mask is not None else (None, 0)
+        _lib.check(lib.hd_fft_band_pass_scatter(plan, axis, load, src.ptr, src.pitch, int(nrows), mp, mpitch, int(shift_cols),
+                                                int(inverse), int(real_out), ctypes.byref(sc), int(keep_cols),
+                                                ctypes.c_void_p(work.data_ptr()), nbytes, dev.stream_ptr()))
+
+    def _pass_exchange(self, plan, axis, load, src, counts, n_out, ranges, segs, out, dtype, mask=None, **kw):
+        """(Fallback when the ranks cannot map each other's memory.)  A row pass of the sharded Fourier stage followed by its all-to-all, software pipelined: the local rows are
+        transformed in a few chunks, the transposed block of chunk c (n_out x chunk rows) is on its way (NCCL's stream)
+        while chunk c + 1 is being transformed, and the blocks that arrive are put in place one chunk behind.
+          counts[i]  rows rank i transforms in this pass          ranges[j]  row ranges of the transposed block rank j gets
+          segs[i]    [(local row0, output column0, length)]: where rank i's local rows land along the columns of ``out``
+        ``out`` rows = the concatenation of ranges[me]."""
+        comm, W, me = self.comm, self.comm.world, self.comm.rank
+        nch = 1          # (chunked pipelining did not overlap: NCCL's send / recv kernels wait behind the persistent grids)
+        chunks = [band_bounds(c, nch, 2) for c in counts]
+        tdt = {_lib.C64: torch.complex64, _lib.F32: torch.float32}[dtype]
+        pending = []
         to = out.tensor()
-        for i, b in enumerate(bufs):
-            if b is None:
-                continue
-            k = 0
-            for c0, c1 in recv_cols[i]:
-                to[:, c0:c1].copy_(b[:, k:k + (c1 - c0)])
-                k += c1 - c0
+
+        def place(item):
+            handle, places, _keep = item
+            handle.wait()
+            for buf, off, i, ia, ib in places:
+                for l0, c0, ln in segs[i]:
+                    lo, hi = max(ia, l0), min(ib, l0 + ln)
+                    if hi > lo:
+                        to[off:off + buf.shape[0], c0 + (lo - l0):c0 + (hi - l0)].copy_(buf[:, lo - ia:hi - ia])
+
+        for c in range(nch):
+            ra, rb = chunks[me][c]
+            t, sends = None, []
+            if rb > ra:
+                t = self._dense(n_out, rb - ra, dtype)
+                self._pass(plan, axis, load, src.sub(ra, rb, 0, src.nx), rb - ra, t,
+                           mask=mask.sub(ra, rb, 0, mask.nx) if mask is not None else None, **kw)
+                tt = t.tensor()
+                for j in range(W):
+                    sends += [(_cview(tt[a:b]), j) for a, b in ranges[j] if b > a]
+            recvs, places = [], []
+            for i in range(W):
+                ia, ib = chunks[i][c]
+                off = 0
+                for a, b in ranges[me]:
+                    if b > a and ib > ia:
+                        buf = torch.empty((b - a, ib - ia), dtype=tdt, device=to.device)
+                        recvs.append((_cview(buf), i))
+                        places.append((buf, off, i, ia, ib))
+                    off += b - a
+            pending.append((comm.p2p_async(sends, recvs), places, t))
+            if len(pending) > 1:
+                place(pending.pop(0))
+        while pending:
+            place(pending.pop(0))
         return out
 
     def _k_layouts(self):
@@ -340,41 +544,42 @@ class Band:
         rows = self.rows
         src = dev.convert(srtm, _lib.F32)
 
-        # forward, along x: two real rows per transform, half spectrum kept; transposed block (nh x rows)
-        t1 = self._dense(nh, rows, _lib.C64)
-        self._pass(plan, 0, LOAD_REAL, src, rows, t1, keep_cols=nh)
+        TRACE.mark("daf:start")
+        counts_rows = [b - a for a, b in RB]
+        counts_cb = [b - a for a, b in CB]
+        counts_xb = [b - a for a, b in XB]
         c0, c1 = CB[me]
-        at = self._dense(c1 - c0, ny, _lib.C64)                     # my columns of the half spectrum, all y
-        self._transpose_exchange(t1, CB, [[RB[i]] for i in range(W)], at)
-        del t1
-        # forward, along y; transposed block (ny x my columns), natural ky order
-        t2 = self._dense(ny, c1 - c0, _lib.C64)
-        self._pass(plan, 1, LOAD_C64, at, c1 - c0, t2)
+        # forward along x (two real rows per transform, half spectrum kept) + all-to-all: my columns of the half
+        # spectrum, all y
+        peers = self._peer_setup(KL, CB, XB)
+        if peers is not None:
+            # the transposes store straight into the owning rank's buffers over NVLink (no NCCL, no unpack copies);
+            # device-side barriers say "destinations free" / "all stores landed"
+            comm.device_barrier()
+            at = peers.view("at", c1 - c0, ny, _lib.C64)
+            self._pass_scatter(plan, 0, LOAD_REAL, src, rows, [(CB[j][0], CB[j][1], peers.ptr(j, "at"), ny, 0) for j in range(W)],
+                               [(0, RB[me][0], rows)], keep_cols=nh)
+            comm.device_barrier()
+            TRACE.mark("F1 rows + T1")
+            half = peers.view("half", kl["rows"], nh, _lib.C64)
+            segs2 = []
+            for j, k in enumerate(KL):
+                segs2.append((k["a"], k["b"], peers.ptr(j, "half"), nh, 0))
+                segs2.append((k["hlo"], k["hlo"] + k["nhi"], peers.ptr(j, "half"), nh, k["nlo"]))
+            self._pass_scatter(plan, 1, LOAD_C64, at, c1 - c0, segs2, [(0, c0, c1 - c0)])
+            comm.device_barrier()
+        else:
+            at = self._dense(c1 - c0, ny, _lib.C64)
+            self._pass_exchange(plan, 0, LOAD_REAL, src, counts_rows, nh, [[cb] for cb in CB],
+                                [[(0, RB[i][0], counts_rows[i])] for i in range(W)], at, _lib.C64, keep_cols=nh)
+            TRACE.mark("F1 rows + T1")
+            # forward along y + exchange into the K layout: rank i gets rows ky in [a_i, b_i) and their mirrors
+            half = self._dense(kl["rows"], nh, _lib.C64)
+            self._pass_exchange(plan, 1, LOAD_C64, at, counts_cb, ny,
+                                [[(k["a"], k["b"]), (k["hlo"], k["hlo"] + k["nhi"])] for k in KL],
+                                [[(0, CB[i][0], counts_cb[i])] for i in range(W)], half, _lib.C64)
         del at
-        # to the K layout: rank i gets rows ky in [a_i, b_i) and their mirrors
-        half = self._dense(kl["rows"], nh, _lib.C64)
-        tt, ht = t2.tensor(), half.tensor()
-        sends, recvs, bufs = [], [], []
-        for i, k in enumerate(KL):
-            if c1 > c0:
-                sends.append((_cview(tt[k["a"]:k["b"]].contiguous()), i))
-                if k["nhi"]:
-                    sends.append((_cview(tt[k["hlo"]:k["hlo"] + k["nhi"]].contiguous()), i))
-        for j, (d0, d1) in enumerate(CB):
-            if d1 > d0:
-                lo = torch.empty((kl["nlo"], d1 - d0), dtype=torch.complex64, device=ht.device)
-                recvs.append((_cview(lo), j))
-                hi = None
-                if kl["nhi"]:
-                    hi = torch.empty((kl["nhi"], d1 - d0), dtype=torch.complex64, device=ht.device)
-                    recvs.append((_cview(hi), j))
-                bufs.append((d0, d1, lo, hi))
-        comm.p2p(sends, recvs)
-        for d0, d1, lo, hi in bufs:
-            ht[:kl["nlo"], d0:d1].copy_(lo)
-            if hi is not None:
-                ht[kl["nlo"]:, d0:d1].copy_(hi)
-        del t2, bufs
+        TRACE.mark("F2 cols + T2")
         # conjugate half, column shift, |F|  (FourierInitial, custom_filters.py:859-877)
         nk = kl["rows"]
         fshift = self._dense(nk, nx, _lib.C64)
@@ -382,6 +587,7 @@ class Band:
         _lib.check(lib.hd_hermitian_complete(half.ptr, half.pitch, fshift.ptr, fshift.pitch, fabs.ptr, fabs.pitch, kl["a"],
                                              kl["b"], ny, nx, dev.stream_ptr()))
         del half
+        TRACE.mark("hermitian complete")
 
         # ---- peak detector on row slabs of the two upper quarters (FourierProcessQuarters, :880-1050) -------------
         my, y_odd, mx, x_odd = ny // 2, ny & 1, nx // 2, nx & 1
@@ -389,19 +595,25 @@ class Band:
         qh, qw = my - m, mx - m
         cf.check_window((qh, qw), cf.BLANKS_WINDOW)
         shifted = [(k["ky"] + ny // 2) % ny for k in KL]            # shifted row id of every local K row, per rank
-        SL = band_bounds(qh, W, 1)
-        if min(b - a for a, b in SL) < 16:                           # tiny quarters: one rank runs the detector
-            SL = [(0, qh)] + [(qh, qh)] * (W - 1)
+        # a rank's slab = the quarter rows it already owns (its mirror rows are a contiguous range of the upper half):
+        # only the 61 rows of context on either side have to travel
+        SL = []
+        for sh in shifted:
+            q = np.sort(sh[sh < qh])
+            SL.append((int(q[0]), int(q[-1]) + 1) if len(q) and q[-1] - q[0] + 1 == len(q) else None)
+        if any(x is None for x in SL) or sorted(SL) != sorted(set(SL)) or sum(b - a for a, b in SL) != qh \
+                or min(b - a for a, b in SL) < 16:
+            SL = band_bounds(qh, W, 1)
+            if min(b - a for a, b in SL) < 16:                       # tiny quarters: one rank runs the detector
+                SL = [(0, qh)] + [(qh, qh)] * (W - 1)
         ctx = [(max(0, a - MASK_HALO), min(qh, b + MASK_HALO)) if b > a else (0, 0) for a, b in SL]
         slab_ids = [np.arange(lo, hi) for lo, hi in ctx]
         s0, s1 = SL[me]
         lo, hi = ctx[me]
         masks = []
-        if hi > lo:
-            slab = self._dense(hi - lo, nx, _lib.F32)
-        else:
-            slab = self._dense(0, nx, _lib.F32)
+        slab = self._dense(hi - lo, nx, _lib.F32)
         redistribute_rows(comm, fabs.tensor(), shifted, slab_ids, slab.tensor()[:hi - lo], key=("fabs", ny, nx))
+        TRACE.mark("fabs to slabs")
         x0 = mx + m + x_odd
         for (xa, xb) in ((0, qw), (x0, nx)):
             own = self._dense(s1 - s0, qw, _lib.U8)
@@ -412,6 +624,7 @@ class Band:
                 own.tensor().copy_(mk.tensor()[s0 - lo:s1 - lo])
             masks.append(own)
         del slab
+        TRACE.mark("peak detector")
         # the quarter-mask rows each rank's K rows look at (point mirror for the lower half, :1002-1027)
         need = []
         for sh in shifted:
@@ -433,26 +646,43 @@ class Band:
                                                      mask.ptr, mask.pitch, nk, kl["a"], kl["b"], ny, nx, m,
                                                      dev.stream_ptr()))
         self._last_mask = (mask, kl)
+        TRACE.mark("mask back + assemble")
 
-        # ---- inverse, along x: (1 - mask) * F on this rank's spectrum rows; the Hermitian (odd x odd) path needs only
-        # ky <= ny/2.  Transposed block (nx x rows) ---------------------------------------------------------------
-        n_i1 = kl["nlo"] if odd else nk
-        t3 = self._dense(nx, n_i1, _lib.C64)
-        self._pass(plan, 0, LOAD_MASKED, fshift, n_i1, t3, mask=mask, shift_cols=nx // 2, inverse=1)
-        del fshift
+        # ---- inverse along x: (1 - mask) * F on this rank's spectrum rows (the Hermitian, odd x odd, path needs only
+        # ky <= ny/2) + all-to-all: my x columns, all ky -------------------------------------------------------------
+        counts_i1 = [(k["nlo"] if odd else k["rows"]) for k in KL]
         xa, xb = XB[me]
-        bt = self._dense(xb - xa, ny, _lib.C64)
-        cols = [[(k["a"], k["b"])] + ([(k["hlo"], k["hlo"] + k["nhi"])] if (not odd and k["nhi"]) else []) for k in KL]
-        self._transpose_exchange(t3, XB, cols, bt)
-        del t3
+        segs = [[(0, k["a"], k["nlo"])] + ([(k["nlo"], k["hlo"], k["nhi"])] if (not odd and k["nhi"]) else []) for k in KL]
+        if peers is not None:
+            bt = peers.view("bt", xb - xa, ny, _lib.C64)
+            self._pass_scatter(plan, 0, LOAD_MASKED, fshift, counts_i1[me],
+                               [(XB[j][0], XB[j][1], peers.ptr(j, "bt"), ny, 0) for j in range(W)], segs[me], mask=mask,
+                               shift_cols=nx // 2, inverse=1)
+            comm.device_barrier()
+        else:
+            bt = self._dense(xb - xa, ny, _lib.C64)
+            self._pass_exchange(plan, 0, LOAD_MASKED, fshift, counts_i1, nx, [[x] for x in XB], segs, bt, _lib.C64, mask=mask,
+                                shift_cols=nx // 2, inverse=1)
+        del fshift
+        TRACE.mark("I1 rows + T3")
         if odd:
             _lib.check(lib.hd_conj_mirror_fill(bt.ptr, bt.pitch, xb - xa, ny, dev.stream_ptr()))
-        # inverse, along y: real output (two columns per transform on the Hermitian path); transposed block (ny x my x)
-        t4 = self._dense(ny, xb - xa, _lib.F32)
-        self._pass(plan, 1, LOAD_HPAIR if odd else LOAD_C64, bt, xb - xa, t4, inverse=1, real_out=1)
+        # inverse along y: real output (two columns per transform on the Hermitian path) + all-to-all: my rows, all x
+        if peers is not None:
+            pitch, _ = peers.dem_pitch[me]
+            dbuf = peers.arena[peers.offsets["dem"]:peers.offsets["dem"] + (self.up + rows + self.down) * pitch * 4]
+            out_ext = ExtRaster(dev.DeviceRaster(dbuf.view(torch.float32).view(self.up + rows + self.down, pitch),
+                                                 self.up + rows + self.down, nx, _lib.F32, np.float64), self.up, rows, self.down)
+            self._pass_scatter(plan, 1, LOAD_HPAIR if odd else LOAD_C64, bt, xb - xa,
+                               [(RB[j][0], RB[j][1], peers.ptr(j, "dem") + peers.dem_pitch[j][1] * peers.dem_pitch[j][0] * 4,
+                                 peers.dem_pitch[j][0], 0) for j in range(W)], [(0, xa, xb - xa)], inverse=1, real_out=1)
+            comm.device_barrier()
+        else:
+            out_ext = out_ext or self.alloc_ext(_lib.F32, np.float64)
+            self._pass_exchange(plan, 1, LOAD_HPAIR if odd else LOAD_C64, bt, counts_xb, ny, [[rb] for rb in RB],
+                                [[(0, XB[i][0], counts_xb[i])] for i in range(W)], out_ext.owned(), _lib.F32, inverse=1, real_out=1)
         del bt
-        out_ext = out_ext or self.alloc_ext(_lib.F32, np.float64)
-        self._transpose_exchange(t4, RB, [[XB[i]] for i in range(W)], out_ext.owned())
+        TRACE.mark("I2 cols + T4")
         return out_ext
 
     # -- the whole chain on row bands (BASELINE.json configs[4]: one mosaic over the GPUs of a box) --------------------
@@ -463,21 +693,27 @@ class Band:
         one of them bit-identical to the single-GPU ConditioningChain on the whole mosaic."""
         from .pipeline import ConditioningChain
         chain = ConditioningChain(groves_iterations=groves_iterations, with_hydrology=False)
+        TRACE.mark("chain:start")
         g_ext = groves_class if isinstance(groves_class, ExtRaster) else self.extended(dev.convert(groves_class, _lib.U8))
         h_ext = hsheds if isinstance(hsheds, ExtRaster) else self.extended(hsheds)
         if isinstance(g_ext, ExtRaster) and groves_class is g_ext:
             self.exchange_halo(g_ext)
         if isinstance(h_ext, ExtRaster) and hsheds is h_ext:
             self.exchange_halo(h_ext)
+        TRACE.mark("input halos")
         dem = self.detect_apply_fourier(srtm)                                        # image_srtm.py:125-126
         self.exchange_halo(dem)
+        TRACE.mark("dem halo")
         st = {"fourier": dem.raster}
         chain._stage_groves(st, g_ext.raster)                                        # image_srtm.py:177-199
+        TRACE.mark("groves")
         chain._stage_combine(st, h_ext.raster, None)                                 # LagoonsDetection ... :149
+        TRACE.mark("lagoons + combine")
         own = lambda r: r.sub(self.up, self.up + self.rows, 0, self.nx)              # noqa: E731
         out = {"final": own(st["final"]), "dem_complete": own(st["dem_complete"])}
         if with_hydrology:
             out["filled"], out["d8"] = self.sinkfill(ExtRaster(st["final32"], self.up, self.rows, self.down))
+            TRACE.mark("sink-fill + D8")
         return out
 
     # -- sink-fill + D8 -----------------------------------------------------------------------------------------------------
@@ -486,12 +722,18 @@ class Band:
         of the band's rows, or an ExtRaster whose owned rows hold them (its margin rows are overwritten)."""
         lib = _lib.load()
         comm = self.comm
-        if not isinstance(z, ExtRaster):
-            ext = self.alloc_ext(_lib.F32, np.float32)
-            ext.owned().tensor().copy_(dev.convert(z, _lib.F32).tensor())
-            z = ext
-        self.exchange_halo(z, 1)
-        zv, n_up, n_down = z.with_halo(1)
+        # The bands OVERLAP by FILL_OVERLAP rows on either side of a cut (an alternating Schwarz iteration converges in far
+        # fewer rounds with overlap: a drainage path has to wander that many rows across a cut before it costs another
+        # round).  The outermost row of the extended band is the boundary row received from the neighbour; the rows in
+        # between are relaxed by both ranks and agree at the fixed point.
+        ov = self.fill_overlap if comm.world > 1 else 1
+        src = z.owned() if isinstance(z, ExtRaster) else dev.convert(z, _lib.F32)
+        up, down = (ov if comm.rank > 0 else 0), (ov if comm.rank < comm.world - 1 else 0)
+        zx = ExtRaster(dev.empty(up + self.rows + down, self.nx, _lib.F32, np.float32), up, self.rows, down)
+        zx.owned().tensor().copy_(src.tensor())
+        z = zx
+        self.exchange_halo(z, ov)
+        zv, n_up, n_down = z.with_halo(ov)
         rows, nx = self.rows, self.nx
         w = dev.empty(zv.ny, nx, _lib.F32, np.float32)
         d8 = dev.empty(zv.ny, nx, _lib.U8, np.uint8)
@@ -504,19 +746,46 @@ class Band:
         recv_up = torch.empty(nx, dtype=torch.float32, device=dev.device()) if n_up else None
         recv_down = torch.empty(nx, dtype=torch.float32, device=dev.device()) if n_down else None
         rounds = 0
+        wc_g = None
+        TRACE.mark("fill: overlap exchange")
+        if comm.world > 1:
+            # global multigrid start: pool my band, all-gather the coarse DEM, fill the whole coarse mosaic on every rank
+            nyc, nxc = -(-self.ny // 8), -(-nx // 8)
+            cp = (nxc + 31) // 32 * 32
+            zc_g = torch.empty((nyc, cp), dtype=torch.float32, device=dev.device())
+            wc_g = torch.empty((nyc, cp), dtype=torch.float32, device=dev.device())
+            cb = [(a // 8, -(-b // 8)) for a, b in self.bounds]
+            c0, c1 = cb[comm.rank]
+            scratch = torch.zeros(((c1 - c0) // 64 + 2) * (nxc // 64 + 2), dtype=torch.int32, device=dev.device())
+            own = z.owned()
+            _lib.check(lib.hd_fill_pool_band(own.ptr, own.pitch, rows, nx, ctypes.c_void_p(zc_g[c0].data_ptr()),
+                                             ctypes.c_void_p(wc_g[c0].data_ptr()), cp, flags,
+                                             ctypes.c_void_p(scratch.data_ptr()), dev.stream_ptr()))
+            for g in (zc_g, wc_g):
+                comm.p2p([(g[c0:c1], j) for j in range(comm.world) if j != comm.rank],
+                         [(g[a:b], i) for i, (a, b) in enumerate(cb) if i != comm.rank])
+            cbytes = lib.hd_pdfill_workspace_bytes(nyc, nxc)
+            cwork = dev.scratch(cbytes)
+            _lib.check(lib.hd_pdfill_coarse(ctypes.c_void_p(zc_g.data_ptr()), ctypes.c_void_p(wc_g.data_ptr()), cp, nyc, nxc,
+                                            ctypes.c_void_p(cwork.data_ptr()), cbytes, dev.stream_ptr()))
+        TRACE.mark("fill: global coarse level")
         while True:
-            _lib.check(lib.hd_pdfill_band(zv.ptr, zv.pitch, w.ptr, w.pitch, zv.ny, nx, wp, nbytes,
-                                          flags | (1 if rounds else 0), None, dev.stream_ptr()))
+            if rounds == 0 and wc_g is not None:
+                _lib.check(lib.hd_pdfill_band_start(zv.ptr, zv.pitch, w.ptr, w.pitch, zv.ny, nx, wp, nbytes, flags,
+                                                    ctypes.c_void_p(wc_g.data_ptr()), cp, self.r0 - n_up, dev.stream_ptr()))
+            else:
+                _lib.check(lib.hd_pdfill_band(zv.ptr, zv.pitch, w.ptr, w.pitch, zv.ny, nx, wp, nbytes,
+                                              flags | (1 if rounds else 0), None, dev.stream_ptr()))
             rounds += 1
             if comm.world == 1:
                 break
             lowered.zero_()
             sends, recvs = [], []
             if n_up:                                               # my first / last OWNED rows go to the neighbours' halo rows
-                sends.append((tw[n_up, :nx], comm.rank - 1))
+                sends.append((tw[2 * n_up - 1, :nx], comm.rank - 1))      # = the neighbour's last (boundary) row
                 recvs.append((recv_up, comm.rank - 1))
             if n_down:
-                sends.append((tw[n_up + rows - 1, :nx], comm.rank + 1))
+                sends.append((tw[n_up + rows - n_down, :nx], comm.rank + 1))   # = the neighbour's first (boundary) row
                 recvs.append((recv_down, comm.rank + 1))
             comm.p2p(sends, recvs)
             lp = ctypes.c_void_p(lowered.data_ptr())
@@ -526,6 +795,7 @@ class Band:
                 last = w.sub(zv.ny - 1, zv.ny, 0, nx)
                 _lib.check(lib.hd_halo_min_flag(last.ptr, ctypes.c_void_p(recv_down.data_ptr()), nx, lp, dev.stream_ptr()))
             comm.allreduce_max_(lowered)
+            TRACE.mark(f"fill: round {rounds}")
             if int(lowered.item()) == 0:                           # the one host read of the round
                 break
             if rounds >= max_rounds:

@@ -194,6 +194,26 @@ int hd_fft_rows(void* plan, const void* in, int in_dtype, int64_t in_pitch, void
 int hd_fft_band_pass(void* plan, int axis, int load, const void* in, int64_t in_pitch, int64_t nrows, const void* mask,
                      int64_t mask_pitch, int shift_cols, int inverse, int real_out, void* out_t, int64_t out_t_pitch,
                      int64_t keep_cols, void* workspace, int64_t workspace_bytes, void* stream);
+/* The same pass with the all-to-all FUSED into the transpose: every element of the transposed result is stored straight
+ * into the memory of the rank that owns it (peer pointers from hd_ipc_import), 256-byte row segments per warp over NVLink --
+ * no send buffer, no NCCL call, no unpack copy.  Output row `orow` (a frequency / pixel index of the transposed axis) in
+ * [row0, row1) of a segment lives at base[(orow - row0 + dst_row0) * pitch + column]; this rank's local row r lands at
+ * column col_dst0[q] + (r - col_local0[q]).  The caller synchronises the ranks before (destinations free) and after. */
+#define HD_SCATTER_MAX_SEGS 16
+typedef struct { int64_t row0, row1; void* base; int64_t pitch; int64_t dst_row0; } hd_scatter_seg;
+typedef struct {
+    int32_t nseg, ncolseg;
+    hd_scatter_seg seg[HD_SCATTER_MAX_SEGS];
+    int64_t col_local0[2], col_dst0[2], col_len[2];
+} hd_scatter;
+int hd_fft_band_pass_scatter(void* plan, int axis, int load, const void* in, int64_t in_pitch, int64_t nrows, const void* mask,
+                             int64_t mask_pitch, int shift_cols, int inverse, int real_out, const hd_scatter* sc,
+                             int64_t keep_cols, void* workspace, int64_t workspace_bytes, void* stream);
+/* CUDA IPC plumbing for the peer pointers (one process per GPU): export the allocation that holds ptr (handle64: 64 bytes;
+ * *offset = ptr's byte offset inside it), open it in another process (the mapping starts at the allocation base), close. */
+int hd_ipc_export(const void* ptr, void* handle64, int64_t* offset);
+int hd_ipc_import(const void* handle64, void** base);
+int hd_ipc_close(void* base);
 /* "K layout" of a rank's spectrum rows: ky in [a, b) (b <= ny/2 + 1) followed by their mirrors ny - ky in ascending
  * order -- closed under ky -> -ky, so the conjugate half of a real raster's spectrum is completed locally. */
 int64_t hd_klayout_rows(int64_t a, int64_t b, int64_t ny);
@@ -260,6 +280,19 @@ int hd_pdfill_finish_d8(void* w, int64_t w_pitch, void* d8, int64_t d8_pitch, in
 int hd_pdfill_status(const void* workspace, int* status_out, void* stream);
 /* Row-band fill after a halo exchange: w_halo = min(w_halo, received); *lowered (device int) = 1 if a cell went down. */
 int hd_halo_min_flag(void* w_halo, const void* received, int64_t nx, int* lowered, void* stream);
+/* Row-band fill with a GLOBAL multigrid start (hydrodem_b200/sharding.py): every rank pools its band to 8x8 block maxima
+ * (hd_fill_pool_band; the band's first row is a multiple of 8 in mosaic coordinates; flags 2 / 4 = top / bottom edge is an
+ * interior cut; tile_flags_scratch: >= ceil(nyc/64) * ceil(nxc/64) ints), the coarse rows are all-gathered, each rank fills
+ * the whole coarse mosaic (hd_pdfill_coarse: W carries the outlet marks on entry; workspace
+ * hd_pdfill_workspace_bytes(nyc, nxc)) and starts its band from that upper bound (hd_pdfill_band_start: y_origin = mosaic
+ * row of the extended band's row 0).  Same fixed point as hd_pdfill, far fewer exchange rounds. */
+int hd_fill_pool_band(const void* z, int64_t z_pitch, int64_t ny, int64_t nx, void* zc, void* wc, int64_t c_pitch, int flags,
+                      void* tile_flags_scratch, void* stream);
+int hd_pdfill_coarse(const void* zc, void* wc, int64_t c_pitch, int64_t nyc, int64_t nxc, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+int hd_pdfill_band_start(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* workspace,
+                         int64_t workspace_bytes, int flags, const void* wc_global, int64_t c_pitch, int64_t y_origin,
+                         void* stream);
 int hd_pdfill_finish(const void* z, int64_t z_pitch, void* w, int64_t w_pitch, int64_t ny, int64_t nx, void* stream);
 /* D8 flow direction on a (filled) F32 surface -> U8 ESRI codes (E=1, SE=2, S=4, SW=8, W=16, NW=32, N=64, NE=128);
  * steepest positive drop, diagonals scaled by 0.70710678f, ties -> first in that order, frame / NaN / flat -> 0. */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "hd_majority": (_i, [_p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),
     "hd_nanfix": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),
     "hd_isolated": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _p]),
+    "hd_route_rivers": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _p, _i64, _p]),
     "hd_quadratic": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
     "hd_groves_correction": (_i, [_p, _i, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _i, _d, _p]),
     "hd_median": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _i, _p]),

@@ -124,6 +124,55 @@ class IsolatedPoints(_InPlace3):
         self.window_size = window_size
 
 
+class RouteRivers(WindowFilter):
+    """Route / expand rivers along the low cells of a reference DEM (custom_filters.py:128-199): a raster scan over the
+    mask cells with value 1 that marks the minima of each 3x3 DEM window and consumes them (10000) as it goes -- order
+    dependent, run on the device as an order-preserving wavefront (csrc/rivers.cu).  Returns float64 zeros / ones."""
+
+    def __init__(self, *, window_size, dem):
+        import copy
+        self.window_size = window_size
+        self.dem = dem if isinstance(dem, dev.DeviceRaster) else copy.deepcopy(dem)      # (:163)
+
+    def run_device(self, raster):
+        import ctypes
+        check_window(raster.shape, self.window_size)
+        dem = self.dem if isinstance(self.dem, dev.DeviceRaster) else dev.upload(np.ascontiguousarray(self.dem))
+        if dem.shape != raster.shape:
+            raise ValueError(f"dem shape {dem.shape} does not match the rivers mask {raster.shape}")
+        check_window(dem.shape, self.window_size)
+        # the working copy the reference mutates: dem_sliding.grid = dem.astype('float32') (sliding_window.py:132)
+        g = dev.empty(dem.ny, dem.nx, _lib.F32, np.float32)
+        dev.elementwise(_lib.OP_COPY, dem, None, 0.0, g)
+        mask = as_f32(raster)
+        out = dev.empty(raster.ny, raster.nx, _lib.U8, np.float64)
+        nbytes = raster.ny * 4
+        work = dev.scratch(nbytes)
+        _lib.check(_lib.load().hd_route_rivers(mask.ptr, mask.pitch, g.ptr, g.pitch, out.ptr, out.pitch, raster.ny, raster.nx,
+                                               int(self.window_size), ctypes.c_void_p(work.data_ptr()), nbytes,
+                                               dev.stream_ptr()),
+                   window_size=self.window_size, shape=raster.shape)
+        return out
+
+
+class ProcessRivers(ComposedFilter):
+    """MaskPositives -> ExpandFilter(3) -> RouteRivers(3, dem=hsheds) -> BinaryClosing() (custom_filters.py:770-798)."""
+
+    def __init__(self, hsheds):
+        super().__init__()
+        self.filters = [MaskPositives(), ExpandFilter(window_size=3), RouteRivers(window_size=3, dem=hsheds),
+                        BinaryClosing()]
+
+
+class ClipLagoonsRivers(ComposedFilter):
+    """Rivers minus their intersection with the lagoons: ProductFilter(factor=mask_lagoons) ->
+    BitwiseXOR(operand=rivers_routed_closing) (custom_filters.py:801-831)."""
+
+    def __init__(self, mask_lagoons, rivers_routed_closing):
+        super().__init__()
+        self.filters = [ProductFilter(factor=mask_lagoons), BitwiseXOR(operand=rivers_routed_closing)]
+
+
 class QuadraticFilter(WindowFilter):
     """Least-squares quadratic smoothing over a square window -- the "isotropic" filter
     (custom_filters.py:202-257).  Result in the input's dtype, ws//2 border unchanged."""

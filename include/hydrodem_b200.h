@@ -141,6 +141,13 @@ int hd_groves_correction(const void* in, int in_dtype, int64_t in_pitch, const v
 int hd_median(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx, int ws, int circular,
               void* stream);
 
+/* RouteRivers.apply, custom_filters.py:165-199 (window_size = 3 as used by ProcessRivers, :796): the order-dependent raster
+ * scan, run as an order-preserving wavefront (one warp per row, pipelined on per-row progress counters).  mask: F32 (visits
+ * where int(v) == 1); g: F32 working copy of the reference DEM, consumed cells are overwritten with 10000 IN PLACE like
+ * dem_sliding.grid (:198); out: U8 (zeroed here), 1 = routed river.  workspace: ny ints. */
+int hd_route_rivers(const void* mask, int64_t mask_pitch, void* g, int64_t g_pitch, void* out, int64_t out_pitch, int64_t ny,
+                    int64_t nx, int ws, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Fourier stripe removal (filters/custom_filters.py:369-462, :834-1101) ------------------------ */
 /* BlanksFourier.apply, custom_filters.py:395-427 (ws = 55, inner = 5 as hard-coded there, :417-419, :457).
  * in: F32 spectrum quarter.  mask_out (U8 or F32, `mask_dtype`) = mask_prev (U8, may be NULL) + (centre > factor *

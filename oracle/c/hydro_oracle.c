@@ -179,3 +179,28 @@ void ho_d8(const float *w, uint8_t *out, int64_t ny, int64_t nx)
             out[j * nx + i] = code;
         }
 }
+
+
+/* RouteRivers.apply, filters/custom_filters.py:165-199, window_size = 3: raster scan over interior cells of the mask with
+ * int(v) == 1 (float32 snapshot); minimum of the 3x3 window of the float32 working DEM g (np.amin: NaN poisons it), every
+ * cell equal to it becomes river and 10000 in g.  g is modified in place; out (uint8) must be zeroed by the caller. */
+void ho_route_rivers(const float* mask, float* g, unsigned char* out, long ny, long nx)
+{
+    for (long j = 1; j < ny - 1; ++j)
+        for (long i = 1; i < nx - 1; ++i) {
+            const float mv = mask[j * nx + i];
+            if (!(mv == mv) || (int)mv != 1) continue;
+            float m = g[(j - 1) * nx + (i - 1)];
+            int nan = 0;
+            for (int a = -1; a <= 1; ++a)
+                for (int b = -1; b <= 1; ++b) {
+                    const float v = g[(j + a) * nx + (i + b)];
+                    if (v != v) nan = 1;
+                    if (v < m) m = v;
+                }
+            if (nan) continue;
+            for (int a = -1; a <= 1; ++a)
+                for (int b = -1; b <= 1; ++b)
+                    if (g[(j + a) * nx + (i + b)] == m) { g[(j + a) * nx + (i + b)] = 10000.0f; out[(j + a) * nx + (i + b)] = 1; }
+        }
+}

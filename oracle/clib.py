@@ -28,6 +28,8 @@ def lib():
         _lib.ho_median.argtypes = [p, p, i64, i64, ctypes.c_int, ctypes.c_int]
         _lib.ho_priority_flood.argtypes = [p, p, i64, i64]
         _lib.ho_d8.argtypes = [p, p, i64, i64]
+        _lib.ho_route_rivers.argtypes = [p, p, p, i64, i64]
+        _lib.ho_route_rivers.restype = None
         for f in (_lib.ho_majority, _lib.ho_expand, _lib.ho_median, _lib.ho_priority_flood, _lib.ho_d8):
             f.restype = None
     return _lib
@@ -70,3 +72,11 @@ def d8(w):
     out = np.zeros(g.shape, dtype=np.uint8)
     lib().ho_d8(g.ctypes.data, out.ctypes.data, g.shape[0], g.shape[1])
     return out
+
+
+def route_rivers(mask, dem):
+    """RouteRivers(window_size=3, dem=dem).apply(mask) (custom_filters.py:165-199): float64 zeros / ones."""
+    m, g = _f32c(mask), _f32c(dem).copy()
+    out = np.zeros(m.shape, dtype=np.uint8)
+    lib().ho_route_rivers(m.ctypes.data, g.ctypes.data, out.ctypes.data, m.shape[0], m.shape[1])
+    return out.astype(np.float64)

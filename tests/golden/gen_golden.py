@@ -198,10 +198,57 @@ def run_simple():
     save("run_simple", **out)
 
 
+def synth_rivers(ny, nx, seed, n_rivers=6):
+    """Rasterised river polylines: random walks drifting across the tile, value 1 on a float32 raster (what
+    rasterize_rivers leaves, utils_dem.py); a few thick spots and a river that runs along the frame."""
+    rng = np.random.default_rng(seed)
+    r = np.zeros((ny, nx), dtype=np.float32)
+    for k in range(n_rivers):
+        y, x = int(rng.integers(0, ny)), 0
+        while x < nx:
+            r[min(max(y, 0), ny - 1), x] = 1
+            step = rng.integers(-1, 2)
+            if step and rng.random() < 0.5:
+                y += int(step)
+                r[min(max(y, 0), ny - 1), x] = 1
+            x += 1
+    r[ny // 3:ny // 3 + 4, nx // 2:nx // 2 + 5] = 1
+    r[0, :nx // 3] = 1
+    r[:, nx - 1] = 1
+    return r
+
+
+def run_rivers():
+    """RouteRivers / ProcessRivers / ClipLagoonsRivers (custom_filters.py:128-199, :770-831) on seeded inputs: the
+    integer-valued HydroSHEDS raster gives plateaus (several window cells tie for the minimum), the float one does not."""
+    out = {}
+    for tag, (ny, nx, seed) in {"a": (150, 190, 5), "b": (97, 260, 9)}.items():
+        sc = SynthScene(ny, nx, 400 + seed)
+        hs = sc.hsheds()
+        hs[hs < 0] = 90.0                                             # (voids are fixed before rivers are routed)
+        dem_f = sc.srtm()
+        rivers = synth_rivers(ny, nx, seed)
+        mask = ref_cf.ExpandFilter(window_size=3).apply(ref_cf.MaskPositives().apply(rivers))
+        out[f"{tag}_hsheds"], out[f"{tag}_srtm"], out[f"{tag}_rivers"], out[f"{tag}_mask"] = hs, dem_f, rivers, mask
+        out[f"{tag}_routed_int"] = ref_cf.RouteRivers(window_size=3, dem=hs).apply(mask)
+        out[f"{tag}_routed_float"] = ref_cf.RouteRivers(window_size=3, dem=dem_f).apply(mask)
+        routed = ref_cf.ProcessRivers(hs).apply(rivers)
+        out[f"{tag}_process"] = routed
+        lag = ref_cf.LagoonsDetection()
+        lag.apply(sc.hsheds())
+        out[f"{tag}_mask_lagoons"] = lag.mask_lagoons
+        out[f"{tag}_clip"] = ref_cf.ClipLagoonsRivers(lag.mask_lagoons, routed).apply(routed)
+    save("run_rivers", **out)
+
+
 if __name__ == "__main__":
+    if "--only-rivers" in sys.argv:
+        run_rivers()
+        sys.exit(0)
     convert_reference_goldens()
     window_kats()
     run_stencils()
     run_lagoons_and_final()
     run_fourier()
     run_simple()
+    run_rivers()

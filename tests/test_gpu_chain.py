@@ -42,6 +42,40 @@ def test_chain_vs_oracle(shape, seed):
     np.testing.assert_array_equal(res.d8, hydrology.d8(res.filled))
 
 
+def test_c2_chain_vs_oracle_at_3601():
+    """BASELINE.json configs[1] at its FULL size: the whole chain on a synthetic 3601 x 3601 tile against the CPU
+    oracle (about a minute of CPU).  Exact stages must be identical, tolerance stages within 1e-5 relative; the rounded
+    DEM may differ only where the 3x3 mean sits on a half-integer -- the number of such cells is printed."""
+    import time
+    from oracle import stencils
+    sc = SynthScene(3601, 3601, 1002)
+    srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()
+    res = ConditioningChain(keep_intermediates=True).apply(srtm, groves, hsheds.copy())
+    t0 = time.time()
+    with np.errstate(all="ignore"):
+        want = ochain.conditioning_chain(srtm, groves, hsheds.copy(), with_hydrology=False)
+    print(f"C2: oracle chain {time.time() - t0:.0f} s")
+    lag = want["lagoons"]
+    np.testing.assert_array_equal(res.hsheds_nan_fixed, lag["CorrectNANValues"])
+    np.testing.assert_array_equal(res.majority, lag["MajorityFilter"])
+    np.testing.assert_array_equal(res.lagoons_values, lag["TidyingLagoons"])
+    np.testing.assert_array_equal(res.groves.astype(bool), want["groves"])
+    mism = int((res.fourier_mask != want["mask"]).sum())
+    print("C2: Fourier mask cells that differ:", mism, "of", int(want["mask"].sum()), "blanked")
+    assert mism == 0
+    np.testing.assert_allclose(res.fourier, want["fourier"], rtol=1e-5)
+    np.testing.assert_allclose(res.srtm, want["srtm"], rtol=1e-5)
+    np.testing.assert_allclose(res.dem_complete, want["dem_complete"], rtol=1e-5)
+    mean = stencils.convolve_reflect(want["dem_complete"], np.ones((3, 3))) / 9
+    flips = res.final != want["final"]
+    frac = np.abs(mean - np.floor(mean) - 0.5)
+    print("C2: rounding flips:", int(flips.sum()), "of", flips.size)
+    assert flips.mean() < 1e-4 and (frac[flips] < 1e-3).all() and np.abs(res.final - want["final"])[flips].max(initial=0) <= 1
+    # hydrology on the chain's own final DEM (C priority-flood oracle)
+    np.testing.assert_array_equal(res.filled, hydrology.sinkfill(res.final))
+    np.testing.assert_array_equal(res.d8, hydrology.d8(res.filled))
+
+
 def test_chain_with_rivers():
     sc = SynthScene(200, 260, 9)
     srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()

@@ -132,14 +132,20 @@ def test_fft_vs_cufft():
 
 
 def test_stripe_removal_bundled_tile():
-    """C1 tile (519 x 508, srtm_corrected.tif): GPU stage against the oracle run side by side."""
+    """C1 tile (519 x 508, srtm_corrected.tif): GPU stage against the oracle run side by side.  On real SRTM a few
+    spectral bins sit exactly on the detector's threshold (centre > 4 x hollow mean, float32): the mismatch count is
+    reported and bounded, and the VALUES are compared in any case -- against the oracle's inverse transform applied to
+    the mask the GPU found, so a borderline bin cannot hide an error elsewhere."""
     g = load_golden("ref_tiles")
     a = g["srtm_corrected"]
     want, mask, fabs = fourier.detect_apply_fourier(a)
     daf = cf.DetectApplyFourier()
     got = daf.apply(a)
     mism = int((daf.mask != mask).sum())
-    assert mism <= 4, f"{mism} mask cells differ"                          # reported; borderline threshold flips only
+    print("bundled tile: mask cells that differ from the oracle:", mism)
+    assert mism <= 4, f"{mism} mask cells differ"
+    _, fshift = fourier.fourier_initial(a)
+    np.testing.assert_allclose(got, fourier.apply_mask(daf.mask, fshift), rtol=RTOL)
     if mism == 0:
         np.testing.assert_allclose(got, want, rtol=RTOL)
 
@@ -208,3 +214,39 @@ def test_stripe_removal_odd_sizes_hermitian_path(shape, monkeypatch):
     monkeypatch.setenv("HD_FFT_NO_HERMITIAN", "1")
     plain = cf.DetectApplyFourier().apply(a)
     np.testing.assert_allclose(got, plain, rtol=1e-6)
+
+
+
+def test_c3_fourier_isotropic_median_at_10801():
+    """BASELINE.json configs[2]: Fourier stripe removal + the isotropic (quadratic) filter + the median filter on a
+    synthetic 10801 x 10801 tile.  The Fourier stage is compared on the WHOLE tile against scipy / the oracle (the
+    rounding floor of a single-precision transform grows with N: this is where a complex64 inverse would show); the
+    two window filters run on the whole tile on the GPU and are compared on a 700-row strip (windows are local; the
+    oracle's per-cell cost is the same everywhere)."""
+    import time
+    from hydrodem_b200 import device as dev
+    from hydrodem_b200.filters import new_filters as nf
+    from hydrodem_b200.synth import DeviceMosaic
+    n = 10801
+    srtm_t, _, _ = DeviceMosaic(n, n, 1003).band(0, n)
+    a = srtm_t.cpu().numpy()
+    del srtm_t
+    t0 = time.time()
+    want, mask, _ = fourier.detect_apply_fourier(a)
+    t_cpu = time.time() - t0
+    daf = cf.DetectApplyFourier()
+    d_in = dev.upload(a)
+    d_out = daf.run_device(d_in)
+    got = dev.download(d_out)
+    mism = int((daf.mask != mask).sum())
+    print(f"C3: oracle Fourier stage {t_cpu:.1f} s; mask cells that differ: {mism}; blanked bins: {int(mask.sum())}")
+    assert mism == 0 and mask.sum() > 0
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    # isotropic + median on the stripe-free DEM, strip rows [r0, r1) (oracle fed with the halo it needs)
+    r0, r1, h = 5000, 5700, 7
+    smooth = dev.download(cf.QuadraticFilter(window_size=15).run_device(d_out))
+    med = dev.download(nf.MedianFilter(window_size=5).run_device(d_out))
+    strip = got[r0 - h:r1 + h]
+    np.testing.assert_allclose(smooth[r0:r1], stencils.quadratic(strip, 15)[h:-h], rtol=RTOL)
+    from oracle import clib
+    np.testing.assert_array_equal(med[r0:r1], clib.median(strip, 5)[h:-h])

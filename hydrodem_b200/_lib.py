@@ -15,8 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libhydrodem_b200.so")
 # hd_status / hd_dtype / op codes (mirrors of the header enums)
 HD_OK, HD_ERR_NULL, HD_ERR_WINDOW_HIGH, HD_ERR_WINDOW_EVEN = 0, -1, -2, -3
 HD_ERR_ALIGN, HD_ERR_CUDA, HD_ERR_UNSUPPORTED, HD_ERR_ARG, HD_ERR_WORKSPACE = -4, -5, -6, -7, -8
-U8, F32, F64, I64, C64, C128, I32 = range(7)
-OP_COPY, OP_MUL, OP_ADD, OP_RSUB, OP_LT, OP_GT, OP_ABS, OP_RINT, OP_XOR = range(9)
+U8, F32, F64, I64, C64, C128, I32, I16 = range(8)
+OP_COPY, OP_MUL, OP_ADD, OP_RSUB, OP_LT, OP_GT, OP_ABS, OP_RINT, OP_XOR, OP_TRUNC = range(10)
 MORPH_ERODE, MORPH_DILATE, MORPH_CLOSE, MORPH_OPEN = range(4)
 
 _p, _i, _i64, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double

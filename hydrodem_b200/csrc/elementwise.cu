@@ -17,6 +17,7 @@ __device__ __forceinline__ cplx load_as(const void* p, int dtype, int64_t idx)
         case HD_F64: return {((const double*)p)[idx], 0.0};
         case HD_I64: return {(double)((const int64_t*)p)[idx], 0.0};
         case HD_I32: return {(double)((const int32_t*)p)[idx], 0.0};
+        case HD_I16: return {(double)((const int16_t*)p)[idx], 0.0};
         case HD_C64: { float2 v = ((const float2*)p)[idx]; return {(double)v.x, (double)v.y}; }
         default: { double2 v = ((const double2*)p)[idx]; return {v.x, v.y}; }
     }
@@ -26,6 +27,7 @@ __device__ __forceinline__ int64_t load_int(const void* p, int dtype, int64_t id
     switch (dtype) {
         case HD_U8: return ((const uint8_t*)p)[idx];
         case HD_I32: return ((const int32_t*)p)[idx];
+        case HD_I16: return ((const int16_t*)p)[idx];
         default: return ((const int64_t*)p)[idx];
     }
 }
@@ -37,6 +39,7 @@ __device__ __forceinline__ void store_as(void* p, int dtype, int64_t idx, cplx v
         case HD_F64: ((double*)p)[idx] = v.re; break;
         case HD_I64: ((int64_t*)p)[idx] = (int64_t)v.re; break;
         case HD_I32: ((int32_t*)p)[idx] = (int32_t)v.re; break;
+        case HD_I16: ((int16_t*)p)[idx] = (int16_t)(int32_t)v.re; break;
         case HD_C64: ((float2*)p)[idx] = make_float2((float)v.re, (float)v.im); break;
         default: ((double2*)p)[idx] = make_double2(v.re, v.im); break;
     }
@@ -56,6 +59,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(int op, const void* __
             const int64_t r = va ^ vb;
             if (out_dtype == HD_U8) ((uint8_t*)out)[io] = (uint8_t)r;
             else if (out_dtype == HD_I32) ((int32_t*)out)[io] = (int32_t)r;
+            else if (out_dtype == HD_I16) ((int16_t*)out)[io] = (int16_t)r;
             else ((int64_t*)out)[io] = r;
             continue;
         }
@@ -74,6 +78,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(int op, const void* __
             case HD_OP_GT: r.re = va.re > vb.re ? 1.0 : 0.0; break;
             case HD_OP_ABS: r.re = (va.im == 0.0) ? fabs(va.re) : hypot(va.re, va.im); break;
             case HD_OP_RINT: r.re = rint(va.re); break;
+            case HD_OP_TRUNC: r.re = (va.re == va.re) ? trunc(va.re) : 0.0; break;
             default: break;
         }
         store_as(out, out_dtype, io, r);
@@ -87,11 +92,11 @@ extern "C" int hd_elementwise(int op, const void* a, int a_dtype, int64_t a_pitc
                               int64_t nx, void* stream)
 {
     if (!a || !out) return HD_ERR_NULL;
-    if (op < HD_OP_COPY || op > HD_OP_XOR) return HD_ERR_ARG;
+    if (op < HD_OP_COPY || op > HD_OP_TRUNC) return HD_ERR_ARG;
     if (!hd_dtype_size(a_dtype) || !hd_dtype_size(out_dtype) || (b && !hd_dtype_size(b_dtype))) return HD_ERR_ARG;
     if (ny < 0 || nx < 0 || a_pitch < nx || out_pitch < nx || (b && b_pitch < nx)) return HD_ERR_ARG;
     if (op == HD_OP_XOR) {
-        auto is_int = [](int d) { return d == HD_U8 || d == HD_I64 || d == HD_I32; };
+        auto is_int = [](int d) { return d == HD_U8 || d == HD_I64 || d == HD_I32 || d == HD_I16; };
         if (!is_int(a_dtype) || (b && !is_int(b_dtype)) || !is_int(out_dtype)) return HD_ERR_UNSUPPORTED;
     }
     if (ny == 0 || nx == 0) return HD_OK;

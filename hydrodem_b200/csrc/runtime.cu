@@ -63,6 +63,7 @@ size_t hd_dtype_size(int dtype)
         case HD_U8: return 1;
         case HD_F32: return 4;
         case HD_I32: return 4;
+        case HD_I16: return 2;
         case HD_F64: return 8;
         case HD_I64: return 8;
         case HD_C64: return 8;

@@ -22,12 +22,12 @@ from .exceptions import DeviceError, NumpyArrayExpectedError
 
 _NP2HD = {np.dtype(np.uint8): _lib.U8, np.dtype(np.bool_): _lib.U8, np.dtype(np.float32): _lib.F32,
           np.dtype(np.float64): _lib.F64, np.dtype(np.int64): _lib.I64, np.dtype(np.int32): _lib.I32,
-          np.dtype(np.complex64): _lib.C64, np.dtype(np.complex128): _lib.C128}
+          np.dtype(np.complex64): _lib.C64, np.dtype(np.complex128): _lib.C128, np.dtype(np.int16): _lib.I16}
 _HD2TORCH = {_lib.U8: torch.uint8, _lib.F32: torch.float32, _lib.F64: torch.float64, _lib.I64: torch.int64,
-             _lib.I32: torch.int32, _lib.C64: torch.complex64, _lib.C128: torch.complex128}
+             _lib.I32: torch.int32, _lib.C64: torch.complex64, _lib.C128: torch.complex128, _lib.I16: torch.int16}
 _HD2NP = {_lib.U8: np.dtype(np.uint8), _lib.F32: np.dtype(np.float32), _lib.F64: np.dtype(np.float64),
           _lib.I64: np.dtype(np.int64), _lib.I32: np.dtype(np.int32), _lib.C64: np.dtype(np.complex64),
-          _lib.C128: np.dtype(np.complex128)}
+          _lib.C128: np.dtype(np.complex128), _lib.I16: np.dtype(np.int16)}
 
 
 def hd_dtype_of(np_dtype):

@@ -90,11 +90,17 @@ class _InPlace3(WindowFilter):
             raise dev.DeviceError(f"{type(self).__name__}: only window_size=3 is implemented on the device")
         if raster.dtype in (_lib.F32, _lib.F64):
             src = raster
+        elif raster.dtype in (_lib.I16, _lib.U8):
+            src = dev.convert(raster, _lib.F32)          # exact, and the windows are float32 anyway (sliding_window.py:132)
         else:
             src = dev.convert(raster, _lib.F64)
         out = dev.empty(raster.ny, raster.nx, src.dtype, raster.ref_dtype)
         fn = getattr(_lib.load(), self._entry)
         _lib.check(fn(src.ptr, src.pitch, out.ptr, out.pitch, src.dtype, src.ny, src.nx, dev.stream_ptr()))
+        if np.dtype(raster.ref_dtype).kind in "iu":
+            # the reference writes the float32 result into the caller's INTEGER array (dem[center] = mean, :316):
+            # NumPy truncates toward zero on assignment, and the next stage (MajorityFilter) counts those integers
+            dev.elementwise(_lib.OP_TRUNC, out, None, 0.0, out)
         return out
 
     def apply(self, image_to_filter):

@@ -45,7 +45,8 @@ typedef enum {
     HD_I64 = 3,
     HD_C64 = 4,  /* interleaved float re, im  */
     HD_C128 = 5, /* interleaved double re, im */
-    HD_I32 = 6
+    HD_I32 = 6,
+    HD_I16 = 7   /* SRTM / HydroSHEDS on disk: what gdal ReadAsArray hands the reference (image_srtm.py:125, image_hsheds.py:133) */
 } hd_dtype;
 
 /* ---- runtime --------------------------------------------------------------------------------- */
@@ -87,7 +88,9 @@ typedef enum {
     HD_OP_GT = 5,   /* out = a > b      GreaterThan.apply        simple_filters.py:81-96                   */
     HD_OP_ABS = 6,  /* out = |a|        AbsoluteValues.apply     extension_filters.py:78-95 (C64 -> F32)   */
     HD_OP_RINT = 7, /* out = around(a)  Around.apply             extension_filters.py:113-130 (half-even)  */
-    HD_OP_XOR = 8   /* out = b ^ a      BitwiseXOR.apply         extension_filters.py:43-60 (U8/I64)       */
+    HD_OP_XOR = 8,  /* out = b ^ a      BitwiseXOR.apply         extension_filters.py:43-60 (U8/I64)       */
+    HD_OP_TRUNC = 9 /* out = trunc(a), NaN -> 0: what NumPy's assignment of a float into an integer array does
+                     * (CorrectNANValues on the int16 HydroSHEDS raster, custom_filters.py:316) */
 } hd_elementwise_op;
 /* `b` may be NULL: then the scalar `b_scalar` is the second operand.  Arithmetic is done in double and
  * rounded once to out_dtype (innocuous double rounding: identical to native float32 arithmetic). */

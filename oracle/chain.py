@@ -34,8 +34,9 @@ def srtm_branch(srtm_raw, groves_class_raw):
     GrovesCorrectionsIter(iterations=3) (:199)."""
     corrected, mask, fabs = fourier.detect_apply_fourier(srtm_raw)
     groves = morphology.binary_closing(groves_class_raw, np.ones((3, 3)))
-    out = stencils.groves_corrections_iter(corrected, groves, 3)
-    return out, dict(fourier=corrected, mask=mask, fabs=fabs, groves=groves)
+    trace = []
+    out = stencils.groves_corrections_iter(corrected, groves, 3, trace=trace)
+    return out, dict(fourier=corrected, mask=mask, fabs=fabs, groves=groves, groves_hi=trace)
 
 
 def final_terms(srtm, lag, rivers):

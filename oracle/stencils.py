@@ -198,21 +198,25 @@ def quadratic(dem, ws, rows_per_chunk=32):
     return out
 
 
-def groves_correction(dem, groves_class, ws=15):
+def groves_correction(dem, groves_class, ws=15, trace=None):
     """GrovesCorrection.apply (custom_filters.py:704-732), one iteration:
     smooth = Quadratic(dem); hi = dem - smooth; tall = (hi > 1.5)*1;
-    keep = 1 - groves_class*tall; result = keep*hi + smooth."""
+    keep = 1 - groves_class*tall; result = keep*hi + smooth.
+    ``trace``: a list that receives ``hi`` of this iteration (the parity tests use it to find the cells that sit ON
+    the 1.5 m threshold, where a tolerance-class difference upstream legitimately flips the decision)."""
     smooth = quadratic(dem, ws)
     hi = dem - smooth
+    if trace is not None:
+        trace.append(hi)
     tall = (hi > 1.5) * 1
     keep = 1 - groves_class * tall
     return hi * keep + smooth
 
 
-def groves_corrections_iter(dem, groves_class, iterations=3, ws=15):
+def groves_corrections_iter(dem, groves_class, iterations=3, ws=15, trace=None):
     """GrovesCorrectionsIter (custom_filters.py:755-767)."""
     for _ in range(iterations):
-        dem = groves_correction(dem, groves_class, ws)
+        dem = groves_correction(dem, groves_class, ws, trace)
     return dem
 
 

@@ -241,7 +241,33 @@ def run_rivers():
     save("run_rivers", **out)
 
 
+def run_int16():
+    """The reference's PRODUCTION dtype: gdal ReadAsArray hands int16 rasters to LagoonsDetection (image_hsheds.py:133-135)
+    and DetectApplyFourier (image_srtm.py:125-126).  CorrectNANValues then writes its float32 means into an int16 array
+    (truncation on assignment) and scipy.fftpack promotes the integer raster to float64 / complex128."""
+    sc = SynthScene(230, 260, 77)
+    hs = sc.hsheds().astype(np.int16)
+    hs[100, 100:104] = -32768                                         # a run of voids: means that are not integers
+    hs[101, 101] = -32768
+    out = {"hsheds_i16": hs.copy()}
+    work = hs.copy()
+    lag = ref_cf.LagoonsDetection()
+    ret = lag.apply(work)
+    out["lag_return"] = ret
+    for k in ("CorrectNANValues", "MajorityFilter", "TidyingLagoons", "MaskPositives"):
+        out["lag_" + k] = np.asarray(lag.results[k])
+    assert lag.results["CorrectNANValues"].dtype == np.int16 and lag.results["CorrectNANValues"] is work
+    srtm = np.round(sc.srtm()).astype(np.int16)
+    out["srtm_i16"] = srtm
+    daf = ref_cf.DetectApplyFourier()
+    out["daf_i16"] = daf.apply(srtm)
+    save("run_int16", **out)
+
+
 if __name__ == "__main__":
+    if "--only-int16" in sys.argv:
+        run_int16()
+        sys.exit(0)
     if "--only-rivers" in sys.argv:
         run_rivers()
         sys.exit(0)
@@ -252,3 +278,4 @@ if __name__ == "__main__":
     run_fourier()
     run_simple()
     run_rivers()
+    run_int16()

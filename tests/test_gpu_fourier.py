@@ -250,3 +250,14 @@ def test_c3_fourier_isotropic_median_at_10801():
     np.testing.assert_allclose(smooth[r0:r1], stencils.quadratic(strip, 15)[h:-h], rtol=RTOL)
     from oracle import clib
     np.testing.assert_array_equal(med[r0:r1], clib.median(strip, 5)[h:-h])
+
+
+def test_int16_input_stripe_removal():
+    """SRTM arrives as int16 (image_srtm.py:125-126): scipy.fftpack promotes it to float64 / complex128, the device path
+    widens it to float32 (exact) and stays in single precision -- inside the stage's 1e-5 tolerance."""
+    g = load_golden("run_int16")
+    a = g["srtm_i16"]
+    assert a.dtype == np.int16
+    got = cf.DetectApplyFourier().apply(a)
+    assert got.dtype == np.float64
+    np.testing.assert_allclose(got, g["daf_i16"], rtol=RTOL)

@@ -166,3 +166,26 @@ def test_boundary_errors():
         cf.ExpandFilter(window_size=11).apply(np.zeros((9, 20)))
     with pytest.raises(WindowSizeHighError):
         cf.MajorityFilter(window_size=10).apply(np.zeros((9, 20)))     # too large is reported before even
+
+
+def test_int16_production_dtype_lagoons():
+    """gdal ReadAsArray hands the reference INT16 rasters (image_hsheds.py:133-135).  CorrectNANValues then stores its
+    float32 means into the caller's int16 array -- truncation on assignment -- and MajorityFilter counts those integers.
+    Fixture: the unmodified reference on an int16 HydroSHEDS raster with a run of voids (non-integer means)."""
+    from hydrodem_b200 import device as dev
+    g = load_golden("run_int16")
+    hs = g["hsheds_i16"].copy()
+    assert hs.dtype == np.int16
+    rt = dev.download(dev.upload(hs))
+    assert rt.dtype == np.int16
+    np.testing.assert_array_equal(rt, hs)
+    lag = cf.LagoonsDetection()
+    ret = lag.apply(hs)
+    assert lag.results["CorrectNANValues"] is hs and hs.dtype == np.int16          # in place, caller's array
+    np.testing.assert_array_equal(hs, g["lag_CorrectNANValues"])
+    assert (g["lag_CorrectNANValues"] != g["hsheds_i16"]).sum() >= 5                # the voids were filled
+    for k in ("MajorityFilter", "TidyingLagoons", "MaskPositives"):
+        got = lag.results[k]
+        assert got.dtype == g["lag_" + k].dtype, k
+        np.testing.assert_array_equal(got, g["lag_" + k])
+    np.testing.assert_array_equal(ret, g["lag_return"])

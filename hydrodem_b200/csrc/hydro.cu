@@ -178,6 +178,34 @@ __global__ void __launch_bounds__(FNT) fill_sweep_kernel(const __grid_constant__
 //            flight, 0 means the global fixed point is reached.
 //   memory : W is read with ld.global.cg (L2, never a stale L1 line) and written with plain stores followed by
 //            __threadfence() before the neighbour is published.
+//
+// Memory-ordering argument of the poke / ticket protocol (compute-sanitizer is closed on the measurement pool, so the
+// argument is written down here and the kernel is stress-tested against the CPU priority-flood oracle instead:
+// tests/test_gpu_new_stages.py::test_fill_worklist_stress):
+//   1. Single writer.  A tile's W cells are stored only by the CTA that holds the tile in state T_RUNNING; the state
+//      moves IDLE -> QUEUED (poker, atomicCAS) -> RUNNING (the ticket holder, atomicExch) -> IDLE / QUEUED (the same CTA,
+//      atomicCAS).  A poke that finds RUNNING turns it into DIRTY and the running CTA re-queues the tile itself, so two
+//      CTAs never relax the same tile concurrently and a lowered W can never be overwritten by a stale higher value.
+//   2. Publication.  The writer stores W, executes __threadfence() (release at device scope), and only then pokes the
+//      neighbour (atomicCAS on its state + atomicAdd on `tail` + volatile store of the slot).  The consumer obtains the
+//      tile id from the slot (volatile load in a spin loop), performs atomicExch(state, RUNNING) + __threadfence()
+//      (acquire) and loads W with ld.global.cg.  Slot store -> slot load is the synchronises-with edge; the fences on
+//      either side order the W stores before it and the W loads after it, so a visit triggered by a poke sees at least
+//      the values that caused the poke.  (Seeing NEWER values is harmless: W only decreases towards the fixed point.)
+//   3. Halo reads race by design.  A tile reads its neighbours' edge cells while they may be running.  Every value ever
+//      stored in W is an upper bound of the fixed point and a candidate max(z, min(neighbours)) computed from upper bounds
+//      is again an upper bound, so a stale read can only delay a lowering, never produce a wrong one; and a neighbour that
+//      lowers an edge cell afterwards pokes this tile (test in step "decide which neighbours have to look again" re-reads
+//      the halo cell from L2 before deciding), so no lowering is lost.  32-bit aligned stores / loads are single-copy
+//      atomic, and the 16-byte vector stores are four of them: a torn read mixes old and new upper bounds.
+//   4. Termination.  `pending` counts tiles queued or running: incremented before a tile id becomes visible in a slot,
+//      decremented (after a __threadfence) only when the visit's own pokes have been issued.  It can therefore reach 0
+//      only when no tile is queued, running or about to be poked, i.e. at the global fixed point; waiting CTAs leave when
+//      they read pending <= 0.  A CTA that waits longer than SPIN_LIMIT sets the sticky status word (FILL_STALLED): the
+//      finish pass poisons W[0][0] and hd_pdfill_status reports it -- a stalled fill cannot pass silently.
+//   5. Ring capacity.  A slot is written only after its previous occupant was consumed: at most ntiles entries are
+//      outstanding (one per tile: QUEUED is exclusive), the ring has ntiles + 8192 slots, consumers reset a slot to
+//      SLOT_EMPTY before using the id, and tickets (`head`) can run ahead of `tail` by at most the number of CTAs.
 struct FillCtl {
     int head, tail, pending, error;
     unsigned long long visits, changed_visits, iterations;

@@ -108,3 +108,28 @@ def test_fused_fill_d8_equals_separate_passes():
     np.testing.assert_array_equal(filled, nf.SinkFill().apply(z))
     np.testing.assert_array_equal(d8, nf.D8FlowDirection().apply(filled))
     assert fused.status() == 0 and fused.sweeps >= 1
+
+
+@pytest.mark.parametrize("ctas_per_sm", ["1", "4"])
+def test_fill_worklist_stress(ctas_per_sm, monkeypatch):
+    """The inter-CTA polling protocol of fill_async_kernel (csrc/hydro.cu: poke / ticket / pending) under different
+    amounts of concurrency, many odd shapes, NaN outlets on and off the frame, large flats: always the priority-flood
+    fixed point, status word 0.  (compute-sanitizer racecheck is closed on the measurement pool.)"""
+    from hydrodem_b200.filters import new_filters as nf
+    from oracle import hydrology
+    monkeypatch.setenv("HD_FILL_CTAS_PER_SM", ctas_per_sm)
+    rng = np.random.default_rng(int(ctas_per_sm))
+    for k in range(12):
+        ny, nx = int(rng.integers(65, 700)), int(rng.integers(65, 900))
+        z = np.round(SynthScene(ny, nx, 500 + k).srtm() * (1 + k % 3))
+        if k % 2:
+            z[ny // 3:ny // 3 + 3, nx // 4:nx // 4 + 9] = np.nan
+            z[0, nx // 2] = np.nan
+        if k % 4 == 0:
+            z[ny // 2:ny // 2 + 40, 5:nx - 5] = z.min() - 3            # a long flat trench across tiles
+        f = nf.SinkFillD8()
+        filled, d8 = f.apply(z)
+        want = hydrology.sinkfill(z)
+        np.testing.assert_array_equal(filled, want)
+        np.testing.assert_array_equal(d8, hydrology.d8(want))
+        assert f.status() == 0

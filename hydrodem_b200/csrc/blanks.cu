@@ -36,8 +36,11 @@ constexpr int NSEG = 4, SEG_ROWS = (IN_H + NSEG - 1) / NSEG;          // column 
 constexpr size_t I_BYTES = (size_t)(IN_H + 1) * IS * sizeof(double);
 constexpr size_t CTR_BYTES = (size_t)BT * BT * sizeof(float);
 constexpr size_t OFF_BYTES = (size_t)NSEG * IN_W * sizeof(double);
-constexpr size_t SMEM = STAGE + I_BYTES + CTR_BYTES + OFF_BYTES;
+constexpr int CSEG = 4, SEG_COLS = IN_W / CSEG;                       // row scans run as CSEG column segments too
+constexpr size_t ROFF_BYTES = (size_t)CSEG * IN_H * sizeof(double);
+constexpr size_t SMEM = STAGE + I_BYTES + CTR_BYTES + OFF_BYTES + ROFF_BYTES;
 static_assert(NSEG * IN_W <= BNT, "one thread per (segment, column)");
+static_assert(CSEG * IN_H <= BNT && IN_W % CSEG == 0, "one thread per (row, column segment)");
 
 template <typename MaskT>
 __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ CUtensorMap tm_in,
@@ -52,6 +55,7 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
     double* I = reinterpret_cast<double*>(smem + STAGE);       // [(IN_H + 1)][IS], I[r][c] = sum tile[<r][<c]
     float* ctrs = reinterpret_cast<float*>(smem + STAGE + I_BYTES);             // the tile's own 64 x 64 cells
     double* off = reinterpret_cast<double*>(smem + STAGE + I_BYTES + CTR_BYTES);   // [NSEG][IN_W] segment offsets
+    double* roff = off + NSEG * IN_W;                                              // [CSEG][IN_H] row-segment totals
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int t = threadIdx.x; t < IS; t += BNT) I[t] = 0.0;                    // row 0
     for (int t = threadIdx.x; t <= IN_H; t += BNT) I[t * IS] = 0.0;            // column 0
@@ -110,20 +114,34 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
             }
         }
         __syncthreads();
-        // ---- pass 2: row prefix sums, one thread per ROW runs along the columns (lanes = consecutive rows; the odd
-        //      stride IS keeps the 64-bit accesses on distinct banks); the segment offsets of pass 1 are added on the way
-        if (threadIdx.x < IN_H) {
-            double* row = I + (threadIdx.x + 1) * IS + 1;
-            const double* o = off + (threadIdx.x / SEG_ROWS) * IN_W;
+        // ---- pass 2: row prefix sums as CSEG column segments per row (472 threads x 30 dependent adds instead of 118
+        //      threads x 120: this scan was 40 % of a tile's time); the column offsets of pass 1 are added on the way, the
+        //      totals of the segments to the left are added in a third, fully parallel sweep
+        if (threadIdx.x < CSEG * IN_H) {
+            const int sg = threadIdx.x / IN_H, r = threadIdx.x - sg * IN_H;          // lanes = consecutive rows
+            double* row = I + (r + 1) * IS + 1 + sg * SEG_COLS;
+            const double* o = off + (r / SEG_ROWS) * IN_W + sg * SEG_COLS;
             double acc = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < IN_W; ++c) {
+#pragma unroll 6
+            for (int c = 0; c < SEG_COLS; ++c) {
                 acc += row[c] + o[c];
                 row[c] = acc;
             }
+            roff[sg * IN_H + r] = acc;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < IN_H * (IN_W - SEG_COLS); t += BNT) {
+            const int r = t / (IN_W - SEG_COLS), c = SEG_COLS + (t - r * (IN_W - SEG_COLS));
+            const int sg = c / SEG_COLS;
+            double add = roff[r];
+            if (sg > 1) add += roff[IN_H + r];
+            if (sg > 2) add += roff[2 * IN_H + r];
+            I[(r + 1) * IS + 1 + c] += add;
         }
         __syncthreads();
         // ---- outputs ----------------------------------------------------------------------------------------
+        // (a tile whose windows are never clipped has the same number of valid cells everywhere: 55^2 - 5^2)
+        const bool interior = ty0 >= H && ty0 + BT - 1 + H <= ny - 1 && tx0 >= H && tx0 + BT - 1 + H <= nx - 1;
 #pragma unroll
         for (int rep = 0; rep < BT * BT / BNT; ++rep) {
             const int idx = rep * BNT + threadIdx.x;
@@ -139,7 +157,8 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
                 const int64_t lo = p - h < 0 ? 0 : p - h, hi = p + h > n - 1 ? n - 1 : p + h;
                 return (int)(hi - lo + 1);
             };
-            const int cnt = span(y, ny, H) * span(x, nx, H) - span(y, ny, HI) * span(x, nx, HI);
+            const int cnt = interior ? WS * WS - INNER * INNER
+                                     : span(y, ny, H) * span(x, nx, H) - span(y, ny, HI) * span(x, nx, HI);
             const float mean = (float)((big - inner) / (double)cnt);               // np.nanmean -> float32  (:421)
             const float ctr = ctrs[idx];
             const bool hit = ctr > __fmul_rn(factor, mean);                        // centre > 4 * mean      (:424)

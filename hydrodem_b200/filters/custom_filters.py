@@ -14,7 +14,7 @@ from ..exceptions import (NumpyArrayExpectedError, WindowSizeEvenError, WindowSi
 from .extension_filters import (AbsoluteValues, Around, BinaryClosing, BinaryErosion, BitwiseXOR, Convolve,  # noqa: F401
                                 GreyDilation)
 from .simple_filters import (AdditionFilter, BooleanToInteger, GreaterThan, LowerThan, ProductFilter,     # noqa: F401
-                             SubtractionFilter)
+                             SubtractionFilter, binary_op)
 
 
 def check_window(shape, window_size):
@@ -203,15 +203,35 @@ class QuadraticFilter(WindowFilter):
 class GrovesCorrection(DeviceFilter):
     """One groves-correction pass (custom_filters.py:664-732): QuadraticFilter(15) -> dem - smooth ->
     > 1.5 -> x groves_class -> 1 - . -> x (dem - smooth) -> + smooth, fused into ONE kernel.
-    Returns float64 like the reference.  ``partial_results`` is not materialised."""
+    Returns float64 like the reference.  ``partial_results`` (the five intermediates the reference deep-copies, :728)
+    is materialised lazily, with separate kernels, only when somebody reads it."""
 
     window_size = 15
     threshold = 1.5
 
     def __init__(self, groves_class):
-        self.partial_results = []
+        self._partials = []
+        self._partials_pending = []
         self.groves_class = groves_class
         self._groves_dev = None
+
+    @property
+    def partial_results(self):
+        """[smooth, dem - smooth, (> 1.5) * 1, x groves_class, 1 - .] per apply() call, in the reference's dtypes."""
+        for src in self._partials_pending:
+            smooth = QuadraticFilter(window_size=self.window_size).run_device(src)
+            hi = binary_op(_lib.OP_RSUB, smooth, src, np.subtract)            # SubtractionFilter(minuend=dem)
+            tall = MaskTallGroves().run_device(hi)
+            g = self.groves_class if isinstance(self.groves_class, dev.DeviceRaster) else np.asarray(self.groves_class)
+            prod = ProductFilter(factor=g).run_device(tall)
+            keep = SubtractionFilter(minuend=1).run_device(prod)
+            self._partials += [dev.download(r) for r in (smooth, hi, tall, prod, keep)]
+        self._partials_pending = []
+        return self._partials
+
+    @partial_results.setter
+    def partial_results(self, value):
+        self._partials, self._partials_pending = list(value), []
 
     def _groves(self, shape):
         if self._groves_dev is None:
@@ -244,7 +264,9 @@ class GrovesCorrection(DeviceFilter):
         if not isinstance(image_to_filter, np.ndarray):
             raise NumpyArrayExpectedError(image_to_filter)
         check_window(image_to_filter.shape, self.window_size)
-        return dev.download(self.run_device(dev.upload(image_to_filter)))
+        src = dev.upload(image_to_filter)
+        self._partials_pending.append(src)
+        return dev.download(self.run_device(src))
 
 
 class GrovesCorrectionsIter(ComposedFilter):

@@ -261,3 +261,22 @@ def test_int16_input_stripe_removal():
     got = cf.DetectApplyFourier().apply(a)
     assert got.dtype == np.float64
     np.testing.assert_allclose(got, g["daf_i16"], rtol=RTOL)
+
+
+def test_groves_partial_results_are_materialised_lazily():
+    """GrovesCorrection.partial_results (custom_filters.py:728): the five intermediates, reference dtypes; computed by
+    separate kernels only when read (the fused kernel never writes them)."""
+    g = load_golden("run_stencils")
+    dem, groves = g["srtm64"], g["groves_closed"]
+    gc = cf.GrovesCorrection(groves)
+    out = gc.apply(dem)
+    assert gc._partials == [] and len(gc._partials_pending) == 1            # nothing computed yet
+    pr = gc.partial_results
+    assert len(pr) == 5 and gc.partial_results is pr
+    smooth = stencils.quadratic(dem, 15)
+    np.testing.assert_allclose(pr[0], smooth, rtol=RTOL)
+    np.testing.assert_allclose(pr[1], dem - smooth, rtol=1e-3, atol=1e-4)
+    assert pr[2].dtype == np.int64 and set(np.unique(pr[2])) <= {0, 1}
+    np.testing.assert_array_equal(pr[3], groves * pr[2])
+    np.testing.assert_array_equal(pr[4], 1 - pr[3])
+    np.testing.assert_allclose(out, pr[4] * pr[1] + pr[0], rtol=RTOL)        # (:729-731)

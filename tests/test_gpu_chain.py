@@ -75,7 +75,7 @@ def test_c2_chain_vs_oracle_at_3601():
     allowed = ndimage.binary_dilation(border, structure=np.ones((3, 3)), iterations=14)
     bad = ~np.isclose(res.srtm, want["srtm"], rtol=1e-5, atol=0)
     print("C2: groves cells on the 1.5 m threshold:", int(border.sum()), "-> cells that differ:", int(bad.sum()))
-    assert border.sum() < 200 and not (bad & ~allowed).any()
+    assert border.sum() < 1e-4 * border.size and bad.sum() <= border.sum() and not (bad & ~allowed).any()
     ok = ~ndimage.binary_dilation(allowed, structure=np.ones((3, 3)))
     np.testing.assert_allclose(res.dem_complete[~allowed], want["dem_complete"][~allowed], rtol=1e-5)
     mean = stencils.convolve_reflect(want["dem_complete"], np.ones((3, 3))) / 9

@@ -83,10 +83,13 @@ def test_banded_detect_apply_fourier_is_bit_identical(world, shape):
         np.testing.assert_array_equal(m, want_mask[(kl["ky"] + ny // 2) % ny].astype(np.uint8))
 
 
-@pytest.mark.parametrize("world,shape", [(2, (420, 333)), (3, (421, 333)), (4, (640, 300))])
-def test_banded_chain_is_bit_identical(world, shape):
-    """The whole conditioning chain on row bands against the single-GPU chain: EVERY output identical."""
+@pytest.mark.parametrize("world,shape,direct", [(2, (420, 333), "1"), (3, (421, 333), "1"), (4, (640, 300), "1"),
+                                                (3, (420, 334), "0")])
+def test_banded_chain_is_bit_identical(world, shape, direct, monkeypatch):
+    """The whole conditioning chain on row bands against the single-GPU chain: EVERY output identical -- with the
+    exchanges of the Fourier stage as peer-memory stores from the transposes (direct) and as send / recv messages."""
     from hydrodem_b200.pipeline import ConditioningChain
+    monkeypatch.setenv("HD_BAND_DIRECT", direct)
     sc = SynthScene(*shape, 81)
     srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()
     hsheds[shape[0] // 2, 40] = -32768.0                       # a void right next to a cut

@@ -324,6 +324,13 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
     return d;
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // One marching sweep of a 64-thread group through the tile: F = shared-memory step along the march, L = step to the
 // neighbouring thread's line.  A cell is relaxed against the three cells behind it and its two lateral neighbours
 // (the opposite group covers the three ahead; the check pass covers all eight).  Per step: three reads of the next
@@ -681,8 +688,19 @@ __global__ void __launch_bounds__(256) fill_finish_d8_kernel(float* __restrict__
             win[dy][0] = x0 > 0 ? __ldcg(p - 1) : 0.f;
             win[dy][1] = q[0]; win[dy][2] = q[1]; win[dy][3] = q[2]; win[dy][4] = q[3];
             win[dy][5] = x0 + 4 < nx ? __ldcg(p + 4) : 0.f;
+        }
+        // nodata cells are -inf here: only a window that holds one needs the NaN conversion (and the restore below)
+        float lowest = win[0][0];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) win[dy][j] = win[dy][j] == ninf ? qnan : win[dy][j];   // nodata
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int j = 0; j < 6; j += 2) lowest = fmin3(lowest, win[dy][j], win[dy][j + 1]);
+        const bool has_nodata = lowest == ninf;
+        if (has_nodata) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) win[dy][j] = win[dy][j] == ninf ? qnan : win[dy][j];
         }
         uint8_t codes[4] = {0, 0, 0, 0};
         bool restore = false;
@@ -690,19 +708,26 @@ __global__ void __launch_bounds__(256) fill_finish_d8_kernel(float* __restrict__
         for (int j = 0; j < 4; ++j) {
             const int64_t x = x0 + j;
             const float c = win[1][j + 1];
-            restore |= (c != c) && x < nx;
+            restore |= has_nodata && (c != c) && x < nx;
             if (y == 0 || y >= ny - 1 || x == 0 || x >= nx - 1) continue;
-            const float nb[8] = {win[1][j + 2], win[2][j + 2], win[2][j + 1], win[2][j], win[1][j], win[0][j],
-                                 win[0][j + 1], win[0][j + 2]};
-            float best = 0.f;
-            uint8_t code = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float drop = __fsub_rn(c, nb[k]);
-                if (k & 1) drop = __fmul_rn(drop, 0.70710678f);
-                if (drop > best) { best = drop; code = (uint8_t)(1u << k); }
-            }
-            codes[j] = code;
+            // E, SE, S, SW, W, NW, N, NE; diagonal drops scaled in float32
+            const float d0 = __fsub_rn(c, win[1][j + 2]), d1 = __fmul_rn(__fsub_rn(c, win[2][j + 2]), 0.70710678f);
+            const float d2 = __fsub_rn(c, win[2][j + 1]), d3 = __fmul_rn(__fsub_rn(c, win[2][j]), 0.70710678f);
+            const float d4 = __fsub_rn(c, win[1][j]), d5 = __fmul_rn(__fsub_rn(c, win[0][j]), 0.70710678f);
+            const float d6 = __fsub_rn(c, win[0][j + 1]), d7 = __fmul_rn(__fsub_rn(c, win[0][j + 2]), 0.70710678f);
+            // "first strictly larger drop wins" == the FIRST direction that attains the maximum, if it is positive
+            // (three-input max: 4 instructions; NaN drops are skipped by max and never compare equal)
+            const float best = fmax3(fmax3(d0, d1, d2), fmax3(d3, d4, d5), fmax3(d6, d7, 0.f));
+            unsigned code = 0u;
+            code = d7 == best ? 128u : code;
+            code = d6 == best ? 64u : code;
+            code = d5 == best ? 32u : code;
+            code = d4 == best ? 16u : code;
+            code = d3 == best ? 8u : code;
+            code = d2 == best ? 4u : code;
+            code = d1 == best ? 2u : code;
+            code = d0 == best ? 1u : code;
+            codes[j] = best > 0.f ? (uint8_t)code : (uint8_t)0;
         }
         if (restore) {                                                    // rare: rewrite the quad with NaN at the nodata cells
 #pragma unroll

@@ -46,22 +46,45 @@ __device__ __forceinline__ void write_bits(const uint32_t* res, OutT* out, int64
                                            int64_t ny, int64_t nx, int border, const float* __restrict__ select = nullptr,
                                            int64_t sel_pitch = 0)
 {
+    // a tile that lies inside the frame [border, n - border) needs no per-cell edge tests (almost every tile)
+    const bool inner = ty0 >= border && ty0 + TH <= ny - border && tx0 >= border && tx0 + TW <= nx - border;
 #pragma unroll
     for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
         const int idx = rep * NT + threadIdx.x;
         const int ro = idx >> 5, c4 = idx & 31;
         const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
         if (y >= ny || x >= nx) continue;
-        const uint32_t nib = (res[ro * 4 + (c4 >> 3)] >> ((c4 & 7) * 4)) & 15u;
-        const bool yin = (y >= border) && (y < ny - border);
+        uint32_t nib = (res[ro * 4 + (c4 >> 3)] >> ((c4 & 7) * 4)) & 15u;
+        if (!inner) {
+            const bool yin = (y >= border) && (y < ny - border);
+            uint32_t keep = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) keep |= (yin && (x + j >= border) && (x + j < nx - border)) ? (1u << j) : 0u;
+            nib &= keep;
+        }
+        if constexpr (sizeof(OutT) == 1) {
+            if (!select) {
+                // 0 / 1 bytes straight from the nibble: one 32-bit store
+                const uint32_t word = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                uint8_t* q = reinterpret_cast<uint8_t*>(out) + y * out_pitch + x;
+                if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+                    *reinterpret_cast<uint32_t*>(q) = word;
+                } else {
+                    for (int j = 0; j < 4; ++j)
+                        if (x + j < nx) q[j] = (uint8_t)((nib >> j) & 1u);
+                }
+                continue;
+            }
+        }
         float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (yin && (x + j >= border) && (x + j < nx - border) && ((nib >> j) & 1u)) ? 1.f : 0.f;
+        for (int j = 0; j < 4; ++j) v[j] = ((nib >> j) & 1u) ? 1.f : 0.f;
         if (select) {
             // fused ProductFilter(factor = select): factor * expanded  (TidyingLagoons, custom_filters.py:589-590, :607)
+            float sv[4];
+            gload4(select + y * sel_pitch + x, x, nx, sv);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (x + j < nx) v[j] = __fmul_rn(select[y * sel_pitch + x + j], v[j]);
+            for (int j = 0; j < 4; ++j) v[j] = __fmul_rn(sv[j], v[j]);
         }
         store4<OutT>(out, out_pitch, y, x, nx, v);
     }

@@ -41,6 +41,7 @@ SIGNATURES = {
     "hd_pack_i16": (_i, [_p, _i64, _p, _i64, _i64, _p, _p]),
     "hd_elementwise": (_i, [_i, _p, _i, _i64, _p, _i, _i64, _d, _p, _i, _i64, _i64, _i64, _p]),
     "hd_final_terms": (_i, [_p, _i, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _p]),
+    "hd_final_mean3": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p]),
     "hd_expand": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i64, _i, _p]),
     "hd_expand_select": (_i, [_p, _i, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _p]),
     "hd_majority": (_i, [_p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),

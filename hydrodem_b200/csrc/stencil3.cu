@@ -184,6 +184,79 @@ __global__ void __launch_bounds__(NT) conv3_kernel(const __grid_constant__ CUten
     });
 }
 
+
+// ---- _prepare_final_terms + the three-term sum + PostProcessingFinal in ONE pass (no rivers) ----------------------------
+// hydro_dem_process.py:60-91, :148-149 with rivers = 0:  complete = srtm * (1 - mask) + lagoon_values + hsheds * 0,
+// mask = lagoon_values > 0, then Convolve(ones(3,3)) / 9 (mode='reflect') and Around.  With 0/1 masks `complete` is
+// either the SRTM cell or the lagoon value (or NaN when a term is not finite) -- exactly a float32 -- so the staged
+// 34 x 136 block of it lives in shared memory as float32 and the 3x3 mean accumulates it in double in scipy's order:
+// the result is bit-identical to hd_final_terms + hd_convolve3, for 16 B/cell of HBM traffic instead of 40 (the float64
+// `complete` raster and the float64 copy of the rounded DEM are never written unless asked for).
+template <bool WITH_COMPLETE>
+__global__ void __launch_bounds__(NT) final_mean3_kernel(const __grid_constant__ CUtensorMap tm_srtm,
+                                                         const __grid_constant__ CUtensorMap tm_lag,
+                                                         const __grid_constant__ CUtensorMap tm_hs, float* __restrict__ out32,
+                                                         int64_t out32_pitch, double* __restrict__ complete,
+                                                         int64_t complete_pitch, int64_t ny, int64_t nx, int tiles_x, int ntiles)
+{
+    constexpr int HX = hd_halo_x(1, 4);
+    constexpr int IN_W = TW + 2 * HX;
+    constexpr uint32_t PLANE = (uint32_t)((IN_W * IN_H3 * 4 + 127) / 128 * 128);
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    float* cplt = reinterpret_cast<float*>(smem + 3 * PLANE);            // [IN_H3][IN_W]
+    const TilePlane planes[3] = {{&tm_srtm, 0u, (uint32_t)(IN_W * IN_H3 * 4), HX, 1},
+                                 {&tm_lag, PLANE, (uint32_t)(IN_W * IN_H3 * 4), HX, 1},
+                                 {&tm_hs, 2 * PLANE, (uint32_t)(IN_W * IN_H3 * 4), HX, 1}};
+    tile_loop<3, 1>(smem, 3 * PLANE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        const float* ps = reinterpret_cast<const float*>(st);
+        const float* pl = reinterpret_cast<const float*>(st + PLANE);
+        const float* ph = reinterpret_cast<const float*>(st + 2 * PLANE);
+        for (int t = threadIdx.x; t < IN_W * IN_H3; t += NT) {
+            const double s = (double)ps[t], lv = (double)pl[t];
+            const double mask = lv > 0.0 ? 1.0 : 0.0;
+            const double first = __dmul_rn(s, 1.0 - (mask + 0.0));
+            double acc = __dadd_rn(first, lv);
+            acc = __dadd_rn(acc, 0.0 * (double)ph[t]);
+            cplt[t] = (float)acc;
+            if (WITH_COMPLETE) {
+                const int r = t / IN_W, c = t - r * IN_W;
+                const int64_t y = (int64_t)ty0 - 1 + r, x = (int64_t)tx0 - HX + c;
+                if (r >= 1 && r <= TH && c >= HX && c < HX + TW && y < ny && x < nx) complete[y * complete_pitch + x] = acc;
+            }
+        }
+        __syncthreads();
+        patch_reflect<float>(cplt, IN_W, IN_H3, ty0 - 1, tx0 - HX, ny, nx);
+#pragma unroll
+        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+            const int idx = rep * NT + threadIdx.x;
+            const int ro = idx >> 5, c4 = idx & 31;
+            const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+            if (y >= ny || x >= nx) continue;
+            const float* c = cplt + ro * IN_W + 4 * c4 + HX;
+            float win[3][6];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const float4 q = *reinterpret_cast<const float4*>(c + dy * IN_W);
+                win[dy][0] = c[dy * IN_W - 1];
+                win[dy][1] = q.x; win[dy][2] = q.y; win[dy][3] = q.z; win[dy][4] = q.w;
+                win[dy][5] = c[dy * IN_W + 4];
+            }
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double acc = 0.0;                             // NI_Correlate: tmp = 0; tmp += in * w, row-major (w = 1)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) acc = __dadd_rn(acc, __dmul_rn((double)win[dy][j + dx], 1.0));
+                v[j] = (float)rint(__ddiv_rn(acc, 9.0));      // / weights.size, np.around; integer metres: exact in float32
+            }
+            store4<float>(out32, out32_pitch, y, x, nx, v);
+        }
+    });
+}
+
 template <int MODE>
 int launch_fix3(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
                 void* stream)
@@ -255,6 +328,41 @@ extern "C" int hd_convolve3(const void* in, int64_t in_pitch, void* out, int64_t
         hd_prof_begin("conv3_kernel", s);
         conv3_kernel<double><<<grid_for(ntiles, 3), NT, smem, s>>>(tm, (double*)out, out_pitch, (float*)out32, out32_pitch, ny, nx,
                                                                   p, in_w, tiles_x, ntiles);
+    }
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+// srtm (groves-corrected DEM), lagoon_values, hsheds_fixed: F32 rasters.  final32 (F32): the rounded 3x3 mean of
+// `complete` = srtm * (1 - (lagoon_values > 0)) + lagoon_values + hsheds_fixed * 0 (hydro_dem_process.py:60-91, :148-149,
+// no rivers).  complete_out (F64, may be NULL): `complete` itself.  Same bits as hd_final_terms + hd_convolve3.
+extern "C" int hd_final_mean3(const void* srtm, int64_t srtm_pitch, const void* lagoon_values, int64_t lag_pitch,
+                              const void* hsheds_fixed, int64_t hs_pitch, void* final32, int64_t final32_pitch,
+                              void* complete_out, int64_t complete_pitch, int64_t ny, int64_t nx, void* stream)
+{
+    if (!srtm || !lagoon_values || !hsheds_fixed || !final32) return HD_ERR_NULL;
+    if (ny < 1 || nx < 1 || srtm_pitch < nx || lag_pitch < nx || hs_pitch < nx || final32_pitch < nx ||
+        (complete_out && complete_pitch < nx))
+        return HD_ERR_ARG;
+    constexpr int IN_W = TW + 2 * hd_halo_x(1, 4);
+    CUtensorMap tms, tml, tmh;
+    if (int e = hd_make_tmap_2d(&tms, srtm, HD_F32, ny, nx, srtm_pitch, IN_W, IN_H3, false)) return e;
+    if (int e = hd_make_tmap_2d(&tml, lagoon_values, HD_F32, ny, nx, lag_pitch, IN_W, IN_H3, false)) return e;
+    if (int e = hd_make_tmap_2d(&tmh, hsheds_fixed, HD_F32, ny, nx, hs_pitch, IN_W, IN_H3, false)) return e;
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    const size_t plane = (IN_W * IN_H3 * 4 + 127) / 128 * 128, smem = 4 * plane;
+    cudaStream_t s = (cudaStream_t)stream;
+    hd_prof_begin("final_mean3_kernel", s);
+    if (complete_out) {
+        HD_CUDA_OK(cudaFuncSetAttribute(final_mean3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        final_mean3_kernel<true><<<grid_for(ntiles, 3), NT, smem, s>>>(tms, tml, tmh, (float*)final32, final32_pitch,
+                                                                      (double*)complete_out, complete_pitch, ny, nx, tiles_x,
+                                                                      ntiles);
+    } else {
+        HD_CUDA_OK(cudaFuncSetAttribute(final_mean3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        final_mean3_kernel<false><<<grid_for(ntiles, 3), NT, smem, s>>>(tms, tml, tmh, (float*)final32, final32_pitch, nullptr, 0,
+                                                                       ny, nx, tiles_x, ntiles);
     }
     HD_LAUNCH_CHECK();
     hd_count_launch();

@@ -266,7 +266,10 @@ class ConditioningChain:
     >>> out.final, out.filled, out.d8
     """
 
-    def __init__(self, *, groves_iterations=3, with_hydrology=True, keep_intermediates=False, fill_stats=False):
+    def __init__(self, *, groves_iterations=3, with_hydrology=True, keep_intermediates=False, fill_stats=False,
+                 keep_complete=False, fused_combine=True):
+        self.keep_complete = keep_complete    # also return / keep the float64 sum of the final terms ("dem_complete")
+        self.fused_combine = fused_combine    # False: hd_final_terms + hd_convolve3 as two kernels (tests compare both)
         self.fill_stats = fill_stats          # True: SinkFill synchronises once to report its tile-visit count
         self.groves_iterations = groves_iterations
         self.with_hydrology = with_hydrology
@@ -302,12 +305,24 @@ class ConditioningChain:
                                         prod.pitch, ny, nx, 7, dev.stream_ptr()))
         st["lagoons_values"] = tidy = ef.GreyDilation(size=(7, 7)).run_device(prod)
         fixed32 = dev.convert(fixed, _lib.F32)
+        final32 = dev.empty(ny, nx, _lib.F32, np.float32)                   # integer metres: exact in float32
+        if rivers is None and dem.dtype == _lib.F32 and self.fused_combine:
+            # no rivers: the sum of the final terms and PostProcessingFinal are ONE pass (hd_final_mean3, same bits as the
+            # two separate kernels); the float64 `complete` raster is only written when somebody wants to look at it
+            complete = dev.empty(ny, nx, _lib.F64, np.float64) if (self.keep_intermediates or self.keep_complete) else None
+            _lib.check(lib.hd_final_mean3(dem.ptr, dem.pitch, tidy.ptr, tidy.pitch, fixed32.ptr, fixed32.pitch, final32.ptr,
+                                          final32.pitch, complete.ptr if complete is not None else None,
+                                          complete.pitch if complete is not None else 0, ny, nx, dev.stream_ptr()))
+            if complete is not None:
+                st["dem_complete"] = complete
+            st["final"] = final32.with_ref(np.float64)                      # widened to the reference's float64 on download
+            st["final32"] = final32
+            return
         riv = dev.convert(rivers, _lib.F32) if rivers is not None else None
         st["dem_complete"] = complete = dev.empty(ny, nx, _lib.F64, np.float64)
         _lib.check(lib.hd_final_terms(dem.ptr, dem.dtype, dem.pitch, tidy.ptr, tidy.pitch, fixed32.ptr, fixed32.pitch,
                                       riv.ptr if riv is not None else None, riv.pitch if riv is not None else 0,
                                       complete.ptr, complete.dtype, complete.pitch, ny, nx, dev.stream_ptr()))
-        final32 = dev.empty(ny, nx, _lib.F32, np.float32)                   # integer metres: exact in float32
         st["final"] = cf.PostProcessingFinal().run_device(complete, copy32=final32)
         st["final32"] = final32
 
@@ -323,6 +338,8 @@ class ConditioningChain:
         if self.with_hydrology:
             out.update(filled=st["filled"], d8=st["d8"])
             info["fill_sweeps"] = st["fill"].sweeps
+        if self.keep_complete and "dem_complete" in st:
+            out["dem_complete"] = st["dem_complete"]
         if self.keep_intermediates:
             daf = st["daf"]
             out.update(fourier=st["fourier"], fourier_mask=daf._mask_dev, fabs=daf._fabs_dev,

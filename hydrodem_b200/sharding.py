@@ -686,13 +686,13 @@ class Band:
         return out_ext
 
     # -- the whole chain on row bands (BASELINE.json configs[4]: one mosaic over the GPUs of a box) --------------------
-    def conditioning_chain(self, srtm, groves_class, hsheds, groves_iterations=3, with_hydrology=True):
+    def conditioning_chain(self, srtm, groves_class, hsheds, groves_iterations=3, with_hydrology=True, keep_complete=False):
         """HydroDEMProcess.start (hydro_dem_process.py:122-153) on this rank's rows of a mosaic.  Inputs: device rasters
         of the band's rows (F32, U8 0/1, F32), or ExtRaster objects whose owned rows are already in place (groves,
         hsheds: saves the input copy).  Returns {"final", "dem_complete", "filled", "d8"} for the band's rows -- every
         one of them bit-identical to the single-GPU ConditioningChain on the whole mosaic."""
         from .pipeline import ConditioningChain
-        chain = ConditioningChain(groves_iterations=groves_iterations, with_hydrology=False)
+        chain = ConditioningChain(groves_iterations=groves_iterations, with_hydrology=False, keep_complete=keep_complete)
         TRACE.mark("chain:start")
         g_ext = groves_class if isinstance(groves_class, ExtRaster) else self.extended(dev.convert(groves_class, _lib.U8))
         h_ext = hsheds if isinstance(hsheds, ExtRaster) else self.extended(hsheds)
@@ -710,7 +710,9 @@ class Band:
         chain._stage_combine(st, h_ext.raster, None)                                 # LagoonsDetection ... :149
         TRACE.mark("lagoons + combine")
         own = lambda r: r.sub(self.up, self.up + self.rows, 0, self.nx)              # noqa: E731
-        out = {"final": own(st["final"]), "dem_complete": own(st["dem_complete"])}
+        out = {"final": own(st["final"])}
+        if keep_complete:
+            out["dem_complete"] = own(st["dem_complete"])
         if with_hydrology:
             out["filled"], out["d8"] = self.sinkfill(ExtRaster(st["final32"], self.up, self.rows, self.down))
             TRACE.mark("sink-fill + D8")

@@ -104,6 +104,12 @@ int hd_elementwise(int op, const void* a, int a_dtype, int64_t a_pitch, const vo
 int hd_final_terms(const void* srtm, int srtm_dtype, int64_t srtm_pitch, const void* lagoon_values, int64_t lag_pitch,
                    const void* hsheds_fixed, int64_t hs_pitch, const void* rivers, int64_t riv_pitch, void* out, int out_dtype,
                    int64_t out_pitch, int64_t ny, int64_t nx, void* stream);
+/* hd_final_terms (rivers = NULL) + hd_convolve3(ones(3,3), /9, round) in ONE pass: hydro_dem_process.py:60-91, :148-149.
+ * All inputs F32; final32 (F32) = the rounded 3x3 mean (integer metres: exact); complete_out (F64, may be NULL) = the sum
+ * of the final terms.  16 B/cell of HBM traffic instead of 40; same bits as the two separate calls. */
+int hd_final_mean3(const void* srtm, int64_t srtm_pitch, const void* lagoon_values, int64_t lag_pitch,
+                   const void* hsheds_fixed, int64_t hs_pitch, void* final32, int64_t final32_pitch, void* complete_out,
+                   int64_t complete_pitch, int64_t ny, int64_t nx, void* stream);
 
 /* ---- windowed filters (filters/custom_filters.py) ------------------------------------------------ */
 /* ExpandFilter.apply, custom_filters.py:102-125.  in: F32 or U8; out: U8 / F32 / F64, every cell written

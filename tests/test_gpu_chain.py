@@ -88,6 +88,22 @@ def test_c2_chain_vs_oracle_at_3601():
     np.testing.assert_array_equal(res.d8, hydrology.d8(res.filled))
 
 
+def test_fused_combine_equals_separate_kernels():
+    """hd_final_mean3 (final terms + 3x3 mean + round in one pass, float32 staging) against hd_final_terms + hd_convolve3:
+    same bits in every output, frame rows / columns (reflect) included; NaN and lagoon cells present."""
+    sc = SynthScene(421, 517, 19)
+    srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()
+    a = ConditioningChain(keep_complete=True).apply(srtm, groves, hsheds.copy())
+    b = ConditioningChain(keep_complete=True, fused_combine=False).apply(srtm, groves, hsheds.copy())
+    assert a.final.dtype == np.float64
+    np.testing.assert_array_equal(a.final, b.final)
+    np.testing.assert_array_equal(a.host("dem_complete"), b.host("dem_complete"))
+    np.testing.assert_array_equal(a.filled, b.filled)
+    np.testing.assert_array_equal(a.d8, b.d8)
+    c = ConditioningChain().apply(srtm, groves, hsheds.copy())             # production: `complete` is never written
+    np.testing.assert_array_equal(c.final, b.final)
+
+
 def test_chain_with_rivers():
     sc = SynthScene(200, 260, 9)
     srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()

@@ -98,7 +98,7 @@ def test_banded_chain_is_bit_identical(world, shape, direct, monkeypatch):
     def fn(comm):
         band = sharding.Band(comm, *srtm.shape)
         out = band.conditioning_chain(dev.upload(band.take(srtm)), dev.upload(band.take(groves)),
-                                      dev.upload(band.take(hsheds)))
+                                      dev.upload(band.take(hsheds)), keep_complete=True)
         return {k: dev.download(v) for k, v in out.items()}
 
     res = sharding.ThreadComm.run(world, fn)

@@ -50,6 +50,8 @@ SIGNATURES = {
     "hd_route_rivers": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _p, _i64, _p]),
     "hd_quadratic": (_i, [_p, _i64, _p, _i64, _i, _i64, _i64, _i, _p]),
     "hd_groves_correction": (_i, [_p, _i, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _i, _d, _p]),
+    "hd_groves_tile_count": (_i64, [_i64, _i64]),
+    "hd_groves_correction_tiles": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _d, _p, _i, _p]),
     "hd_median": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _i, _p]),
     "hd_hollow_mean_detect": (_i, [_p, _i64, _p, _i64, _p, _i, _i64, _p, _i64, _i64, _i64, _i, _i, _d, _p]),
     "hd_fourier_mask_assemble": (_i, [_p, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),

@@ -148,6 +148,49 @@ __device__ __forceinline__ void tile_loop(unsigned char* smem, uint32_t stage_by
     }
 }
 
+// tile_loop over the tiles whose flag is set (flags[tile] != 0), same double-buffered TMA pipeline: a skipped tile costs one
+// byte of flag traffic -- no tile load, no body, no store.  All threads walk the flag array identically.
+template <int NPLANES, class Body>
+__device__ __forceinline__ void tile_loop_flagged(unsigned char* smem, uint32_t stage_bytes, uint64_t* bars,
+                                                  const TilePlane (&planes)[NPLANES], int tile_w, int tile_h, int tiles_x,
+                                                  int ntiles, const uint8_t* __restrict__ flags, Body&& body)
+{
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+#pragma unroll
+        for (int p = 0; p < NPLANES; ++p) tma_prefetch_desc(planes[p].tm);
+    }
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for (int p = 0; p < NPLANES; ++p) total += planes[p].bytes;
+    auto issue = [&](int tile, int s) {
+        const int ty0 = (tile / tiles_x) * tile_h, tx0 = (tile % tiles_x) * tile_w;
+        mbar_arrive_expect_tx(&bars[s], total);
+#pragma unroll
+        for (int p = 0; p < NPLANES; ++p)
+            tma_load_2d(smem + s * stage_bytes + planes[p].smem_off, planes[p].tm, tx0 - planes[p].halo_x,
+                        ty0 - planes[p].halo_y, &bars[s]);
+    };
+    auto next_flagged = [&](int tile) {                       // first flagged tile of this CTA's sequence at or after `tile`
+        while (tile < ntiles && __ldg(flags + tile) == 0) tile += gridDim.x;
+        return tile;
+    };
+    int tile = next_flagged(blockIdx.x);
+    if (threadIdx.x == 0 && tile < ntiles) issue(tile, 0);
+    for (int k = 0; tile < ntiles; ++k) {
+        const int s = k & 1;
+        const int next = next_flagged(tile + gridDim.x);
+        if (threadIdx.x == 0 && next < ntiles) issue(next, s ^ 1);
+        mbar_wait(&bars[s], (k >> 1) & 1);
+        body(smem + s * stage_bytes, (tile / tiles_x) * tile_h, (tile % tiles_x) * tile_w, tile);
+        __syncthreads();
+        tile = next;
+    }
+}
+
 __device__ __forceinline__ bool hd_isnan(float v) { return v != v; }
 
 // streaming (evict-first) vector stores for outputs that are written once

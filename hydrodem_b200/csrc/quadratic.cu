@@ -37,7 +37,8 @@ template <int H, typename T, typename OutT, bool GROVES>
 __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                        const __grid_constant__ CUtensorMap tm_groves,
                                                        OutT* __restrict__ out, int64_t out_pitch, int64_t ny, int64_t nx,
-                                                       QuadParams p, int tiles_x, int ntiles)
+                                                       QuadParams p, int tiles_x, int ntiles,
+                                                       uint8_t* __restrict__ tile_flags = nullptr, int sparse = 0)
 {
     constexpr int WS = 2 * H + 1;
     constexpr int CWU = TW + 2 * H;                 // window columns touched by a tile
@@ -57,7 +58,10 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
     const TilePlane planes[2] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * sizeof(T)), HX, H},
                                  {&tm_groves, IN_BYTES, (uint32_t)(TH * TW), 0, 0}};
     const TilePlane (&used)[NP] = reinterpret_cast<const TilePlane (&)[NP]>(planes);
-    tile_loop<NP>(smem, STAGE, bars, used, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+    // Groves iterations 2, 3 ... (`sparse`): a cell without groves never changes, so the output raster -- the buffer the
+    // PREVIOUS iteration read from -- already holds it; only the tiles that contain a groves cell (tile_flags, written by the
+    // first iteration) are loaded at all, and inside them only the quads with a groves cell are stored.
+    auto body = [&](unsigned char* st, int ty0, int tx0, int tile_id) {
         const T* tile = reinterpret_cast<const T*>(st);
         const uint32_t* gwords = reinterpret_cast<const uint32_t*>(st + IN_BYTES);   // [TH][TW / 4], zero outside the raster
         // Groves tail: where groves == 0 the reference evaluates smooth + 1 * (dem - smooth), i.e. dem to the last bit or
@@ -78,6 +82,7 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
                 }
                 any_half[hf] = __syncthreads_or(any);
             }
+            if (tile_flags && !sparse && threadIdx.x == 0) tile_flags[tile_id] = (any_half[0] || any_half[1]) ? 1 : 0;
         }
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
@@ -113,6 +118,7 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
                 if (y >= ny || x >= nx) continue;
                 const uint32_t gq = GROVES ? gwords[idx] : 0u;
                 if (GROVES && gq == 0u) {                     // no groves cell in this quad: copy
+                    if (sparse) continue;                     // (the output raster already holds these cells)
                     OutT cp[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) cp[j] = (OutT)tile[(ro + H) * IN_W + 4 * c4 + j + HX];
@@ -153,12 +159,18 @@ __global__ void __launch_bounds__(NT) quadratic_kernel(const __grid_constant__ C
             }
             if (any_half[hf] && hf == 0) __syncthreads();       // the partial sums are rewritten for the second half
         }
-    });
+    };
+    if (GROVES && sparse)
+        tile_loop_flagged<NP>(smem, STAGE, bars, used, TW, TH, tiles_x, ntiles, tile_flags, body);
+    else
+        tile_loop<NP>(smem, STAGE, bars, used, TW, TH, tiles_x, ntiles,
+                      [&](unsigned char* st, int ty0, int tx0) { body(st, ty0, tx0, (ty0 / TH) * tiles_x + tx0 / TW); });
 }
 
 template <int H, typename T, typename OutT, bool GROVES>
 int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_pitch, const void* groves,
-           int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t stream)
+           int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t stream,
+           uint8_t* tile_flags = nullptr, int sparse = 0)
 {
     constexpr int CW = (TW + 2 * H + 1) / 2 * 2 + 2, IN_W = TW + 2 * hd_halo_x(H, sizeof(T)), IN_H = TH + 2 * H;
     constexpr size_t STAGE = (IN_W * IN_H * sizeof(T) + 127) / 128 * 128 + (GROVES ? TH * TW : 0);
@@ -172,7 +184,8 @@ int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_p
     auto kern = quadratic_kernel<H, T, OutT, GROVES>;
     HD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     hd_prof_begin("quadratic_kernel", stream);
-    kern<<<grid_for(ntiles, 2), NT, SMEM, stream>>>(tm, tm_g, (OutT*)out, out_pitch, ny, nx, p, tiles_x, ntiles);
+    kern<<<grid_for(ntiles, 2), NT, SMEM, stream>>>(tm, tm_g, (OutT*)out, out_pitch, ny, nx, p, tiles_x, ntiles, tile_flags,
+                                                    sparse);
     HD_LAUNCH_CHECK();
     hd_count_launch();
     return HD_OK;
@@ -180,11 +193,13 @@ int launch(const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_p
 
 template <typename T, typename OutT, bool GROVES>
 int dispatch_h(int h, const void* in, int dtype, int64_t in_pitch, void* out, int64_t out_pitch, const void* groves,
-               int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t s)
+               int64_t groves_pitch, int64_t ny, int64_t nx, const QuadParams& p, cudaStream_t s,
+               uint8_t* tile_flags = nullptr, int sparse = 0)
 {
     switch (h) {
 #define HD_Q_CASE(HH) \
-    case HH: return launch<HH, T, OutT, GROVES>(in, dtype, in_pitch, out, out_pitch, groves, groves_pitch, ny, nx, p, s);
+    case HH: return launch<HH, T, OutT, GROVES>(in, dtype, in_pitch, out, out_pitch, groves, groves_pitch, ny, nx, p, s, \
+                                                tile_flags, sparse);
         HD_Q_CASE(1) HD_Q_CASE(2) HD_Q_CASE(3) HD_Q_CASE(4) HD_Q_CASE(5) HD_Q_CASE(6) HD_Q_CASE(7)
 #undef HD_Q_CASE
         default: return HD_ERR_UNSUPPORTED;
@@ -217,7 +232,8 @@ QuadParams make_params(int ws, double thr)
 }
 
 int run(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int in_dtype, int out_dtype, const void* groves,
-        int64_t groves_pitch, int64_t ny, int64_t nx, int ws, double thr, void* stream)
+        int64_t groves_pitch, int64_t ny, int64_t nx, int ws, double thr, void* stream, uint8_t* tile_flags = nullptr,
+        int sparse = 0)
 {
     if (!in || !out) return HD_ERR_NULL;
     if (int e = check_window(ny, nx, ws)) return e;
@@ -229,7 +245,8 @@ int run(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int in_d
     const bool g = groves != nullptr;
 #define HD_Q_T(TT, TTAG, OT, OTAG)                                                                                      \
     if (in_dtype == TTAG && out_dtype == OTAG)                                                                          \
-        return g ? dispatch_h<TT, OT, true>(h, in, in_dtype, in_pitch, out, out_pitch, groves, groves_pitch, ny, nx, p, s) \
+        return g ? dispatch_h<TT, OT, true>(h, in, in_dtype, in_pitch, out, out_pitch, groves, groves_pitch, ny, nx, p, s, \
+                                            tile_flags, sparse)                                                         \
                  : dispatch_h<TT, OT, false>(h, in, in_dtype, in_pitch, out, out_pitch, groves, groves_pitch, ny, nx, p, s);
     HD_Q_T(float, HD_F32, float, HD_F32)
     HD_Q_T(float, HD_F32, double, HD_F64)
@@ -253,4 +270,23 @@ extern "C" int hd_groves_correction(const void* in, int in_dtype, int64_t in_pit
     if (!groves) return HD_ERR_NULL;
     if (groves_pitch < nx) return HD_ERR_ARG;
     return run(in, in_pitch, out, out_pitch, in_dtype, out_dtype, groves, groves_pitch, ny, nx, ws, threshold, stream);
+}
+
+// GrovesCorrectionsIter (custom_filters.py:735-767) without re-copying the cells that cannot change.  A cell outside the
+// groves class comes out of GrovesCorrection as it went in, so from the second iteration on only groves cells need work:
+//   sparse = 0  (first iteration): full pass in -> out, and tile_flags[tile] = "this 32 x 128 tile holds a groves cell"
+//   sparse = 1  (later iterations): `out` must already hold the previous iteration's INPUT (ping-pong between two rasters:
+//               iteration k writes into the buffer iteration k-1 read); only flagged tiles are loaded, only quads with a
+//               groves cell are stored.  Same bits as dense iterations.
+// tile_flags: hd_groves_tile_count(ny, nx) bytes.  F32 rasters only.
+extern "C" int64_t hd_groves_tile_count(int64_t ny, int64_t nx) { return (int64_t)hd_cdiv(ny, TH) * hd_cdiv(nx, TW); }
+
+extern "C" int hd_groves_correction_tiles(const void* in, int64_t in_pitch, const void* groves, int64_t groves_pitch, void* out,
+                                          int64_t out_pitch, int64_t ny, int64_t nx, int ws, double threshold, void* tile_flags,
+                                          int sparse, void* stream)
+{
+    if (!groves || !tile_flags) return HD_ERR_NULL;
+    if (groves_pitch < nx || in == out) return HD_ERR_ARG;
+    return run(in, in_pitch, out, out_pitch, HD_F32, HD_F32, groves, groves_pitch, ny, nx, ws, threshold, stream,
+               (uint8_t*)tile_flags, sparse ? 1 : 0);
 }

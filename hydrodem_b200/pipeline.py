@@ -267,7 +267,8 @@ class ConditioningChain:
     """
 
     def __init__(self, *, groves_iterations=3, with_hydrology=True, keep_intermediates=False, fill_stats=False,
-                 keep_complete=False, fused_combine=True):
+                 keep_complete=False, fused_combine=True, sparse_groves=True):
+        self.sparse_groves = sparse_groves    # False: every groves iteration rewrites the whole raster (tests compare both)
         self.keep_complete = keep_complete    # also return / keep the float64 sum of the final terms ("dem_complete")
         self.fused_combine = fused_combine    # False: hd_final_terms + hd_convolve3 as two kernels (tests compare both)
         self.fill_stats = fill_stats          # True: SinkFill synchronises once to report its tile-visit count
@@ -286,6 +287,26 @@ class ConditioningChain:
         """BinaryClosing of the groves class + GrovesCorrectionsIter (image_srtm.py:177-199)."""
         st["groves"] = groves = ef.BinaryClosing(structure=np.ones((3, 3))).run_device(groves_class)   # U8 0/1
         dem = st["fourier"]
+        if self.sparse_groves and dem.dtype == _lib.F32 and not self.keep_intermediates and self.groves_iterations >= 1:
+            # A cell outside the groves class leaves GrovesCorrection as it entered: after a full first pass (which also
+            # flags the tiles that hold a groves cell) the later iterations ping-pong between the two rasters and only
+            # load / store what can change (hd_groves_correction_tiles).  The stripe-free DEM's buffer is reused as the
+            # second raster (it is dead after the first iteration unless the intermediates are kept).
+            lib = _lib.load()
+            import torch
+            ny, nx = dem.shape
+            flags = torch.empty(int(lib.hd_groves_tile_count(ny, nx)), dtype=torch.uint8, device=dev.device())
+            g8 = dev.convert(groves, _lib.U8)
+            src, dst = dem, dev.empty(ny, nx, _lib.F32, np.float64)
+            for it in range(self.groves_iterations):
+                _lib.check(lib.hd_groves_correction_tiles(src.ptr, src.pitch, g8.ptr, g8.pitch, dst.ptr, dst.pitch, ny, nx,
+                                                          cf.GrovesCorrection.window_size, cf.GrovesCorrection.threshold,
+                                                          ctypes.c_void_p(flags.data_ptr()), 1 if it else 0,
+                                                          dev.stream_ptr()),
+                           window_size=cf.GrovesCorrection.window_size, shape=dem.shape)
+                src, dst = dst, src
+            st["srtm"] = src.with_ref(np.float64)
+            return
         gc = cf.GrovesCorrection(groves)
         for _ in range(self.groves_iterations):
             dem = gc.run_device(dem, out_dtype=_lib.F32)

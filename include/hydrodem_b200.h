@@ -144,6 +144,15 @@ int hd_quadratic(const void* in, int64_t in_pitch, void* out, int64_t out_pitch,
  * in: F32 or F64; groves: U8 (0/1 class mask); out: F64 (the reference's dtype), or F32 for F32 input. */
 int hd_groves_correction(const void* in, int in_dtype, int64_t in_pitch, const void* groves, int64_t groves_pitch, void* out,
                          int out_dtype, int64_t out_pitch, int64_t ny, int64_t nx, int ws, double threshold, void* stream);
+/* GrovesCorrectionsIter (custom_filters.py:735-767) without re-copying the cells that cannot change: a cell outside the
+ * groves class leaves GrovesCorrection as it entered.  sparse = 0 (first iteration): full pass, tile_flags[t] = "tile t
+ * holds a groves cell"; sparse = 1 (later iterations): `out` must already hold the previous iteration's INPUT (ping-pong
+ * between two rasters), only flagged tiles are loaded and only quads with a groves cell are stored.  F32 rasters;
+ * tile_flags: hd_groves_tile_count(ny, nx) bytes.  Same bits as dense iterations. */
+int64_t hd_groves_tile_count(int64_t ny, int64_t nx);
+int hd_groves_correction_tiles(const void* in, int64_t in_pitch, const void* groves, int64_t groves_pitch, void* out,
+                               int64_t out_pitch, int64_t ny, int64_t nx, int ws, double threshold, void* tile_flags,
+                               int sparse, void* stream);
 
 /* NEW stage (not in the reference): median filter.  F32 -> F32; interior cells =
  * np.nanmedian of the float32 ws*ws window (ws 3 or 5; corner-less if `circular`), ws/2 border copied. */

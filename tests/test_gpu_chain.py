@@ -102,6 +102,15 @@ def test_fused_combine_equals_separate_kernels():
     np.testing.assert_array_equal(a.d8, b.d8)
     c = ConditioningChain().apply(srtm, groves, hsheds.copy())             # production: `complete` is never written
     np.testing.assert_array_equal(c.final, b.final)
+    # groves iterations 2, 3 that only touch the tiles with groves cells (ping-pong rasters) against dense iterations
+    d = ConditioningChain(keep_complete=True, sparse_groves=False).apply(srtm, groves, hsheds.copy())
+    np.testing.assert_array_equal(a.host("dem_complete"), d.host("dem_complete"))
+    np.testing.assert_array_equal(a.final, d.final)
+    for iters in (1, 2, 4):
+        e = ConditioningChain(keep_complete=True, groves_iterations=iters, with_hydrology=False).apply(srtm, groves, hsheds.copy())
+        f = ConditioningChain(keep_complete=True, groves_iterations=iters, with_hydrology=False,
+                              sparse_groves=False).apply(srtm, groves, hsheds.copy())
+        np.testing.assert_array_equal(e.host("dem_complete"), f.host("dem_complete"))
 
 
 def test_chain_with_rivers():

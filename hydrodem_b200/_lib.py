@@ -54,6 +54,8 @@ SIGNATURES = {
     "hd_groves_correction_tiles": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i, _d, _p, _i, _p]),
     "hd_median": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _i, _p]),
     "hd_hollow_mean_detect": (_i, [_p, _i64, _p, _i64, _p, _i, _i64, _p, _i64, _i64, _i64, _i, _i, _d, _p]),
+    "hd_hollow_tile_count": (_i64, [_i64, _i64]),
+    "hd_hollow_mean_detect_tiles": (_i, [_p, _i64, _p, _i64, _p, _i, _i64, _p, _i64, _i64, _i64, _i, _i, _d, _p, _p, _p]),
     "hd_fourier_mask_assemble": (_i, [_p, _i64, _p, _i64, _p, _i, _i64, _i64, _i64, _i, _i, _p]),
     "hd_fft2_plan_create": (_i, [_i64, _i64, ctypes.POINTER(_p)]),
     "hd_fft2_plan_destroy": (_i, [_p]),

@@ -47,16 +47,34 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
                                                         const uint8_t* __restrict__ mask_prev, int64_t prev_pitch,
                                                         MaskT* __restrict__ mask_out, int64_t mask_pitch,
                                                         float* __restrict__ modified, int64_t mod_pitch, int64_t ny,
-                                                        int64_t nx, float factor, int tiles_x, int ntiles)
+                                                        int64_t nx, float factor, int tiles_x, int ntiles,
+                                                        uint8_t* __restrict__ flags_out = nullptr,
+                                                        const uint8_t* __restrict__ flags_in = nullptr)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
-    const float* tile = reinterpret_cast<const float*>(smem);
-    double* I = reinterpret_cast<double*>(smem + STAGE);       // [(IN_H + 1)][IS], I[r][c] = sum tile[<r][<c]
-    float* ctrs = reinterpret_cast<float*>(smem + STAGE + I_BYTES);             // the tile's own 64 x 64 cells
-    double* off = reinterpret_cast<double*>(smem + STAGE + I_BYTES + CTR_BYTES);   // [NSEG][IN_W] segment offsets
-    double* roff = off + NSEG * IN_W;                                              // [CSEG][IN_H] row-segment totals
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Second BlanksFourier pass (flags_in): it runs on image * (1 - mask of the first pass), which differs from the image
+    // only at the first pass's hits.  A cell whose 55 x 55 window holds no such hit sees the same centre and the same mean as
+    // in the first pass, where it was not a hit -- so new hits can only appear within 27 cells of an old one, and a 64 x 64
+    // tile needs the second pass only if its 3 x 3 tile neighbourhood had a hit in the first (flags_out of that pass).
+    // Peaks are rare (1e-7 .. 1e-4 of the bins): every other tile keeps the previous mask, which mask_widen_kernel (a
+    // streaming pass at full occupancy, launched right before this kernel) has already written into mask_out.  Same bits.
+    const int tiles_y = ntiles / tiles_x;
+    auto active = [&](int t) -> bool {
+        if (!flags_in) return true;
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        int any = 0;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = ty + dy, xx = tx + dx;
+                if (yy >= 0 && yy < tiles_y && xx >= 0 && xx < tiles_x) any |= __ldg(flags_in + yy * tiles_x + xx);
+            }
+        return any != 0;
+    };
+    auto advance = [&](int t) -> int {                       // skipped tiles keep the previous mask (mask_widen_kernel)
+        while (t < ntiles && !active(t)) t += gridDim.x;
+        return t;
+    };
     for (int t = threadIdx.x; t < IS; t += BNT) I[t] = 0.0;                    // row 0
     for (int t = threadIdx.x; t <= IN_H; t += BNT) I[t * IS] = 0.0;            // column 0
     if (threadIdx.x == 0) {
@@ -70,9 +88,9 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
         mbar_arrive_expect_tx(&bar, (uint32_t)(IN_W * IN_H * 4));
         tma_load_2d(smem, &tm_in, tx0 - HX, ty0 - H, &bar);
     };
-    if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x);
-    int k = 0;
-    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++k) {
+    int tl = advance(blockIdx.x);
+    if (threadIdx.x == 0 && tl < ntiles) issue(tl);
+    for (int k = 0; tl < ntiles; ++k) {
         const int ty0 = (tl / tiles_x) * BT, tx0 = (tl % tiles_x) * BT;
         // the previous pass's mask for this thread's outputs: requested now, needed at the very end of the tile
         uint8_t prevs[BT * BT / BNT];
@@ -103,7 +121,8 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
         }
         __syncthreads();
         // the staged tile is no longer needed: fetch the next one underneath the rest of this tile's work
-        if (threadIdx.x == 0 && tl + (int)gridDim.x < ntiles) issue(tl + gridDim.x);
+        const int tl_next = advance(tl + gridDim.x);
+        if (threadIdx.x == 0 && tl_next < ntiles) issue(tl_next);
         if (threadIdx.x < IN_W) {                                  // segment totals -> exclusive offsets
             double run = 0.0;
 #pragma unroll
@@ -140,6 +159,7 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
         }
         __syncthreads();
         // ---- outputs ----------------------------------------------------------------------------------------
+        bool hit_any = false;
         // (a tile whose windows are never clipped has the same number of valid cells everywhere: 55^2 - 5^2)
         const bool interior = ty0 >= H && ty0 + BT - 1 + H <= ny - 1 && tx0 >= H && tx0 + BT - 1 + H <= nx - 1;
 #pragma unroll
@@ -162,11 +182,37 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
             const float mean = (float)((big - inner) / (double)cnt);               // np.nanmean -> float32  (:421)
             const float ctr = ctrs[idx];
             const bool hit = ctr > __fmul_rn(factor, mean);                        // centre > 4 * mean      (:424)
+            hit_any |= hit;
             const uint8_t prev = prevs[rep];
             mask_out[y * mask_pitch + x] = (MaskT)(prev + (hit ? 1 : 0));          // final_mask += filtered (:461)
             if (modified) modified[y * mod_pitch + x] = __fmul_rn(ctr, hit ? 0.f : 1.f);   // image * (1 - mask) (:426)
         }
-        __syncthreads();                                           // I, ctrs and off are rewritten by the next tile
+        const int tile_hit = __syncthreads_or(hit_any);            // (also: I, ctrs and off are rewritten by the next tile)
+        if (flags_out && threadIdx.x == 0) flags_out[tl] = tile_hit ? 1 : 0;
+        tl = tl_next;
+    }
+}
+
+// mask_out = (MaskT) mask_prev (or 0) for the whole raster: eight cells per thread, one 8-byte load, two 16-byte stores
+template <typename MaskT>
+__global__ void __launch_bounds__(256) mask_widen_kernel(const uint8_t* __restrict__ prev, int64_t prev_pitch,
+                                                         MaskT* __restrict__ out, int64_t out_pitch, int64_t ny, int64_t nx)
+{
+    const int64_t nx8 = (nx + 7) / 8;
+    for (CellIter it(nx8); it.y < ny; it.next()) {
+        const int64_t y = it.y, x = 8 * it.x;
+        MaskT* q = out + y * out_pitch + x;
+        const uint8_t* pp = prev ? prev + y * prev_pitch + x : nullptr;
+        if (x + 7 < nx && sizeof(MaskT) == 4 && ((reinterpret_cast<uintptr_t>(q) & 15) == 0) &&
+            (!pp || (reinterpret_cast<uintptr_t>(pp) & 7) == 0)) {
+            const uint2 b = pp ? __ldg(reinterpret_cast<const uint2*>(pp)) : make_uint2(0u, 0u);
+            st_cs_f32x4(reinterpret_cast<float*>(q), (float)(b.x & 255u), (float)((b.x >> 8) & 255u),
+                        (float)((b.x >> 16) & 255u), (float)(b.x >> 24));
+            st_cs_f32x4(reinterpret_cast<float*>(q) + 4, (float)(b.y & 255u), (float)((b.y >> 8) & 255u),
+                        (float)((b.y >> 16) & 255u), (float)(b.y >> 24));
+        } else {
+            for (int j = 0; j < 8 && x + j < nx; ++j) q[j] = (MaskT)(pp ? __ldg(pp + j) : (uint8_t)0);
+        }
     }
 }
 
@@ -228,9 +274,9 @@ __global__ void __launch_bounds__(256) assemble_kernel(const uint8_t* __restrict
 
 }  // namespace
 
-extern "C" int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch,
-                                     void* mask_out, int mask_dtype, int64_t mask_pitch, void* modified, int64_t mod_pitch,
-                                     int64_t ny, int64_t nx, int ws, int inner, double factor, void* stream)
+static int hollow_run(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch, void* mask_out,
+                      int mask_dtype, int64_t mask_pitch, void* modified, int64_t mod_pitch, int64_t ny, int64_t nx, int ws,
+                      int inner, double factor, void* flags_out, const void* flags_in, void* stream)
 {
     if (!in || !mask_out) return HD_ERR_NULL;
     if (ws > ny || ws > nx) return HD_ERR_WINDOW_HIGH;
@@ -242,21 +288,57 @@ extern "C" int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const voi
     if (int e = hd_make_tmap_2d(&tm, in, HD_F32, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
     const int tiles_x = hd_cdiv(nx, BT), tiles_y = hd_cdiv(ny, BT), ntiles = tiles_x * tiles_y;
     const int grid = ntiles < hd_num_sms() ? ntiles : hd_num_sms();
+    if (flags_in) {                                            // the restricted pass leaves untouched tiles to this copy
+        const int64_t total = ny * ((nx + 7) / 8);
+        const int blocks = (int)((total + 255) / 256 < (int64_t)hd_num_sms() * 16 ? (total + 255) / 256 : hd_num_sms() * 16);
+        hd_prof_begin("mask_widen_kernel", (cudaStream_t)stream);
+        if (mask_dtype == HD_U8)
+            mask_widen_kernel<uint8_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)mask_prev, prev_pitch,
+                                                                               (uint8_t*)mask_out, mask_pitch, ny, nx);
+        else
+            mask_widen_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)mask_prev, prev_pitch,
+                                                                             (float*)mask_out, mask_pitch, ny, nx);
+        HD_LAUNCH_CHECK(); hd_count_launch();
+    }
     hd_prof_begin("hollow_kernel", (cudaStream_t)stream);
     if (mask_dtype == HD_U8) {
         HD_CUDA_OK(cudaFuncSetAttribute(hollow_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         hollow_kernel<uint8_t><<<grid, BNT, SMEM, (cudaStream_t)stream>>>(
             tm, (const uint8_t*)mask_prev, prev_pitch, (uint8_t*)mask_out, mask_pitch, (float*)modified, mod_pitch, ny, nx,
-            (float)factor, tiles_x, ntiles);
+            (float)factor, tiles_x, ntiles, (uint8_t*)flags_out, (const uint8_t*)flags_in);
     } else {
         HD_CUDA_OK(cudaFuncSetAttribute(hollow_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         hollow_kernel<float><<<grid, BNT, SMEM, (cudaStream_t)stream>>>(
             tm, (const uint8_t*)mask_prev, prev_pitch, (float*)mask_out, mask_pitch, (float*)modified, mod_pitch, ny, nx,
-            (float)factor, tiles_x, ntiles);
+            (float)factor, tiles_x, ntiles, (uint8_t*)flags_out, (const uint8_t*)flags_in);
     }
     HD_LAUNCH_CHECK();
     hd_count_launch();
     return HD_OK;
+}
+
+extern "C" int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch,
+                                     void* mask_out, int mask_dtype, int64_t mask_pitch, void* modified, int64_t mod_pitch,
+                                     int64_t ny, int64_t nx, int ws, int inner, double factor, void* stream)
+{
+    return hollow_run(in, in_pitch, mask_prev, prev_pitch, mask_out, mask_dtype, mask_pitch, modified, mod_pitch, ny, nx, ws,
+                      inner, factor, nullptr, nullptr, stream);
+}
+
+// The two passes of DetectBlanksFourier (custom_filters.py:441-462) with the second one restricted to where it can find
+// anything: flags_out (pass 1) receives one byte per 64 x 64 tile, "a hit in this tile"; flags_in (pass 2, modified must be
+// NULL) makes the pass run only on tiles whose 3 x 3 tile neighbourhood was flagged -- everywhere else the accumulated mask
+// is the previous mask (see hollow_kernel).  hd_hollow_tile_count(ny, nx) bytes per flag array.
+extern "C" int64_t hd_hollow_tile_count(int64_t ny, int64_t nx) { return (int64_t)hd_cdiv(ny, BT) * hd_cdiv(nx, BT); }
+
+extern "C" int hd_hollow_mean_detect_tiles(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch,
+                                           void* mask_out, int mask_dtype, int64_t mask_pitch, void* modified,
+                                           int64_t mod_pitch, int64_t ny, int64_t nx, int ws, int inner, double factor,
+                                           void* flags_out, const void* flags_in, void* stream)
+{
+    if (flags_in && modified) return HD_ERR_ARG;
+    return hollow_run(in, in_pitch, mask_prev, prev_pitch, mask_out, mask_dtype, mask_pitch, modified, mod_pitch, ny, nx, ws,
+                      inner, factor, flags_out, flags_in, stream);
 }
 
 extern "C" int hd_fourier_mask_assemble(const void* q1, int64_t q1_pitch, const void* q2, int64_t q2_pitch, void* out,

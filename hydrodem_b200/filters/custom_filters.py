@@ -394,16 +394,20 @@ BLANKS_INNER = 5               # BlanksFourier (custom_filters.py:419)
 BLANKS_FACTOR = 4.0            # centre > 4 * mean (custom_filters.py:424)
 
 
-def _hollow_pass(src_f32, prev_mask, window_size, last=False):
+def _hollow_pass(src_f32, prev_mask, window_size, last=False, flags_out=None, flags_in=None):
     """One BlanksFourier pass on the device -> (accumulated mask, modified image F32).  ``last``: the mask is
-    stored as float32 (what IsolatedPoints reads next) and the modified image is not written."""
+    stored as float32 (what IsolatedPoints reads next) and the modified image is not written.  ``flags_out`` /
+    ``flags_in``: per-tile hit flags (torch uint8) written by a first pass / restricting a second pass to the tiles
+    where it can find anything (hd_hollow_mean_detect_tiles)."""
     mask = dev.empty(src_f32.ny, src_f32.nx, _lib.F32 if last else _lib.U8, np.float64)
     mod = None if last else dev.empty(src_f32.ny, src_f32.nx, _lib.F32, np.float64)
     pp, ppitch = (prev_mask.ptr, prev_mask.pitch) if prev_mask is not None else (None, 0)
     mp, mpitch = (mod.ptr, mod.pitch) if mod is not None else (None, 0)
-    _lib.check(_lib.load().hd_hollow_mean_detect(src_f32.ptr, src_f32.pitch, pp, ppitch, mask.ptr, mask.dtype, mask.pitch,
-                                                 mp, mpitch, src_f32.ny, src_f32.nx, int(window_size), BLANKS_INNER,
-                                                 BLANKS_FACTOR, dev.stream_ptr()),
+    fo = ctypes.c_void_p(flags_out.data_ptr()) if flags_out is not None else None
+    fi = ctypes.c_void_p(flags_in.data_ptr()) if flags_in is not None else None
+    _lib.check(_lib.load().hd_hollow_mean_detect_tiles(src_f32.ptr, src_f32.pitch, pp, ppitch, mask.ptr, mask.dtype,
+                                                       mask.pitch, mp, mpitch, src_f32.ny, src_f32.nx, int(window_size),
+                                                       BLANKS_INNER, BLANKS_FACTOR, fo, fi, dev.stream_ptr()),
                window_size=window_size, shape=src_f32.shape)
     return mask, mod
 
@@ -434,9 +438,15 @@ class DetectBlanksFourier(WindowFilter):
 
     def run_device(self, raster):
         check_window(raster.shape, BLANKS_WINDOW)
+        import os
+        import torch
         src = as_f32(raster)
-        mask, mod = _hollow_pass(src, None, BLANKS_WINDOW)
-        mask, _ = _hollow_pass(mod, mask, BLANKS_WINDOW, last=True)
+        flags = None
+        if os.environ.get("HD_HOLLOW_DENSE") != "1":               # (tests compare with the dense second pass)
+            n = int(_lib.load().hd_hollow_tile_count(src.ny, src.nx))
+            flags = torch.empty(n, dtype=torch.uint8, device=dev.device())
+        mask, mod = _hollow_pass(src, None, BLANKS_WINDOW, flags_out=flags)
+        mask, _ = _hollow_pass(mod, mask, BLANKS_WINDOW, last=True, flags_in=flags)
         return mask
 
 

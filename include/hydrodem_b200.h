@@ -174,6 +174,14 @@ int hd_route_rivers(const void* mask, int64_t mask_pitch, void* g, int64_t g_pit
 int hd_hollow_mean_detect(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch, void* mask_out,
                           int mask_dtype, int64_t mask_pitch, void* modified, int64_t mod_pitch, int64_t ny, int64_t nx,
                           int ws, int inner, double factor, void* stream);
+/* The same with per-tile bookkeeping for DetectBlanksFourier's two passes (custom_filters.py:441-462): the second pass runs
+ * on image * (1 - first mask), so it can only find new hits within 27 cells of an old one.  flags_out (pass 1): one byte per
+ * 64 x 64 tile, "a hit in this tile"; flags_in (pass 2; modified must be NULL): only tiles whose 3 x 3 tile neighbourhood
+ * was flagged are processed, everywhere else mask_out = mask_prev.  hd_hollow_tile_count(ny, nx) bytes per array. */
+int64_t hd_hollow_tile_count(int64_t ny, int64_t nx);
+int hd_hollow_mean_detect_tiles(const void* in, int64_t in_pitch, const void* mask_prev, int64_t prev_pitch, void* mask_out,
+                                int mask_dtype, int64_t mask_pitch, void* modified, int64_t mod_pitch, int64_t ny, int64_t nx,
+                                int ws, int inner, double factor, void* flags_out, const void* flags_in, void* stream);
 /* FourierProcessQuarters._fill_complete_quarters / _getting_reversed_masks / _fill_complete_mask,
  * custom_filters.py:968-1050.  q1, q2: U8 masks of the two upper quarters, each (ny/2 - margin, nx/2 - margin);
  * out (U8 / F32 / F64, ny x nx) = assembled point-symmetric mask, or 1 - mask when `invert`. */

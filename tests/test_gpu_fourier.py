@@ -280,3 +280,22 @@ def test_groves_partial_results_are_materialised_lazily():
     np.testing.assert_array_equal(pr[3], groves * pr[2])
     np.testing.assert_array_equal(pr[4], 1 - pr[3])
     np.testing.assert_allclose(out, pr[4] * pr[1] + pr[0], rtol=RTOL)        # (:729-731)
+
+
+def test_second_blanks_pass_only_near_first_hits(monkeypatch):
+    """DetectBlanksFourier's second pass is restricted to the tiles whose 3 x 3 tile neighbourhood had a hit in the first
+    (new hits can only appear within 27 cells of an old one): same mask as two dense passes, on a spectrum with isolated
+    and clustered peaks, hits on tile corners and on the quarter's edges."""
+    rng = np.random.default_rng(11)
+    q = (rng.random((700, 833)).astype(np.float32) + 0.5) * 100
+    for (y, x) in ((0, 0), (63, 63), (64, 64), (127, 500), (128, 501), (350, 400), (351, 430), (699, 832), (300, 0)):
+        q[y, x] = 5000.0
+    q[200:203, 600:603] = 900.0                                   # a cluster: second-pass hits next to first-pass hits
+    q[201, 601] = 20000.0
+    sparse = cf.DetectBlanksFourier().apply(q)
+    monkeypatch.setenv("HD_HOLLOW_DENSE", "1")
+    dense = cf.DetectBlanksFourier().apply(q)
+    np.testing.assert_array_equal(sparse, dense)
+    assert dense.sum() >= 10 and dense.max() >= 1
+    want = stencils.detect_blanks_fourier(q)
+    np.testing.assert_array_equal(sparse, want)

@@ -51,6 +51,13 @@ __global__ void __launch_bounds__(BNT, 1) hollow_kernel(const __grid_constant__ 
                                                         uint8_t* __restrict__ flags_out = nullptr,
                                                         const uint8_t* __restrict__ flags_in = nullptr)
 {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const float* tile = reinterpret_cast<const float*>(smem);
+    double* I = reinterpret_cast<double*>(smem + STAGE);       // [(IN_H + 1)][IS], I[r][c] = sum tile[<r][<c]
+    float* ctrs = reinterpret_cast<float*>(smem + STAGE + I_BYTES);             // the tile's own 64 x 64 cells
+    double* off = reinterpret_cast<double*>(smem + STAGE + I_BYTES + CTR_BYTES);   // [NSEG][IN_W] segment offsets
+    double* roff = off + NSEG * IN_W;                                              // [CSEG][IN_H] row-segment totals
     // Second BlanksFourier pass (flags_in): it runs on image * (1 - mask of the first pass), which differs from the image
     // only at the first pass's hits.  A cell whose 55 x 55 window holds no such hit sees the same centre and the same mean as
     // in the first pass, where it was not a hit -- so new hits can only appear within 27 cells of an old one, and a 64 x 64

@@ -297,6 +297,122 @@ __global__ void __launch_bounds__(NT) maxfilter_kernel(const __grid_constant__ C
     });
 }
 
+
+// ------------------------------------------------------------------------------------------------ TidyingLagoons, fused
+// custom_filters.py:587-610 as ONE kernel: BinaryErosion(iterations=2, cross) -> ExpandFilter(7) -> x majority image ->
+// GreyDilation(7x7, reflect).  The majority tile is staged once with a halo of 2 + 3 + 3 = 8 cells; erosion and expansion
+// run on bit rows in shared memory, the product and the separable 7x7 maximum on a 38 x 136 float array -- 4 B read +
+// 4 B written per cell instead of three kernels with a uint8 and two float32 rasters in between.  Same bits as
+// hd_binary_morph + hd_expand_select + hd_max_filter.
+constexpr int TL_H = 8;                                   // halo
+constexpr int TL_IN_W = TW + 2 * TL_H, TL_IN_H = TH + 2 * TL_H;      // 144 x 48
+constexpr int TL_PW = TW + 8, TL_PH = TH + 6;             // product array: box columns 4 .. 139, box rows 5 .. 42
+constexpr uint32_t TL_STAGE = TL_IN_W * TL_IN_H * 4;
+
+__global__ void __launch_bounds__(NT) tidy_lagoons_kernel(const __grid_constant__ CUtensorMap tm_in, float* __restrict__ out,
+                                                          int64_t out_pitch, int64_t ny, int64_t nx, int tiles_x, int ntiles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t bufA[(TL_IN_H + 2) * NWORD], bufB[(TL_IN_H + 2) * NWORD];
+    __shared__ uint32_t hfull[TL_IN_H * NWORD], hinner[TL_IN_H * NWORD], ex[TL_PH * NWORD];
+    float* prod = reinterpret_cast<float*>(smem + 2 * TL_STAGE);        // [TL_PH][TL_PW]
+    float* hmax = prod + TL_PH * TL_PW;                                  // [TL_PH][TW]
+    const TilePlane planes[1] = {{&tm_in, 0u, TL_STAGE, TL_H, TL_H}};
+    for (int t = threadIdx.x; t < NWORD; t += NT) bufA[t] = bufB[t] = 0u;                       // zero guard rows
+    tile_loop<1>(smem, TL_STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
+        const float* tile = reinterpret_cast<const float*>(st);
+        uint32_t* cur = bufA + NWORD;
+        uint32_t* nxt = bufB + NWORD;
+        // scipy: non-zero elements are True (NaN != 0 is true); cells outside the raster arrive as 0 = border_value
+        tile_to_bits<float>(tile, TL_IN_W, TL_IN_H, cur, [](float v) { return v != 0.f; });
+        if (threadIdx.x < NWORD) { cur[TL_IN_H * NWORD + threadIdx.x] = 0u; nxt[TL_IN_H * NWORD + threadIdx.x] = 0u; }
+        __syncthreads();
+        for (int step = 0; step < 2; ++step) {                           // BinaryErosion(iterations=2), cross
+            for (int t = threadIdx.x; t < TL_IN_H * NWORD; t += NT) {
+                const int r = t / NWORD, k = t - r * NWORD;
+                const uint32_t* rc = cur + r * NWORD;
+                const uint32_t c = rc[k];
+                const uint32_t lft = (c << 1) | (k > 0 ? rc[k - 1] >> 31 : 0u);
+                const uint32_t rgt = (c >> 1) | (k + 1 < NWORD ? rc[k + 1] << 31 : 0u);
+                nxt[t] = c & lft & rgt & rc[k - NWORD] & rc[k + NWORD];
+            }
+            __syncthreads();
+            uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+        }
+        // ExpandFilter(7): windows written by their FIRST column c' (output column c looks at bit c - 3)
+        for (int t = threadIdx.x; t < TL_IN_H * NWORD; t += NT) {
+            const int r = t / NWORD, k = t - r * NWORD;
+            const uint64_t w = win64(cur + r * NWORD, k);
+            uint64_t f = w, in = 0;
+#pragma unroll
+            for (int sft = 1; sft <= 6; ++sft) {
+                f |= w >> sft;
+                if (sft <= 5) in |= w >> sft;
+            }
+            hfull[t] = (uint32_t)f;
+            hinner[t] = (uint32_t)in;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < TL_PH * NWORD; t += NT) {
+            const int pr = t / NWORD, k = t - pr * NWORD, r = pr + 5;    // box row
+            uint32_t acc = hinner[(r - 3) * NWORD + k] | hinner[(r + 3) * NWORD + k];   // corner-less top / bottom rows
+#pragma unroll
+            for (int q = r - 2; q <= r + 2; ++q) acc |= hfull[q * NWORD + k];
+            ex[t] = acc;
+        }
+        __syncthreads();
+        // product with the majority image (ProductFilter(factor=majority), :607); ExpandFilter leaves its 3-cell frame at 0
+        for (int t = threadIdx.x; t < TL_PH * TL_PW; t += NT) {
+            const int pr = t / TL_PW, pc = t - pr * TL_PW;
+            const int r = pr + 5, c = pc + 4;                            // box coordinates
+            const int64_t y = (int64_t)ty0 - TL_H + r, x = (int64_t)tx0 - TL_H + c;
+            const int cb = c - 3;                                        // first column of the window
+            const bool bit = cb >= 0 && ((ex[pr * NWORD + (cb >> 5)] >> (cb & 31)) & 1u);
+            const bool inside = y >= 3 && y < ny - 3 && x >= 3 && x < nx - 3;
+            prod[t] = __fmul_rn(tile[r * TL_IN_W + c], (bit && inside) ? 1.f : 0.f);
+        }
+        __syncthreads();
+        // GreyDilation(size=(7, 7)), mode='reflect'
+        patch_reflect<float>(prod, TL_PW, TL_PH, ty0 - 3, tx0 - 4, ny, nx);
+        for (int t = threadIdx.x; t < TL_PH * (TW / 4); t += NT) {
+            const int r = t / (TW / 4), c = 4 * (t - r * (TW / 4));
+            const float* src = prod + r * TL_PW + c + 1;                 // output column c looks at array columns c+1 .. c+7
+            float v[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) v[k] = src[k];
+            float mid = v[3];
+#pragma unroll
+            for (int k = 4; k <= 6; ++k) mid = fmaxf(mid, v[k]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float mm = mid;
+#pragma unroll
+                for (int k = j; k < 3; ++k) mm = fmaxf(mm, v[k]);
+#pragma unroll
+                for (int k = 7; k <= 6 + j; ++k) mm = fmaxf(mm, v[k]);
+                hmax[r * TW + c + j] = mm;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
+            const int idx = rep * NT + threadIdx.x;
+            const int ro = idx >> 5, c4 = idx & 31;
+            const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
+            if (y >= ny || x >= nx) continue;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = hmax[ro * TW + 4 * c4 + j];
+#pragma unroll
+            for (int sft = 1; sft <= 6; ++sft)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], hmax[(ro + sft) * TW + 4 * c4 + j]);
+            store4v<float>(out, out_pitch, y, x, nx, v);
+        }
+    });
+}
+
 template <typename InT, typename OutT>
 int launch_expand(const CUtensorMap& tm, void* out, int64_t out_pitch, int64_t ny, int64_t nx, int h, int in_w, int in_h,
                   cudaStream_t stream, const float* select = nullptr, int64_t sel_pitch = 0)
@@ -440,6 +556,26 @@ extern "C" int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_
         maxfilter_kernel<double, 0><<<grid_for(ntiles, 1), NT, smem, s>>>(tm, (double*)out, out_pitch, ny, nx, h, in_w, in_h,
                                                                          tiles_x, ntiles);
     }
+    HD_LAUNCH_CHECK();
+    hd_count_launch();
+    return HD_OK;
+}
+
+// TidyingLagoons.apply (custom_filters.py:587-610) in one kernel: majority (F32) -> lagoon values (F32).
+extern "C" int hd_tidy_lagoons(const void* majority, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx,
+                               void* stream)
+{
+    if (!majority || !out) return HD_ERR_NULL;
+    if (int e = check_window(ny, nx, 7)) return e;
+    if (in_pitch < nx || out_pitch < nx || majority == out) return HD_ERR_ARG;
+    CUtensorMap tm;
+    if (int e = hd_make_tmap_2d(&tm, majority, HD_F32, ny, nx, in_pitch, TL_IN_W, TL_IN_H, false)) return e;
+    const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;
+    const size_t smem = 2 * (size_t)TL_STAGE + (size_t)TL_PH * TL_PW * 4 + (size_t)TL_PH * TW * 4;
+    HD_CUDA_OK(cudaFuncSetAttribute(tidy_lagoons_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hd_prof_begin("tidy_lagoons_kernel", (cudaStream_t)stream);
+    tidy_lagoons_kernel<<<grid_for(ntiles, 2), NT, smem, (cudaStream_t)stream>>>(tm, (float*)out, out_pitch, ny, nx, tiles_x,
+                                                                              ntiles);
     HD_LAUNCH_CHECK();
     hd_count_launch();
     return HD_OK;

@@ -267,7 +267,8 @@ class ConditioningChain:
     """
 
     def __init__(self, *, groves_iterations=3, with_hydrology=True, keep_intermediates=False, fill_stats=False,
-                 keep_complete=False, fused_combine=True, sparse_groves=True):
+                 keep_complete=False, fused_combine=True, sparse_groves=True, fused_lagoons=True):
+        self.fused_lagoons = fused_lagoons    # False: TidyingLagoons as three kernels (tests compare both)
         self.sparse_groves = sparse_groves    # False: every groves iteration rewrites the whole raster (tests compare both)
         self.keep_complete = keep_complete    # also return / keep the float64 sum of the final terms ("dem_complete")
         self.fused_combine = fused_combine    # False: hd_final_terms + hd_convolve3 as two kernels (tests compare both)
@@ -320,11 +321,18 @@ class ConditioningChain:
         dem = st["srtm"]
         st["hsheds_nan_fixed"] = fixed = cf.CorrectNANValues().run_device(hsheds)
         st["majority"] = majority = cf.MajorityFilter(window_size=11).run_device(fixed)
-        eroded = ef.BinaryErosion(iterations=2).run_device(majority)
-        prod = dev.empty(ny, nx, _lib.F32, np.float64)                      # majority * expand(7): one fused kernel
-        _lib.check(lib.hd_expand_select(eroded.ptr, eroded.dtype, eroded.pitch, majority.ptr, majority.pitch, prod.ptr,
-                                        prod.pitch, ny, nx, 7, dev.stream_ptr()))
-        st["lagoons_values"] = tidy = ef.GreyDilation(size=(7, 7)).run_device(prod)
+        if self.fused_lagoons and majority.dtype == _lib.F32:
+            # TidyingLagoons as one kernel (erode x2 -> expand 7 -> x majority -> max 7x7): hd_tidy_lagoons
+            tidy = dev.empty(ny, nx, _lib.F32, np.float64)
+            _lib.check(lib.hd_tidy_lagoons(majority.ptr, majority.pitch, tidy.ptr, tidy.pitch, ny, nx, dev.stream_ptr()),
+                       window_size=7, shape=(ny, nx))
+            st["lagoons_values"] = tidy
+        else:
+            eroded = ef.BinaryErosion(iterations=2).run_device(majority)
+            prod = dev.empty(ny, nx, _lib.F32, np.float64)                  # majority * expand(7): one fused kernel
+            _lib.check(lib.hd_expand_select(eroded.ptr, eroded.dtype, eroded.pitch, majority.ptr, majority.pitch, prod.ptr,
+                                            prod.pitch, ny, nx, 7, dev.stream_ptr()))
+            st["lagoons_values"] = tidy = ef.GreyDilation(size=(7, 7)).run_device(prod)
         fixed32 = dev.convert(fixed, _lib.F32)
         final32 = dev.empty(ny, nx, _lib.F32, np.float32)                   # integer metres: exact in float32
         if rivers is None and dem.dtype == _lib.F32 and self.fused_combine:

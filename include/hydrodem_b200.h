@@ -277,6 +277,11 @@ int hd_binary_morph(const void* in, int in_dtype, int64_t in_pitch, void* out, i
  * mode='reflect'.  dtype F32 or F64 (in and out alike).  NaN cells are skipped by the maximum (inputs are NaN-free in the chain). */
 int hd_max_filter(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int dtype, int64_t ny, int64_t nx,
                   int size, void* stream);
+/* TidyingLagoons.apply, custom_filters.py:587-610, as ONE kernel: BinaryErosion(iterations=2) -> ExpandFilter(7) ->
+ * x majority image -> GreyDilation(7x7).  majority, out: F32.  Same bits as hd_binary_morph + hd_expand_select +
+ * hd_max_filter, 8 B/cell of HBM traffic instead of ~22. */
+int hd_tidy_lagoons(const void* majority, int64_t in_pitch, void* out, int64_t out_pitch, int64_t ny, int64_t nx,
+                    void* stream);
 /* Convolve.apply + Around.apply = PostProcessingFinal, extension_filters.py:166-184, :113-130,
  * custom_filters.py:1124-1125.  3x3 correlation with `weights` (9 doubles, row-major, already reversed for
  * a convolution), mode='reflect', double accumulator in row-major order (scipy NI_Correlate), result cast

@@ -106,6 +106,12 @@ def test_fused_combine_equals_separate_kernels():
     d = ConditioningChain(keep_complete=True, sparse_groves=False).apply(srtm, groves, hsheds.copy())
     np.testing.assert_array_equal(a.host("dem_complete"), d.host("dem_complete"))
     np.testing.assert_array_equal(a.final, d.final)
+    # TidyingLagoons as one kernel (hd_tidy_lagoons) against erosion + expand-select + max filter
+    g = ConditioningChain(keep_intermediates=True, fused_lagoons=False).apply(srtm, groves, hsheds.copy())
+    h = ConditioningChain(keep_intermediates=True).apply(srtm, groves, hsheds.copy())
+    np.testing.assert_array_equal(h.host("lagoons_values"), g.host("lagoons_values"))
+    assert np.count_nonzero(h.host("lagoons_values")) > 0
+    np.testing.assert_array_equal(h.final, g.final)
     for iters in (1, 2, 4):
         e = ConditioningChain(keep_complete=True, groves_iterations=iters, with_hydrology=False).apply(srtm, groves, hsheds.copy())
         f = ConditioningChain(keep_complete=True, groves_iterations=iters, with_hydrology=False,

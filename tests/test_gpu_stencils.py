@@ -189,3 +189,29 @@ def test_int16_production_dtype_lagoons():
         assert got.dtype == g["lag_" + k].dtype, k
         np.testing.assert_array_equal(got, g["lag_" + k])
     np.testing.assert_array_equal(ret, g["lag_return"])
+
+
+@pytest.mark.parametrize("shape", [(97, 131), (64, 128), (33, 260), (300, 7), (7, 300), (161, 129)])
+def test_tidy_lagoons_fused_kernel(shape):
+    """hd_tidy_lagoons (custom_filters.py:587-610 in one kernel) against the four filter classes and the oracle: blobs on
+    the frame, across tile seams (x = 128, y = 32) and thin ones that the erosion removes."""
+    from hydrodem_b200 import _lib, device as dev
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    ny, nx = shape
+    maj = np.zeros(shape, dtype=np.float32)
+    for _ in range(12):
+        y, x = rng.integers(0, ny), rng.integers(0, nx)
+        hh, ww = rng.integers(1, 14), rng.integers(1, 14)
+        maj[max(0, y - hh):y + hh, max(0, x - ww):x + ww] = rng.integers(1, 4)
+    maj[rng.random(shape) < 0.01] = 0
+    lib = _lib.load()
+    src = dev.upload(maj)
+    out = dev.empty(ny, nx, _lib.F32, np.float64)
+    _lib.check(lib.hd_tidy_lagoons(src.ptr, src.pitch, out.ptr, out.pitch, ny, nx, dev.stream_ptr()))
+    got = dev.download(out)
+    eroded = ef.BinaryErosion(iterations=2).apply(maj)
+    expanded = cf.ExpandFilter(window_size=7).apply(eroded)
+    want = ef.GreyDilation(size=(7, 7)).apply(sf.ProductFilter(factor=maj).apply(expanded))
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got, cf.TidyingLagoons().apply(maj))
+    np.testing.assert_array_equal(got, chain.tidying_lagoons(maj))

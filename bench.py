@@ -376,8 +376,8 @@ def run_gpu(args):
 
     def e2e_step():
         if world == 1:
-            out = chain.apply(host["srtm"], host["groves"], host["hsheds"])
-            got = (out.final, out.filled, out.d8)                          # host arrays, copies complete
+            out = chain.apply_to_host(host["srtm"], host["groves"], host["hsheds"])    # three streams, eager kernels
+            got = (out["final"], out["filled"], out["d8"])                 # host arrays, copies complete
         else:
             out = band.apply_to_host(host["srtm"], host["groves"], host["hsheds"])
             got = (out["final"], out["filled"], out["d8"])
@@ -459,7 +459,7 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": cells / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
-                    "api": ("hydrodem_b200.pipeline.ConditioningChain().apply(srtm, groves, hsheds) -> .final / .filled / .d8"
+                    "api": ("hydrodem_b200.pipeline.ConditioningChain().apply_to_host(srtm, groves, hsheds) -> final / filled / d8 ndarrays"
                             if world == 1 else
                             "hydrodem_b200.sharding.Band(comm, ny, nx).apply_to_host(srtm_rows, groves_rows, hsheds_rows)"),
                     "host": {"cpus": len(os.sched_getaffinity(0)), "ranks_on_box": env_int("LOCAL_WORLD_SIZE", 1)}},

@@ -23,17 +23,21 @@ constexpr int MNT = 512;   // threads per CTA: 2 CTAs x 16 warps per SM (the ker
 
 struct BM { float c; int n; };
 
+// Both updates are written as selects: with `if` chains the compiler emits a divergent branch (BSSY / BRA / BSYNC) per
+// element, ~15 instructions per push; the kernel is bound by its instruction count (ncu: 360 instructions per cell).
 __device__ __forceinline__ void bm_push(BM& s, float v)
 {
-    if (s.n == 0) { s.c = v; s.n = 1; }
-    else if (v == s.c) ++s.n;            // NaN == x is false: every NaN is its own key (custom_filters.py:69)
-    else --s.n;
+    const bool z = (s.n == 0);
+    s.c = z ? v : s.c;
+    // NaN == x is false: every NaN is its own key (custom_filters.py:69); an empty summary adopts v, NaN included
+    s.n += (z || v == s.c) ? 1 : -1;
 }
 __device__ __forceinline__ void bm_merge(BM& s, float c2, int n2)
 {
-    if (c2 == s.c) s.n += n2;
-    else if (n2 > s.n) { s.c = c2; s.n = n2 - s.n; }
-    else s.n -= n2;
+    const bool eq = (c2 == s.c);
+    const int d = s.n - n2;
+    s.c = (!eq && d < 0) ? c2 : s.c;
+    s.n = eq ? s.n + n2 : abs(d);
 }
 
 template <int H, typename OutT>
@@ -115,13 +119,23 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
                         }
                         if (count >= min_count) result = first;        // count > (ws^2-1)*0.7  (:71-72)
                     } else {
-                        // any other value: equal floats are the same bits, the candidate itself is the first key
+                        // any other value: equal floats are the same bits, the candidate itself is the first key.
+                        // A column whose summary counter equals its height is one repeated value: its count is known
+                        // without a look at the cells (the whole window inside a lagoon plateau); only mixed columns
+                        // are counted cell by cell.
+#pragma unroll 1
+                        for (int d = 0; d < WS; ++d) {
+                            const bool outer = (d == 0 || d == WS - 1);
+                            const int rows = outer ? WS - 2 : WS;
+                            const float cd = outer ? cand_in[base + d] : cand_fu[base + d];
+                            const int nd = outer ? (int)cnt_in[base + d] : (int)cnt_fu[base + d];
+                            if (nd == rows) {
+                                count += (cd == b.c) ? rows : 0;
+                            } else {
+                                const float* col = w + d;
 #pragma unroll
-                        for (int dy = 0; dy < WS; ++dy) {
-#pragma unroll
-                            for (int dx = 0; dx < WS; ++dx) {
-                                if ((dy == 0 || dy == WS - 1) && (dx == 0 || dx == WS - 1)) continue;   // NaN corners
-                                count += (w[dy * IN_W + dx] == b.c);
+                                for (int dy = 1; dy < WS - 1; ++dy) count += (col[dy * IN_W] == b.c);
+                                if (!outer) count += (col[0] == b.c) + (col[(WS - 1) * IN_W] == b.c);
                             }
                         }
                         if (count >= min_count) result = b.c;

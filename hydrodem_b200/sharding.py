@@ -686,7 +686,8 @@ class Band:
         return out_ext
 
     # -- the whole chain on row bands (BASELINE.json configs[4]: one mosaic over the GPUs of a box) --------------------
-    def conditioning_chain(self, srtm, groves_class, hsheds, groves_iterations=3, with_hydrology=True, keep_complete=False):
+    def conditioning_chain(self, srtm, groves_class, hsheds, groves_iterations=3, with_hydrology=True, keep_complete=False,
+                           ready=None, on_ready=None):
         """HydroDEMProcess.start (hydro_dem_process.py:122-153) on this rank's rows of a mosaic.  Inputs: device rasters
         of the band's rows (F32, U8 0/1, F32), or ExtRaster objects whose owned rows are already in place (groves,
         hsheds: saves the input copy).  Returns {"final", "dem_complete", "filled", "d8"} for the band's rows -- every
@@ -696,12 +697,23 @@ class Band:
         TRACE.mark("chain:start")
         g_ext = groves_class if isinstance(groves_class, ExtRaster) else self.extended(dev.convert(groves_class, _lib.U8))
         h_ext = hsheds if isinstance(hsheds, ExtRaster) else self.extended(hsheds)
-        if isinstance(g_ext, ExtRaster) and groves_class is g_ext:
-            self.exchange_halo(g_ext)
-        if isinstance(h_ext, ExtRaster) and hsheds is h_ext:
-            self.exchange_halo(h_ext)
-        TRACE.mark("input halos")
+        cur = torch.cuda.current_stream()
+
+        def input_halos():
+            for name, ext, given in (("groves", g_ext, groves_class), ("hsheds", h_ext, hsheds)):
+                if ready and ready.get(name) is not None:
+                    cur.wait_event(ready[name])
+                if given is ext:
+                    self.exchange_halo(ext)
+            TRACE.mark("input halos")
+
+        if ready is None:
+            input_halos()
+        elif ready.get("srtm") is not None:
+            cur.wait_event(ready["srtm"])
         dem = self.detect_apply_fourier(srtm)                                        # image_srtm.py:125-126
+        if ready is not None:
+            input_halos()                                 # their uploads ran underneath the Fourier stage
         self.exchange_halo(dem)
         TRACE.mark("dem halo")
         st = {"fourier": dem.raster}
@@ -711,11 +723,16 @@ class Band:
         TRACE.mark("lagoons + combine")
         own = lambda r: r.sub(self.up, self.up + self.rows, 0, self.nx)              # noqa: E731
         out = {"final": own(st["final"])}
+        if on_ready:
+            on_ready("final", out["final"])
         if keep_complete:
             out["dem_complete"] = own(st["dem_complete"])
         if with_hydrology:
             out["filled"], out["d8"] = self.sinkfill(ExtRaster(st["final32"], self.up, self.rows, self.down))
             TRACE.mark("sink-fill + D8")
+            if on_ready:
+                on_ready("filled", out["filled"])
+                on_ready("d8", out["d8"])
         return out
 
     # -- sink-fill + D8 -----------------------------------------------------------------------------------------------------
@@ -828,11 +845,42 @@ class Band:
                 raise NumpyArrayExpectedError(a)
             if a.shape != (self.rows, self.nx):
                 raise ValueError(f"expected this rank's rows {(self.rows, self.nx)}, got {a.shape}")
+        # three streams: the SRTM rows go up first, groves + HydroSHEDS follow underneath the Fourier stage, and the
+        # final DEM travels down while the sink-fill rounds run (what ConditioningChain.apply_to_host does on one GPU)
         cur = torch.cuda.current_stream()
-        srtm = dev.upload(np.ascontiguousarray(srtm_rows, dtype=np.float32))
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        up, down = self._copy_streams
         g_ext, h_ext = self.alloc_ext(_lib.U8, np.uint8), self.alloc_ext(_lib.F32, np.float32)
+        up.wait_stream(cur)
+        ready, keep = {}, []
+
+        def send_up(name, host, into=None):
+            if into is None:
+                r, ready[name] = dev.upload_async(host, up)
+            else:
+                r, ready[name] = into, dev.upload_into(into, host, up)
+            if not dev._is_pinned(host):
+                up.synchronize()                              # a pageable source may be released by the caller
+            keep.append(host)
+            return r
+
+        srtm = send_up("srtm", np.ascontiguousarray(srtm_rows, dtype=np.float32))
         g = np.ascontiguousarray(groves_rows)
-        dev.upload_into(g_ext.owned(), g.view(np.uint8) if g.dtype == np.bool_ else g.astype(np.uint8, copy=False), cur)
-        dev.upload_into(h_ext.owned(), np.ascontiguousarray(hsheds_rows, dtype=np.float32), cur)
-        out = self.conditioning_chain(srtm, g_ext, h_ext)
-        return {k: dev.download(out[k]) for k in ("final", "filled", "d8")}
+        send_up("groves", g.view(np.uint8) if g.dtype == np.bool_ else g.astype(np.uint8, copy=False), g_ext.owned())
+        send_up("hsheds", np.ascontiguousarray(hsheds_rows, dtype=np.float32), h_ext.owned())
+        pending = {}
+
+        def send_down(name, raster):
+            conv = dev.convert(raster, dev.hd_dtype_of(raster.ref_dtype))
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            down.wait_event(ev)
+            pending[name] = dev.download_async(conv, down) + (conv,)
+
+        self.conditioning_chain(srtm, g_ext, h_ext, ready=ready, on_ready=send_down)
+        out = {}
+        for name, (host, ev, _conv) in pending.items():
+            ev.synchronize()
+            out[name] = host
+        return out

@@ -142,6 +142,22 @@ def test_apply_to_host_matches_lazy_path():
         np.testing.assert_array_equal(b["final"], a.final)
         np.testing.assert_array_equal(b["filled"], a.filled)
         np.testing.assert_array_equal(b["d8"], a.d8)
+    # mosaic-sized rasters take the eager three-stream path (no captured slot): pageable and pinned inputs
+    from hydrodem_b200 import device as dev
+    chain.eager_cells = 0
+    pinned = []
+    for arr in (srtm, groves.astype(np.uint8), hsheds):
+        p = dev.pinned_empty(arr.shape, arr.dtype)
+        p[...] = arr
+        pinned.append(p)
+    for args in ((srtm, groves, hsheds.copy()), tuple(pinned), tuple(pinned)):
+        b = chain.apply_to_host(*args)
+        assert b["final"].dtype == np.float64 and b["filled"].dtype == np.float32 and b["d8"].dtype == np.uint8
+        np.testing.assert_array_equal(b["final"], a.final)
+        np.testing.assert_array_equal(b["filled"], a.filled)
+        np.testing.assert_array_equal(b["d8"], a.d8)
+    assert chain.last_transfer_bytes == (srtm.nbytes + groves.size + hsheds.nbytes,
+                                         8 * srtm.size + 4 * srtm.size + srtm.size)
 
 
 def test_captured_graph_matches_eager():

@@ -109,3 +109,34 @@ def test_banded_chain_is_bit_identical(world, shape, direct, monkeypatch):
     np.testing.assert_array_equal(got["d8"], ref.d8)
     np.testing.assert_array_equal(got["filled"], hydrology.sinkfill(got["final"]))
     np.testing.assert_array_equal(got["d8"], hydrology.d8(got["filled"]))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_banded_apply_to_host_is_bit_identical(world):
+    """Band.apply_to_host (copies on their own streams, underneath the kernels) returns the single-GPU bits; pageable and
+    pinned inputs, called twice (recycled buffers)."""
+    from hydrodem_b200.pipeline import ConditioningChain
+    sc = SynthScene(420, 333, 83)
+    srtm, groves, hsheds = sc.srtm(), sc.groves(), sc.hsheds()
+    ref = ConditioningChain().apply(srtm, groves, hsheds.copy())
+
+    def fn(comm):
+        band = sharding.Band(comm, *srtm.shape)
+        rows = [np.ascontiguousarray(band.take(a)) for a in (srtm, groves.astype(np.uint8), hsheds)]
+        pinned = []
+        for a in rows:
+            p = dev.pinned_empty(a.shape, a.dtype)
+            p[...] = a
+            pinned.append(p)
+        a = band.apply_to_host(*rows)
+        b = band.apply_to_host(*pinned)
+        b = {k: v.copy() for k, v in band.apply_to_host(*pinned).items()}
+        return a, b
+
+    res = sharding.ThreadComm.run(world, fn)
+    for which in (0, 1):
+        got = {k: np.concatenate([r[which][k] for r in res]) for k in ("final", "filled", "d8")}
+        assert got["final"].dtype == np.float64 and got["filled"].dtype == np.float32 and got["d8"].dtype == np.uint8
+        np.testing.assert_array_equal(got["final"], ref.final)
+        np.testing.assert_array_equal(got["filled"], ref.filled)
+        np.testing.assert_array_equal(got["d8"], ref.d8)

@@ -10,7 +10,7 @@
 //   2. merges 2h+1 column summaries per output cell (the two outer columns use the inner-row summary:
 //      that is exactly the corner-less footprint),
 //   3. verifies the candidate with an exact count only where the summary counter leaves the threshold
-//      reachable: true_count <= (n_window + counter) / 2.
+//      reachable: true_count <= (n_window + counter) / 2 -- warp-cooperatively, by column counts.
 // This kernel is ALU / shared-memory bound, not HBM bound: ~8 B/cell of HBM traffic
 // against a few hundred shared-memory operations per cell.
 #include "common.cuh"
@@ -19,7 +19,8 @@
 namespace {
 
 constexpr int STRIP = 8;   // output rows per column-summary work item
-constexpr int MNT = 512;   // threads per CTA: 2 CTAs x 16 warps per SM (the kernel is latency / ALU bound)
+constexpr int MNT = 576;   // threads per CTA: the (TW + 2h) x 4 column-summary items of a tile in ONE pass (h <= 7)
+constexpr int MCELL = 512; // of which the first 16 warps merge / verify (8 output cells each)
 
 struct BM { float c; int n; };
 
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
     constexpr uint32_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bars[2];
+    __shared__ uint32_t colcnt[MCELL / 32][32 + 2 * H + 2];             // per warp: candidate counts of 32 + 2H window columns
     float* cand_in = reinterpret_cast<float*>(smem + 2 * STAGE);       // [TH][CW] summary over the 2H-1 inner rows
     float* cand_fu = cand_in + TH * CW;                                // [TH][CW] summary over all 2H+1 rows
     uint8_t* cnt_in = reinterpret_cast<uint8_t*>(cand_fu + TH * CW);
@@ -85,64 +87,74 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
         }
         __syncthreads();
         // ---- 2. merge + 3. verify -------------------------------------------------------------------
+        // A warp works on 32 consecutive cells of one output row.  The verification is WARP-COOPERATIVE: for each distinct
+        // candidate among the lanes that need one (almost always a single value: the level of the plateau the warp
+        // touches), lane j counts the candidate in window column j (and lanes 0 .. 2H-1 in column 32 + j): 42 column
+        // counts of 11 cells instead of 32 window counts of 117, then every lane adds up its 2H+1 columns.
+        if (threadIdx.x < MCELL) {
+            const int lane = threadIdx.x & 31;
+            uint32_t* cc = colcnt[threadIdx.x >> 5];
 #pragma unroll 1
-        for (int rep = 0; rep < TH * TW / MNT; ++rep) {
-            const int idx = rep * MNT + threadIdx.x;
-            const int ro = idx / TW, xo = idx % TW;
-            const int64_t y = ty0 + ro, x = tx0 + xo;
-            if (y >= ny || x >= nx) continue;
-            float result = 0.f;                                        // np.zeros border / no majority (:66)
-            if (y >= H && y < ny - H && x >= H && x < nx - H) {
-                const int base = ro * CW + xo;
-                BM b{cand_in[base], (int)cnt_in[base]};
+            for (int rep = 0; rep < TH * TW / MCELL; ++rep) {
+                const int idx = rep * MCELL + threadIdx.x;
+                const int ro = idx / TW, xo = idx % TW;
+                const int64_t y = ty0 + ro, x = tx0 + xo;
+                const bool valid = y < ny && x < nx;
+                float result = 0.f;                                    // np.zeros border / no majority (:66)
+                BM b{0.f, 0};
+                bool plausible = false;
+                if (valid && y >= H && y < ny - H && x >= H && x < nx - H) {
+                    const int base = ro * CW + xo;
+                    b.c = cand_in[base];
+                    b.n = (int)cnt_in[base];
 #pragma unroll
-                for (int d = 1; d <= 2 * H - 1; ++d) bm_merge(b, cand_fu[base + d], (int)cnt_fu[base + d]);
-                bm_merge(b, cand_in[base + 2 * H], (int)cnt_in[base + 2 * H]);
-                // true count of the candidate <= (NWIN + counter) / 2
-                if (NWIN + b.n >= 2 * min_count) {
-                    const float* w = tile + ro * IN_W + xo + XOFF;     // top-left of the window
-                    int count = 0;
-                    if (b.c == 0.f) {
-                        // Counter keeps the first-inserted key of an == class: +0.0 and -0.0 need the scan order
-                        float first = b.c;
-                        bool found = false;
+                    for (int d = 1; d <= 2 * H - 1; ++d) bm_merge(b, cand_fu[base + d], (int)cnt_fu[base + d]);
+                    bm_merge(b, cand_in[base + 2 * H], (int)cnt_in[base + 2 * H]);
+                    // true count of the candidate <= (NWIN + counter) / 2; a NaN is its own key (count 1 < min_count)
+                    plausible = (NWIN + b.n >= 2 * min_count) && (b.c == b.c);
+                }
+                unsigned need = __ballot_sync(0xffffffffu, plausible);
+                const float* w0 = tile + ro * IN_W + (xo - lane) + XOFF;       // window column 0 of the warp's first cell
+#pragma unroll 1
+                while (need) {
+                    const float c = __shfl_sync(0xffffffffu, b.c, __ffs(need) - 1);
 #pragma unroll
-                        for (int dy = 0; dy < WS; ++dy) {
+                    for (int part = 0; part < 2; ++part) {
+                        const int j = part == 0 ? lane : 32 + (lane < 2 * H ? lane : 0);
+                        const float* col = w0 + j;
+                        int inner = 0;
 #pragma unroll
-                            for (int dx = 0; dx < WS; ++dx) {
+                        for (int dy = 1; dy < WS - 1; ++dy) inner += (col[dy * IN_W] == c);
+                        const int full = inner + (col[0] == c) + (col[(WS - 1) * IN_W] == c);
+                        if (part == 0 || lane < 2 * H) cc[j] = (uint32_t)full | ((uint32_t)inner << 16);
+                    }
+                    __syncwarp();
+                    uint32_t sum = 0;
+#pragma unroll
+                    for (int d = 1; d <= 2 * H - 1; ++d) sum += cc[lane + d];
+                    // the two outer columns without their end cells: the corner-less footprint
+                    const int count = (int)(sum & 0xffffu) + (int)(cc[lane] >> 16) + (int)(cc[lane + 2 * H] >> 16);
+                    __syncwarp();
+                    const bool mine = plausible && (b.c == c);
+                    if (mine && count >= min_count) {                  // count > (ws^2-1)*0.7  (:71-72)
+                        result = b.c;
+                        if (b.c == 0.f) {
+                            // Counter keeps the first-inserted key of an == class: +0.0 / -0.0 by the scan order
+                            const float* w = w0 + lane;
+                            bool found = false;
+#pragma unroll 1
+                            for (int k = 1; k < WS * WS - 1 && !found; ++k) {
+                                const int dy = k / WS, dx = k - dy * WS;
                                 if ((dy == 0 || dy == WS - 1) && (dx == 0 || dx == WS - 1)) continue;   // NaN corners
                                 const float v = w[dy * IN_W + dx];
-                                const bool eq = (v == b.c);
-                                if (eq && !found) { first = v; found = true; }
-                                count += eq;
+                                if (v == 0.f) { result = v; found = true; }
                             }
                         }
-                        if (count >= min_count) result = first;        // count > (ws^2-1)*0.7  (:71-72)
-                    } else {
-                        // any other value: equal floats are the same bits, the candidate itself is the first key.
-                        // A column whose summary counter equals its height is one repeated value: its count is known
-                        // without a look at the cells (the whole window inside a lagoon plateau); only mixed columns
-                        // are counted cell by cell.
-#pragma unroll 1
-                        for (int d = 0; d < WS; ++d) {
-                            const bool outer = (d == 0 || d == WS - 1);
-                            const int rows = outer ? WS - 2 : WS;
-                            const float cd = outer ? cand_in[base + d] : cand_fu[base + d];
-                            const int nd = outer ? (int)cnt_in[base + d] : (int)cnt_fu[base + d];
-                            if (nd == rows) {
-                                count += (cd == b.c) ? rows : 0;
-                            } else {
-                                const float* col = w + d;
-#pragma unroll
-                                for (int dy = 1; dy < WS - 1; ++dy) count += (col[dy * IN_W] == b.c);
-                                if (!outer) count += (col[0] == b.c) + (col[(WS - 1) * IN_W] == b.c);
-                            }
-                        }
-                        if (count >= min_count) result = b.c;
                     }
+                    need &= ~__ballot_sync(0xffffffffu, mine);
                 }
+                if (valid) out[y * out_pitch + x] = (OutT)result;
             }
-            out[y * out_pitch + x] = (OutT)result;
         }
     });
 }

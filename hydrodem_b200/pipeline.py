@@ -259,6 +259,77 @@ class _StreamSlot:
         return collect
 
 
+class NarrowDownload:
+    """The final DEM holds integer metres (hydro_dem_process.py:149 rounds it): it crosses PCIe as int16 (a quarter of the
+    float64 bytes) in row chunks on the ``down`` stream, and a helper thread widens each chunk to float64 on the host's
+    cores as it lands -- underneath the sink-fill and the download of the filled DEM.  hd_pack_i16 raises a device flag
+    if any value is not an int16 integer; ``result()`` fetches the float64 raster itself then.  Same bits either way."""
+
+    def __init__(self, raster, cur, down, threads=None, chunks=8):
+        import threading
+        import torch
+        lib = _lib.load()
+        ny, nx = raster.shape
+        self.raster = raster
+        dense = torch.empty((ny, nx), dtype=torch.int16, device=dev.device())
+        flag = torch.zeros(1, dtype=torch.int32, device=dev.device())
+        with torch.cuda.stream(cur):
+            _lib.check(lib.hd_pack_i16(raster.ptr, raster.pitch, ctypes.c_void_p(dense.data_ptr()), ny, nx,
+                                       ctypes.c_void_p(flag.data_ptr()), dev.stream_ptr()))
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        down.wait_event(ev)
+        dense.record_stream(down)
+        flag.record_stream(down)
+        flag_host = dev.pinned_empty((1,), np.int32)
+        _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(flag_host.ctypes.data), 4, ctypes.c_void_p(flag.data_ptr()), 4, 4, 1,
+                                       ctypes.c_void_p(down.cuda_stream)))
+        host16 = dev.pinned_empty((ny, nx), np.int16)
+        self.wide = wide = dev.pinned_empty((ny, nx), np.float64)
+        parts = []
+        step = max(1, -(-ny // chunks))
+        for a in range(0, ny, step):
+            b = min(ny, a + step)
+            nbytes = (b - a) * nx * 2
+            _lib.check(lib.hd_memcpy2d_d2h(ctypes.c_void_p(host16[a:b].ctypes.data), nbytes,
+                                           ctypes.c_void_p(dense.data_ptr() + a * nx * 2), nbytes, nbytes, 1,
+                                           ctypes.c_void_p(down.cuda_stream)))
+            done = torch.cuda.Event()
+            done.record(down)
+            parts.append((a, b, done))
+        self.nbytes, self.extra_bytes = host16.nbytes + 4, 0
+        self.state = state = {"inexact": False, "error": None}
+        device_index = torch.cuda.current_device()
+        if threads is None:
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+            threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(local, 1)))
+
+        def widen():
+            try:
+                torch.cuda.set_device(device_index)
+                for a, b, done in parts:
+                    done.synchronize()
+                    if int(flag_host[0]) != 0:                         # copied before the first chunk
+                        state["inexact"] = True
+                        return
+                    _lib.check(lib.hd_host_widen_i16(ctypes.c_void_p(wide[a:b].ctypes.data), _lib.F64,
+                                                     ctypes.c_void_p(host16[a:b].ctypes.data), (b - a) * nx, threads))
+            except Exception as exc:     # noqa: BLE001  (re-raised on the calling thread)
+                state["error"] = exc
+
+        self.thread = threading.Thread(target=widen, name="hydrodem-widen")
+        self.thread.start()
+
+    def result(self):
+        self.thread.join()
+        if self.state["error"] is not None:
+            raise self.state["error"]
+        if self.state["inexact"]:
+            self.wide = dev.download(self.raster)                      # float64 over PCIe after all
+            self.extra_bytes = self.wide.nbytes
+        return self.wide
+
+
 class ConditioningChain:
     """Run the whole chain on the GPU.
 
@@ -271,6 +342,8 @@ class ConditioningChain:
         self.fused_lagoons = fused_lagoons    # False: TidyingLagoons as three kernels (tests compare both)
         # apply_to_host: rasters of at least this many cells run eagerly on three streams instead of captured slots
         self.eager_cells = int(os.environ.get("HD_EAGER_CELLS", str(64 << 20)))
+        # ... and send the final DEM (integer metres) down as int16, widened to float64 by host threads as it lands
+        self.narrow_final = os.environ.get("HD_NARROW_FINAL", "1") != "0"
         self.sparse_groves = sparse_groves    # False: every groves iteration rewrites the whole raster (tests compare both)
         self.keep_complete = keep_complete    # also return / keep the float64 sum of the final terms ("dem_complete")
         self.fused_combine = fused_combine    # False: hd_final_terms + hd_convolve3 as two kernels (tests compare both)
@@ -318,9 +391,14 @@ class ConditioningChain:
     def _stage_combine(self, st, hsheds, rivers):
         """LagoonsDetection (custom_filters.py:633-661, float32 / uint8 intermediates), the sum of the final terms
         (hydro_dem_process.py:60-91, :148) and PostProcessingFinal (:149), float64 like the reference."""
+        self._stage_lagoons(st, hsheds)
+        self._stage_final(st, rivers)
+
+    def _stage_lagoons(self, st, hsheds):
+        """The HydroSHEDS branch up to the lagoon values: independent of the SRTM branch (run_device runs it before the
+        groves stage, so that an overlapped upload can bring HydroSHEDS second and the groves mask last)."""
         lib = _lib.load()
         ny, nx = hsheds.shape
-        dem = st["srtm"]
         st["hsheds_nan_fixed"] = fixed = cf.CorrectNANValues().run_device(hsheds)
         st["majority"] = majority = cf.MajorityFilter(window_size=11).run_device(fixed)
         if self.fused_lagoons and majority.dtype == _lib.F32:
@@ -335,6 +413,11 @@ class ConditioningChain:
             _lib.check(lib.hd_expand_select(eroded.ptr, eroded.dtype, eroded.pitch, majority.ptr, majority.pitch, prod.ptr,
                                             prod.pitch, ny, nx, 7, dev.stream_ptr()))
             st["lagoons_values"] = tidy = ef.GreyDilation(size=(7, 7)).run_device(prod)
+
+    def _stage_final(self, st, rivers):
+        lib = _lib.load()
+        dem, fixed, tidy = st["srtm"], st["hsheds_nan_fixed"], st["lagoons_values"]
+        ny, nx = dem.shape
         fixed32 = dev.convert(fixed, _lib.F32)
         final32 = dev.empty(ny, nx, _lib.F32, np.float32)                   # integer metres: exact in float32
         if rivers is None and dem.dtype == _lib.F32 and self.fused_combine:
@@ -396,12 +479,13 @@ class ConditioningChain:
         st = {}
         need("srtm")
         self._stage_fourier(st, srtm)
+        need("hsheds")
+        self._stage_lagoons(st, hsheds)                       # independent of the SRTM branch
         need("groves")
         self._stage_groves(st, groves_class)
-        need("hsheds")
         if rivers is not None:
             need("rivers")
-        self._stage_combine(st, hsheds, rivers)
+        self._stage_final(st, rivers)
         emit("final")
         if self.with_hydrology:
             self._stage_hydrology(st)
@@ -529,8 +613,8 @@ class ConditioningChain:
         """apply_to_host for a mosaic-sized raster: the same three streams, but the kernels are launched eagerly -- a
         captured slot would pin the whole working set of a 36000^2 mosaic in a private graph pool, and ~45 launches are
         nothing against 160 ms of kernels.  Timeline at 36000^2 on PCIe 5: SRTM up (94 ms) | Fourier stage under the
-        groves + HydroSHEDS upload (118 ms) | groves, lagoons, combine | final DEM down (189 ms) over the sink-fill |
-        filled DEM + D8 down (118 ms)."""
+        HydroSHEDS upload (94 ms) | lagoon branch under the groves upload (24 ms) | groves, final terms | final DEM
+        down as int16 (47 ms) over the sink-fill, widened on the host underneath | filled DEM + D8 down (118 ms)."""
         import torch
         cur = torch.cuda.current_stream()
         if not hasattr(self, "_streams"):
@@ -538,7 +622,7 @@ class ConditioningChain:
         up, down = self._streams
         up.wait_stream(cur)                                   # recycled blocks: earlier work on them is over
         rasters, ready, keep = {}, {}, []
-        for name in _StreamSlot.ORDER:
+        for name in ("srtm", "hsheds", "groves", "rivers"):   # the order run_device first needs them in
             if name not in arrays:
                 continue
             host = np.ascontiguousarray(arrays[name])
@@ -546,14 +630,23 @@ class ConditioningChain:
             if not dev._is_pinned(host):
                 up.synchronize()                              # a pageable source may be released by the caller
             keep.append(host)
-        pending = {}
+        pending, narrow = {}, {}
+        lib = _lib.load()
+        d2h_bytes = [0]
 
         def send(name, raster):
+            if self.narrow_final and raster.dtype == _lib.F32 and raster.ref_dtype == np.float64:
+                return send_narrow(name, raster)
             conv = dev.convert(raster, dev.hd_dtype_of(raster.ref_dtype))
             ev = torch.cuda.Event()
             ev.record(cur)
             down.wait_event(ev)
             pending[name] = dev.download_async(conv, down) + (conv,)
+            d2h_bytes[0] += pending[name][0].nbytes
+
+        def send_narrow(name, raster):
+            narrow[name] = NarrowDownload(raster, cur, down)
+            d2h_bytes[0] += narrow[name].nbytes
 
         res = self.run_device(rasters["srtm"], rasters["groves"], rasters["hsheds"], rasters.get("rivers"), ready=ready,
                               on_ready=send)
@@ -561,8 +654,11 @@ class ConditioningChain:
         for name, (host, ev, _conv) in pending.items():
             ev.synchronize()
             out[name] = host
+        for name, nd in narrow.items():
+            out[name] = nd.result()
+            d2h_bytes[0] += nd.extra_bytes
         fill = res.info.get("fill")
         if fill is not None and fill.status() != 0:
             raise DeviceError(f"sink-fill did not reach its fixed point (status {fill.status()}): filled / d8 are invalid")
-        self.last_transfer_bytes = (sum(h.nbytes for h in keep), sum(h.nbytes for h in out.values()))
-        return out
+        self.last_transfer_bytes = (sum(h.nbytes for h in keep), d2h_bytes[0])
+        return {k: out[k] for k in ("final", "filled", "d8") if k in out}

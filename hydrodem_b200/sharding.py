@@ -357,6 +357,7 @@ class Band:
             raise ValueError(f"{ny} rows over {comm.world} ranks leave bands thinner than the {self.halo}-row halo")
         import os
         self.fill_overlap = max(8, int(os.environ.get("HD_FILL_OVERLAP", "64")) // 8 * 8)
+        self.narrow_final = os.environ.get("HD_NARROW_FINAL", "1") != "0"   # apply_to_host: final DEM down as int16
         if comm.world > 1 and min(b - a for a, b in self.bounds) < 2 * self.fill_overlap:
             self.fill_overlap = max(8, min(b - a for a, b in self.bounds) // 16 * 8)
         self.up = self.halo if comm.rank > 0 else 0
@@ -699,28 +700,32 @@ class Band:
         h_ext = hsheds if isinstance(hsheds, ExtRaster) else self.extended(hsheds)
         cur = torch.cuda.current_stream()
 
-        def input_halos():
-            for name, ext, given in (("groves", g_ext, groves_class), ("hsheds", h_ext, hsheds)):
-                if ready and ready.get(name) is not None:
-                    cur.wait_event(ready[name])
-                if given is ext:
-                    self.exchange_halo(ext)
-            TRACE.mark("input halos")
+        def input_halo(name, ext, given):
+            if ready and ready.get(name) is not None:
+                cur.wait_event(ready[name])               # its upload ran underneath the stages before
+            if given is ext:
+                self.exchange_halo(ext)
 
         if ready is None:
-            input_halos()
+            input_halo("groves", g_ext, groves_class)
+            input_halo("hsheds", h_ext, hsheds)
+            TRACE.mark("input halos")
         elif ready.get("srtm") is not None:
             cur.wait_event(ready["srtm"])
         dem = self.detect_apply_fourier(srtm)                                        # image_srtm.py:125-126
+        st = {"fourier": dem.raster}
         if ready is not None:
-            input_halos()                                 # their uploads ran underneath the Fourier stage
+            input_halo("hsheds", h_ext, hsheds)
+        chain._stage_lagoons(st, h_ext.raster)                                       # LagoonsDetection: HydroSHEDS only
+        TRACE.mark("lagoons")
+        if ready is not None:
+            input_halo("groves", g_ext, groves_class)
         self.exchange_halo(dem)
         TRACE.mark("dem halo")
-        st = {"fourier": dem.raster}
         chain._stage_groves(st, g_ext.raster)                                        # image_srtm.py:177-199
         TRACE.mark("groves")
-        chain._stage_combine(st, h_ext.raster, None)                                 # LagoonsDetection ... :149
-        TRACE.mark("lagoons + combine")
+        chain._stage_final(st, None)                                                 # final terms ... :149
+        TRACE.mark("combine")
         own = lambda r: r.sub(self.up, self.up + self.rows, 0, self.nx)              # noqa: E731
         out = {"final": own(st["final"])}
         if on_ready:
@@ -866,12 +871,18 @@ class Band:
             return r
 
         srtm = send_up("srtm", np.ascontiguousarray(srtm_rows, dtype=np.float32))
+        send_up("hsheds", np.ascontiguousarray(hsheds_rows, dtype=np.float32), h_ext.owned())
         g = np.ascontiguousarray(groves_rows)
         send_up("groves", g.view(np.uint8) if g.dtype == np.bool_ else g.astype(np.uint8, copy=False), g_ext.owned())
-        send_up("hsheds", np.ascontiguousarray(hsheds_rows, dtype=np.float32), h_ext.owned())
         pending = {}
 
+        narrow = {}
+
         def send_down(name, raster):
+            if self.narrow_final and raster.dtype == _lib.F32 and raster.ref_dtype == np.float64:
+                from .pipeline import NarrowDownload
+                narrow[name] = NarrowDownload(raster, cur, down)        # int16 over PCIe, widened on host threads
+                return
             conv = dev.convert(raster, dev.hd_dtype_of(raster.ref_dtype))
             ev = torch.cuda.Event()
             ev.record(cur)
@@ -883,4 +894,9 @@ class Band:
         for name, (host, ev, _conv) in pending.items():
             ev.synchronize()
             out[name] = host
-        return out
+        for name, nd in narrow.items():
+            out[name] = nd.result()
+        self.last_transfer_bytes = (sum(h.nbytes for h in keep),
+                                    sum(h.nbytes for h, _e, _c in pending.values())
+                                    + sum(nd.nbytes + nd.extra_bytes for nd in narrow.values()))
+        return {k: out[k] for k in ("final", "filled", "d8")}

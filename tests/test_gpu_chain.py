@@ -156,8 +156,13 @@ def test_apply_to_host_matches_lazy_path():
         np.testing.assert_array_equal(b["final"], a.final)
         np.testing.assert_array_equal(b["filled"], a.filled)
         np.testing.assert_array_equal(b["d8"], a.d8)
+    # the final DEM travels as int16 (+ a 4-byte flag) and is widened on the host
     assert chain.last_transfer_bytes == (srtm.nbytes + groves.size + hsheds.nbytes,
-                                         8 * srtm.size + 4 * srtm.size + srtm.size)
+                                         2 * srtm.size + 4 + 4 * srtm.size + srtm.size)
+    chain.narrow_final = False
+    b = chain.apply_to_host(*pinned)
+    np.testing.assert_array_equal(b["final"], a.final)
+    assert chain.last_transfer_bytes[1] == 8 * srtm.size + 4 * srtm.size + srtm.size
 
 
 def test_captured_graph_matches_eager():
@@ -237,6 +242,15 @@ def test_stream_falls_back_to_float32_transport():
     np.testing.assert_array_equal(got[1]["final"], want_ok.final)
     np.testing.assert_array_equal(got[1]["filled"], want_ok.filled)
     assert got[1]["final"].dtype == np.float64 and got[1]["filled"].dtype == np.float32
+    # the eager three-stream path of mosaic-sized rasters: same flag, float64 fetched instead
+    chain.eager_cells = 0
+    for args, w in (((srtm, groves, hsheds.copy()), want), ((ok.srtm(), ok.groves(), ok.hsheds()), want_ok)):
+        g = chain.apply_to_host(*args)
+        assert g["final"].dtype == np.float64
+        np.testing.assert_array_equal(g["final"], w.final)
+        np.testing.assert_array_equal(g["filled"], w.filled)
+        np.testing.assert_array_equal(g["d8"], w.d8)
+    assert chain.last_transfer_bytes[1] == 2 * srtm.size + 4 + 4 * srtm.size + srtm.size
 
 
 def test_stream_errors_propagate_and_chain_stays_usable():

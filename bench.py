@@ -54,7 +54,8 @@ def algo_bytes_per_cell(odd):
         "transpose_kernel": 16.0, "transpose_real_kernel": 8.0, "quadratic_kernel": 9.0, "majority_kernel": 8.0,
         "fill_async_kernel": 12.0, "hollow_kernel": 9.0 * 0.25, "expand_kernel": 2.0, "morph_kernel": 2.0,
         "maxfilter_kernel": 8.0, "fix3_kernel": 8.0, "conv3_kernel": 20.0, "final_terms_kernel": 20.0,
-        "elementwise_kernel": 9.0, "fill_finish_d8_kernel": 5.0,
+        "elementwise_kernel": 9.0, "fill_finish_d8_kernel": 5.0, "tidy_lagoons_kernel": 8.0, "final_mean3_kernel": 16.0,
+        "fill_init_kernel": 8.0,
     }
 
 

@@ -8,7 +8,8 @@
 //   1. builds one summary per window COLUMN (2h-1 inner rows, and all 2h+1 rows) -- shared by the 2h+1
 //      windows that contain that column,
 //   2. merges 2h+1 column summaries per output cell (the two outer columns use the inner-row summary:
-//      that is exactly the corner-less footprint),
+//      that is exactly the corner-less footprint); aligned pairs of rows (step 1) and of columns (step 2) are
+//      merged once and shared, which roughly halves the dependent update chains,
 //   3. verifies the candidate with an exact count only where the summary counter leaves the threshold
 //      reachable: true_count <= (n_window + counter) / 2 -- warp-cooperatively, by column counts.
 // This kernel is ALU / shared-memory bound, not HBM bound: ~8 B/cell of HBM traffic
@@ -28,10 +29,11 @@ struct BM { float c; int n; };
 // element, ~15 instructions per push; the kernel is bound by its instruction count (ncu: 360 instructions per cell).
 __device__ __forceinline__ void bm_push(BM& s, float v)
 {
-    const bool z = (s.n == 0);
-    s.c = z ? v : s.c;
-    // NaN == x is false: every NaN is its own key (custom_filters.py:69); an empty summary adopts v, NaN included
-    s.n += (z || v == s.c) ? 1 : -1;
+    const bool nz = (s.n != 0);
+    // NaN != x is true: every NaN is its own key (custom_filters.py:69); an empty summary adopts v, NaN included
+    const bool ne = nz && (v != s.c);
+    s.c = nz ? s.c : v;
+    s.n += ne ? -1 : 1;
 }
 __device__ __forceinline__ void bm_merge(BM& s, float c2, int n2)
 {
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
 {
     constexpr int WS = 2 * H + 1;
     constexpr int CW = TW + 2 * H;                 // window columns touched by a tile
+    constexpr int CP = CW / 2;                     // aligned column pairs
     constexpr int HX = hd_halo_x(H, 4);            // x halo of the staged box (16-byte TMA rule)
     constexpr int XOFF = HX - H;
     constexpr int IN_W = TW + 2 * HX;
@@ -59,8 +62,10 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
     __shared__ uint32_t colcnt[MCELL / 32][32 + 2 * H + 2];             // per warp: candidate counts of 32 + 2H window columns
     float* cand_in = reinterpret_cast<float*>(smem + 2 * STAGE);       // [TH][CW] summary over the 2H-1 inner rows
     float* cand_fu = cand_in + TH * CW;                                // [TH][CW] summary over all 2H+1 rows
-    uint8_t* cnt_in = reinterpret_cast<uint8_t*>(cand_fu + TH * CW);
+    float* cand_pr = cand_fu + TH * CW;                                // [TH][CP] full-column summaries of aligned column pairs
+    uint8_t* cnt_in = reinterpret_cast<uint8_t*>(cand_pr + TH * CP);
     uint8_t* cnt_fu = cnt_in + TH * CW;
+    uint8_t* cnt_pr = cnt_fu + TH * CW;
 
     const TilePlane planes[1] = {{&tm_in, 0u, (uint32_t)(IN_W * IN_H * 4), HX, H}};
     tile_loop<1>(smem, STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
@@ -71,11 +76,24 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
             float v[STRIP + 2 * H];
 #pragma unroll
             for (int r = 0; r < STRIP + 2 * H; ++r) v[r] = tile[(s * STRIP + r) * IN_W + c + XOFF];
+            // Summaries are mergeable: aligned PAIRS of rows (equal -> (v, 2), different -> empty) are shared by the
+            // outputs of the strip, so a 2H-1 row summary is one push + H-1 merges instead of 2H-1 dependent pushes.
+            float pc[(STRIP + 2 * H) / 2];
+            int pn[(STRIP + 2 * H) / 2];
+#pragma unroll
+            for (int k = 0; k < (STRIP + 2 * H) / 2; ++k) {
+                pc[k] = v[2 * k];
+                pn[k] = (v[2 * k] == v[2 * k + 1]) ? 2 : 0;
+            }
 #pragma unroll
             for (int o = 0; o < STRIP; ++o) {
                 BM b{0.f, 0};
+                int r = o + 1;                                         // inner rows o+1 .. o+2H-1 (compile-time after unrolling)
+                if (r & 1) { bm_push(b, v[r]); ++r; }
 #pragma unroll
-                for (int r = 1; r <= 2 * H - 1; ++r) bm_push(b, v[o + r]);
+                for (int q = 0; q < H; ++q)
+                    if (r + 1 <= o + 2 * H - 1) { bm_merge(b, pc[r / 2], pn[r / 2]); r += 2; }
+                if (r <= o + 2 * H - 1) bm_push(b, v[r]);
                 const int ro = s * STRIP + o;
                 cand_in[ro * CW + c] = b.c;
                 cnt_in[ro * CW + c] = (uint8_t)b.n;
@@ -84,6 +102,16 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
                 cand_fu[ro * CW + c] = b.c;
                 cnt_fu[ro * CW + c] = (uint8_t)b.n;
             }
+        }
+        __syncthreads();
+        // ---- 1b. aligned pairs of full-column summaries, shared by the cells of a row ----------------------------
+        for (int item = threadIdx.x; item < TH * CP; item += MNT) {
+            const int ro = item / CP, k = item - ro * CP;
+            const int base = ro * CW + 2 * k;
+            BM b{cand_fu[base], (int)cnt_fu[base]};
+            bm_merge(b, cand_fu[base + 1], (int)cnt_fu[base + 1]);
+            cand_pr[item] = b.c;
+            cnt_pr[item] = (uint8_t)b.n;
         }
         __syncthreads();
         // ---- 2. merge + 3. verify -------------------------------------------------------------------
@@ -107,8 +135,12 @@ __global__ void __launch_bounds__(MNT) majority_kernel(const __grid_constant__ C
                     const int base = ro * CW + xo;
                     b.c = cand_in[base];
                     b.n = (int)cnt_in[base];
+                    // full columns xo+1 .. xo+2H-1: one single column + H-1 aligned pairs (same code for both parities)
+                    const int lo = xo + 1, single = (lo & 1) ? lo : lo + 2 * H - 2;
+                    bm_merge(b, cand_fu[ro * CW + single], (int)cnt_fu[ro * CW + single]);
+                    const int k0 = ro * CP + ((lo + 1) >> 1);
 #pragma unroll
-                    for (int d = 1; d <= 2 * H - 1; ++d) bm_merge(b, cand_fu[base + d], (int)cnt_fu[base + d]);
+                    for (int q = 0; q < H - 1; ++q) bm_merge(b, cand_pr[k0 + q], (int)cnt_pr[k0 + q]);
                     bm_merge(b, cand_in[base + 2 * H], (int)cnt_in[base + 2 * H]);
                     // true count of the candidate <= (NWIN + counter) / 2; a NaN is its own key (count 1 < min_count)
                     plausible = (NWIN + b.n >= 2 * min_count) && (b.c == b.c);
@@ -165,7 +197,7 @@ int launch(const void* in, int64_t in_pitch, void* out, int64_t out_pitch, int64
 {
     constexpr int CW = TW + 2 * H, IN_W = TW + 2 * hd_halo_x(H, 4), IN_H = TH + 2 * H;
     constexpr size_t STAGE = (IN_W * IN_H * 4 + 127) / 128 * 128;
-    constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * 4 + 2 * TH * CW;
+    constexpr size_t SMEM = 2 * STAGE + 2 * TH * CW * 4 + 2 * TH * CW + TH * (CW / 2) * 5;
     CUtensorMap tm;
     if (int e = hd_make_tmap_2d(&tm, in, HD_F32, ny, nx, in_pitch, IN_W, IN_H, false)) return e;
     const int tiles_x = hd_cdiv(nx, TW), tiles_y = hd_cdiv(ny, TH), ntiles = tiles_x * tiles_y;

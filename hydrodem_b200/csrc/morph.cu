@@ -19,11 +19,11 @@ constexpr int NWORD = (MAX_IN_W + 31) / 32;            // 5
 constexpr int STAGE_BYTES = MAX_IN_H * (TW + 2 * MAX_HALO) * 4;   // sized for f32 (x halo <= 8), u8 needs less
 
 // threshold one staged tile to bits: bits[r * NWORD + k] bit i  <->  tile cell (r, 32k + i)
-template <typename InT, class Pred>
+template <typename InT, int THREADS = NT, class Pred>
 __device__ __forceinline__ void tile_to_bits(const InT* tile, int in_w, int in_h, uint32_t* bits, Pred pred)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < in_h; r += NT / 32) {
+    for (int r = warp; r < in_h; r += THREADS / 32) {
 #pragma unroll
         for (int k = 0; k < NWORD; ++k) {
             const int c = 32 * k + lane;
@@ -308,8 +308,9 @@ constexpr int TL_H = 8;                                   // halo
 constexpr int TL_IN_W = TW + 2 * TL_H, TL_IN_H = TH + 2 * TL_H;      // 144 x 48
 constexpr int TL_PW = TW + 8, TL_PH = TH + 6;             // product array: box columns 4 .. 139, box rows 5 .. 42
 constexpr uint32_t TL_STAGE = TL_IN_W * TL_IN_H * 4;
+constexpr int TL_NT = 512;                               // 2 CTAs x 16 warps per SM (the kernel is issue / latency bound)
 
-__global__ void __launch_bounds__(NT) tidy_lagoons_kernel(const __grid_constant__ CUtensorMap tm_in, float* __restrict__ out,
+__global__ void __launch_bounds__(TL_NT) tidy_lagoons_kernel(const __grid_constant__ CUtensorMap tm_in, float* __restrict__ out,
                                                           int64_t out_pitch, int64_t ny, int64_t nx, int tiles_x, int ntiles)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -319,17 +320,17 @@ __global__ void __launch_bounds__(NT) tidy_lagoons_kernel(const __grid_constant_
     float* prod = reinterpret_cast<float*>(smem + 2 * TL_STAGE);        // [TL_PH][TL_PW]
     float* hmax = prod + TL_PH * TL_PW;                                  // [TL_PH][TW]
     const TilePlane planes[1] = {{&tm_in, 0u, TL_STAGE, TL_H, TL_H}};
-    for (int t = threadIdx.x; t < NWORD; t += NT) bufA[t] = bufB[t] = 0u;                       // zero guard rows
+    for (int t = threadIdx.x; t < NWORD; t += TL_NT) bufA[t] = bufB[t] = 0u;                       // zero guard rows
     tile_loop<1>(smem, TL_STAGE, bars, planes, TW, TH, tiles_x, ntiles, [&](unsigned char* st, int ty0, int tx0) {
         const float* tile = reinterpret_cast<const float*>(st);
         uint32_t* cur = bufA + NWORD;
         uint32_t* nxt = bufB + NWORD;
         // scipy: non-zero elements are True (NaN != 0 is true); cells outside the raster arrive as 0 = border_value
-        tile_to_bits<float>(tile, TL_IN_W, TL_IN_H, cur, [](float v) { return v != 0.f; });
+        tile_to_bits<float, TL_NT>(tile, TL_IN_W, TL_IN_H, cur, [](float v) { return v != 0.f; });
         if (threadIdx.x < NWORD) { cur[TL_IN_H * NWORD + threadIdx.x] = 0u; nxt[TL_IN_H * NWORD + threadIdx.x] = 0u; }
         __syncthreads();
         for (int step = 0; step < 2; ++step) {                           // BinaryErosion(iterations=2), cross
-            for (int t = threadIdx.x; t < TL_IN_H * NWORD; t += NT) {
+            for (int t = threadIdx.x; t < TL_IN_H * NWORD; t += TL_NT) {
                 const int r = t / NWORD, k = t - r * NWORD;
                 const uint32_t* rc = cur + r * NWORD;
                 const uint32_t c = rc[k];
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(NT) tidy_lagoons_kernel(const __grid_constant_
             uint32_t* tmp = cur; cur = nxt; nxt = tmp;
         }
         // ExpandFilter(7): windows written by their FIRST column c' (output column c looks at bit c - 3)
-        for (int t = threadIdx.x; t < TL_IN_H * NWORD; t += NT) {
+        for (int t = threadIdx.x; t < TL_IN_H * NWORD; t += TL_NT) {
             const int r = t / NWORD, k = t - r * NWORD;
             const uint64_t w = win64(cur + r * NWORD, k);
             uint64_t f = w, in = 0;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(NT) tidy_lagoons_kernel(const __grid_constant_
             hinner[t] = (uint32_t)in;
         }
         __syncthreads();
-        for (int t = threadIdx.x; t < TL_PH * NWORD; t += NT) {
+        for (int t = threadIdx.x; t < TL_PH * NWORD; t += TL_NT) {
             const int pr = t / NWORD, k = t - pr * NWORD, r = pr + 5;    // box row
             uint32_t acc = hinner[(r - 3) * NWORD + k] | hinner[(r + 3) * NWORD + k];   // corner-less top / bottom rows
 #pragma unroll
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(NT) tidy_lagoons_kernel(const __grid_constant_
         }
         __syncthreads();
         // product with the majority image (ProductFilter(factor=majority), :607); ExpandFilter leaves its 3-cell frame at 0
-        for (int t = threadIdx.x; t < TL_PH * TL_PW; t += NT) {
+        for (int t = threadIdx.x; t < TL_PH * TL_PW; t += TL_NT) {
             const int pr = t / TL_PW, pc = t - pr * TL_PW;
             const int r = pr + 5, c = pc + 4;                            // box coordinates
             const int64_t y = (int64_t)ty0 - TL_H + r, x = (int64_t)tx0 - TL_H + c;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(NT) tidy_lagoons_kernel(const __grid_constant_
         __syncthreads();
         // GreyDilation(size=(7, 7)), mode='reflect'
         patch_reflect<float>(prod, TL_PW, TL_PH, ty0 - 3, tx0 - 4, ny, nx);
-        for (int t = threadIdx.x; t < TL_PH * (TW / 4); t += NT) {
+        for (int t = threadIdx.x; t < TL_PH * (TW / 4); t += TL_NT) {
             const int r = t / (TW / 4), c = 4 * (t - r * (TW / 4));
             const float* src = prod + r * TL_PW + c + 1;                 // output column c looks at array columns c+1 .. c+7
             float v[10];
@@ -396,8 +397,8 @@ __global__ void __launch_bounds__(NT) tidy_lagoons_kernel(const __grid_constant_
         }
         __syncthreads();
 #pragma unroll
-        for (int rep = 0; rep < TH * TW / 4 / NT; ++rep) {
-            const int idx = rep * NT + threadIdx.x;
+        for (int rep = 0; rep < TH * TW / 4 / TL_NT; ++rep) {
+            const int idx = rep * TL_NT + threadIdx.x;
             const int ro = idx >> 5, c4 = idx & 31;
             const int64_t y = ty0 + ro, x = tx0 + 4 * c4;
             if (y >= ny || x >= nx) continue;
@@ -574,7 +575,7 @@ extern "C" int hd_tidy_lagoons(const void* majority, int64_t in_pitch, void* out
     const size_t smem = 2 * (size_t)TL_STAGE + (size_t)TL_PH * TL_PW * 4 + (size_t)TL_PH * TW * 4;
     HD_CUDA_OK(cudaFuncSetAttribute(tidy_lagoons_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hd_prof_begin("tidy_lagoons_kernel", (cudaStream_t)stream);
-    tidy_lagoons_kernel<<<grid_for(ntiles, 2), NT, smem, (cudaStream_t)stream>>>(tm, (float*)out, out_pitch, ny, nx, tiles_x,
+    tidy_lagoons_kernel<<<grid_for(ntiles, 2), TL_NT, smem, (cudaStream_t)stream>>>(tm, (float*)out, out_pitch, ny, nx, tiles_x,
                                                                               ntiles);
     HD_LAUNCH_CHECK();
     hd_count_launch();

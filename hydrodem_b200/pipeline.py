@@ -298,6 +298,7 @@ class NarrowDownload:
             done.record(down)
             parts.append((a, b, done))
         self.nbytes, self.extra_bytes = host16.nbytes + 4, 0
+        self._last_copy, self._host16 = parts[-1][2], host16
         self.state = state = {"inexact": False, "error": None}
         device_index = torch.cuda.current_device()
         if threads is None:
@@ -325,6 +326,7 @@ class NarrowDownload:
         if self.state["error"] is not None:
             raise self.state["error"]
         if self.state["inexact"]:
+            self._last_copy.synchronize()                              # the int16 chunks still in flight own host16
             self.wide = dev.download(self.raster)                      # float64 over PCIe after all
             self.extra_bytes = self.wide.nbytes
         return self.wide

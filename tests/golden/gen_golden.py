@@ -264,7 +264,42 @@ def run_int16():
     save("run_int16", **out)
 
 
+def run_geotiff():
+    """The reference's one GDAL-written raster (resources/images/final_dem.tif, an array2raster output): its georeference
+    tags and a crop of its pixels.  The full file is checked here, at generation time: hydrodem_b200.geotiff reads
+    exactly what libtiff (Pillow) reads."""
+    from PIL import Image
+    from hydrodem_b200 import geotiff
+    path = os.path.join(REF, "resources", "images", "final_dem.tif")
+    pil = Image.open(path)
+    want = np.array(pil)
+    info = geotiff.read_info(path)
+    got = geotiff.read_array(path, pinned=False)
+    assert got.dtype == np.float32 and got.shape == want.shape == (519, 508) and np.array_equal(got, want, equal_nan=True)
+    assert info.compression == 1 and not info.tiled and geotiff._contiguous(info)
+    tags = info.geo_tags()
+    for t, (typ, cnt, raw) in tags.items():                           # libtiff decodes the same values
+        v = pil.tag_v2[t]
+        if typ == 12:
+            assert np.array_equal(np.asarray(v, dtype=np.float64), np.frombuffer(raw, dtype="<f8"))
+        elif typ == 3:
+            assert np.array_equal(np.asarray(v), np.frombuffer(raw, dtype="<u2"))
+    sx, sy = pil.tag_v2[33550][:2]
+    tie = pil.tag_v2[33922]
+    gt = (tie[3] - tie[0] * sx, sx, 0.0, tie[4] + tie[1] * sy, 0.0, -sy)   # what GetGeoTransform returns for these tags
+    assert tuple(info.geotransform()) == gt
+    ids = sorted(tags)
+    save("run_geotiff", array=want[200:264, 100:180].copy(), full_shape=np.array(want.shape),
+         full_sum=np.array(np.nansum(want.astype(np.float64))), tag_ids=np.array(ids),
+         tag_types=np.array([tags[t][0] for t in ids]), tag_counts=np.array([tags[t][1] for t in ids]),
+         tag_raw_len=np.array([len(tags[t][2]) for t in ids]),
+         tag_raw=np.frombuffer(b"".join(tags[t][2] for t in ids), dtype=np.uint8), geotransform=np.array(gt))
+
+
 if __name__ == "__main__":
+    if "--only-geotiff" in sys.argv:
+        run_geotiff()
+        sys.exit(0)
     if "--only-int16" in sys.argv:
         run_int16()
         sys.exit(0)
@@ -279,3 +314,4 @@ if __name__ == "__main__":
     run_simple()
     run_rivers()
     run_int16()
+    run_geotiff()

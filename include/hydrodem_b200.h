@@ -70,6 +70,13 @@ int hd_memcpy2d_h2d(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t
 int hd_memcpy2d_d2h(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
                     int64_t rows, void* stream);
 int hd_stream_synchronize(void* stream);
+/* Stats._set_values / Stats._totals, stats.py:21-25, :63-86: confusion-matrix counts of a
+ * simulated raster (F32 / F64; wet = value > threshold, compared in the raster's type) against a water mask (U8 / I16 /
+ * F32), with NumPy's arithmetic per sample type (uint8 differences wrap, 0 * NaN counts as non-zero).
+ * counts: DEVICE array of 6 uint64 -- TP, FN, FP, TN, total positives, total negatives; zeroed by the call. */
+int hd_confusion_counts(const void* sim, int sim_dtype, int64_t sim_pitch, const void* truth, int truth_dtype,
+                        int64_t truth_pitch, int64_t ny, int64_t nx, double threshold, void* counts, void* stream);
+
 /* Narrow PCIe transport of integer-valued rasters (host API; the final DEM of hydro_dem_process.py:149 and the filled
  * DEM hold integer metres).  hd_pack_i16: F32 pitched raster -> dense int16 rows on the device; *inexact_flag (device
  * int) is set to 1 if any value is not an integer in [-32768, 32767] (NaN included) -- the caller then moves float32

@@ -296,7 +296,89 @@ def run_geotiff():
          tag_raw=np.frombuffer(b"".join(tags[t][2] for t in ids), dtype=np.uint8), geotransform=np.array(gt))
 
 
+def run_stats():
+    """The reference's Stats class (stats.py) itself, driven through stub ``gdal`` / ``config_loader`` modules (GDAL is not
+    installed; the class only uses gdal.Open(name).ReadAsArray() and Config.simulation(key)).  Water masks of the sample
+    types GDAL delivers (uint8, int16, float32; one with values outside {0, 1} and a NaN) x three simulated rasters."""
+    import types
+    rasters = {}
+    gdal = types.ModuleType("gdal")
+
+    class _DS:
+        def __init__(self, name):
+            self.name = name
+
+        def ReadAsArray(self):
+            return rasters[self.name]
+
+    gdal.Open = _DS
+    cfg = types.ModuleType("config_loader")
+
+    class Config:
+        @staticmethod
+        def simulation(key):
+            return {"NDWI_IMAGE": "ndwi", "SIM": "sim_{}"}[key]
+
+    cfg.Config = Config
+    saved = {k: sys.modules.get(k) for k in ("gdal", "config_loader")}
+    sys.modules["gdal"], sys.modules["config_loader"] = gdal, cfg
+    try:
+        import importlib
+        ref_stats = importlib.import_module("stats")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = np.random.default_rng(77)
+    shape = (97, 131)
+    water = rng.random(shape) < 0.3
+    out = {}
+    sims = []
+    for d in range(3):
+        depth = np.where(water ^ (rng.random(shape) < 0.15), rng.random(shape) * 2, 0.0).astype(np.float32)
+        depth[rng.random(shape) < 0.02] = np.float32(0.0001)            # exactly the threshold: not wet
+        depth[rng.random(shape) < 0.02] = np.float32(0.00011)
+        sims.append(depth)
+        out[f"sim_{d + 1}"] = depth
+    sims[2] = sims[2].astype(np.float64)
+    out["sim_3"] = sims[2]
+    masks = {"u8": water.astype(np.uint8), "i16": water.astype(np.int16), "f32": water.astype(np.float32)}
+    odd = water.astype(np.float32)
+    odd[5, 7] = np.nan
+    odd[9, 3:9] = 2.0
+    odd[11, 2:5] = -1.0
+    masks["f32odd"] = odd
+    odd8 = water.astype(np.uint8)
+    odd8[9, 3:9] = 2
+    masks["u8odd"] = odd8
+    keys = None
+    for name, ndwi in masks.items():
+        rasters.clear()
+        rasters["ndwi"] = ndwi
+        for d in range(3):
+            rasters[f"sim_{d + 1}"] = sims[d]
+        with np.errstate(all="ignore"):
+            st = ref_stats.Stats("SIM", 4, "x")
+            got = st.get_stats()
+            counts = []
+            for d in range(3):
+                st._set_values(d + 1)
+                counts.append([st.values_file[k] for k in ("TP", "FN", "P", "FP", "TN", "N")])
+        keys = [k for k in got[0] if k != "day"]
+        out[f"ndwi_{name}"] = ndwi
+        out[f"counts_{name}"] = np.array(counts, dtype=np.int64)
+        out[f"totals_{name}"] = np.array([st.total_positives, st.total_negatives], dtype=np.int64)
+        out[f"scores_{name}"] = np.array([[g[k] for k in keys] for g in got], dtype=np.float64)
+    out["score_keys"] = np.array(keys)
+    save("run_stats", **out)
+
+
 if __name__ == "__main__":
+    if "--only-stats" in sys.argv:
+        run_stats()
+        sys.exit(0)
     if "--only-geotiff" in sys.argv:
         run_geotiff()
         sys.exit(0)
@@ -315,3 +397,4 @@ if __name__ == "__main__":
     run_rivers()
     run_int16()
     run_geotiff()
+    run_stats()

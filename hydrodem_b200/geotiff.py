@@ -95,6 +95,13 @@ class GeoTiffInfo:
 
 def read_info(path):
     """Parse the header and the first IFD of ``path``."""
+    try:
+        return _read_info(path)
+    except struct.error:
+        raise GeoTiffError(f"{path}: truncated or corrupt TIFF directory") from None
+
+
+def _read_info(path):
     info = GeoTiffInfo()
     with open(path, "rb") as f:
         head = f.read(16)

@@ -168,3 +168,22 @@ def test_bigtiff_writer_layout(tmp_path):
     assert info.big and len(info.offsets) > 1 and info.nodata == 0.0
     np.testing.assert_array_equal(geotiff.read_array(p, pinned=False), a)
     np.testing.assert_array_equal(np.array(Image.open(p)), a)
+
+
+def test_parallel_pieces(tmp_path, monkeypatch):
+    """Reads and writes larger than one I/O piece are split over the thread pool (pread into disjoint slices of the
+    result; conversion of the output pieces on the pool, writes in order): forced here with a tiny piece size."""
+    monkeypatch.setattr(geotiff, "_PIECE", 1000)
+    a = _rng_raster((301, 257), np.float32, 9)
+    p = tmp_path / "p.tif"
+    geotiff.write_geotiff(p, a.astype(np.float64), dtype=np.float32, strip_bytes=3000)     # converted piece by piece
+    np.testing.assert_array_equal(np.array(Image.open(p)), a)
+    np.testing.assert_array_equal(geotiff.read_array(p, pinned=False), a)
+    geotiff.write_geotiff(p, a[:, ::2], strip_bytes=500)                                   # non-contiguous source rows
+    np.testing.assert_array_equal(geotiff.read_array(p, pinned=False), a[:, ::2])
+    # a truncated file fails loudly instead of returning garbage
+    data = p.read_bytes()
+    info = geotiff.read_info(p)
+    p.write_bytes(data[:int(info.offsets[0]) + 5000] )
+    with pytest.raises(geotiff.GeoTiffError):
+        geotiff.read_array(p, pinned=False)

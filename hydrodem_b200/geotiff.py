@@ -195,6 +195,14 @@ def _pool():
 _POOL = None
 
 
+def shutdown_pool():
+    """Join the I/O threads (a process that is about to fork() should not carry idle pool threads)."""
+    global _POOL
+    if _POOL is not None:
+        _POOL.shutdown(wait=True)
+        _POOL = None
+
+
 def _pread_into(fd, view, offset, path="file"):
     """Fill the byte view from ``offset`` of the file, in parallel pieces."""
     import os

@@ -11,6 +11,12 @@ from conftest import load_golden
 from hydrodem_b200 import geotiff
 
 
+@pytest.fixture(autouse=True, scope="module")
+def _no_leftover_io_threads():
+    yield
+    geotiff.shutdown_pool()              # later test modules fork() worker processes (gloo ranks)
+
+
 def _rng_raster(shape, dtype, seed=0):
     rng = np.random.default_rng(seed)
     if np.dtype(dtype).kind == "f":

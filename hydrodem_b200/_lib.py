@@ -38,6 +38,7 @@ SIGNATURES = {
     "hd_stream_synchronize": (_i, [_p]),
     "hd_host_widen_f32_f64": (_i, [_p, _p, _i64, _i]),
     "hd_host_widen_i16": (_i, [_p, _i, _p, _i64, _i]),
+    "hd_host_lzw_decode": (_i64, [_p, _i64, _p, _i64]),
     "hd_confusion_counts": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i64, ctypes.c_double, _p, _p]),
     "hd_pack_i16": (_i, [_p, _i64, _p, _i64, _i64, _p, _p]),
     "hd_elementwise": (_i, [_i, _p, _i, _i64, _p, _i, _i64, _d, _p, _i, _i64, _i64, _i64, _p]),

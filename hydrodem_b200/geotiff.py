@@ -7,7 +7,8 @@ chain takes ~0.15 s for a 36000^2 mosaic the decode + host copies around it are 
 minimal replacement for exactly those two calls:
 
 * ``read_array(path)``          == ``gdal.Open(path).ReadAsArray()`` for single-band rasters: classic TIFF and BigTIFF,
-  either byte order, strips or tiles, uncompressed or Deflate, horizontal predictor, 8/16/32/64-bit samples.  An
+  either byte order, strips or tiles, uncompressed / Deflate / LZW, horizontal and floating-point predictors,
+  8/16/32/64-bit samples (compressed blocks are decoded in parallel on the I/O threads).  An
   uncompressed striped file whose strips are contiguous (what GDAL and ``array2raster`` write) is ONE ``readinto``
   straight into a pinned host array -- the array the upload DMA reads from, no intermediate copy.
 * ``read_to_device(path)``      the same file -> ``DeviceRaster``, row chunks read into two pinned staging buffers and
@@ -16,7 +17,7 @@ minimal replacement for exactly those two calls:
   (ModelPixelScale / ModelTiepoint / GeoKeyDirectory / GeoDoubleParams / GeoAsciiParams, i.e. geotransform + projection)
   copied from ``rasterfn``.  BigTIFF automatically above 4 GB.
 
-LZW / JPEG / the floating-point predictor are not decoded: ``GeoTiffError`` says so (fail loudly).
+JPEG, PackBits, ZSTD and multi-band rasters are not decoded: ``GeoTiffError`` says so (fail loudly).
 """
 import struct
 import zlib
@@ -149,10 +150,12 @@ def _read_info(path):
     info.dtype = np.dtype(info.byteorder + _SAMPLE_DTYPES[key])
     info.compression = one(259, 1)
     info.predictor = one(317, 1)
-    if info.compression not in (1, 8, 32946):
-        raise GeoTiffError(f"{path}: compression {info.compression} is not decoded here (none and Deflate only)")
-    if info.predictor not in (1, 2):
-        raise GeoTiffError(f"{path}: predictor {info.predictor} is not decoded here (none and horizontal only)")
+    if info.compression not in (1, 5, 8, 32946):
+        raise GeoTiffError(f"{path}: compression {info.compression} is not decoded here (none, LZW and Deflate only)")
+    if info.predictor not in (1, 2, 3):
+        raise GeoTiffError(f"{path}: predictor {info.predictor} is not decoded here")
+    if info.predictor == 3 and info.dtype.kind != "f":
+        raise GeoTiffError(f"{path}: floating-point predictor on {info.dtype} samples")
     if 322 in info.tags:
         info.tiled = True
         info.block_w, info.block_h = one(322), one(323)
@@ -248,9 +251,32 @@ def _host_array(shape, dtype, pinned):
     return np.empty(shape, dtype=dtype)
 
 
+def _lzw(raw, nbytes):
+    """TIFF LZW through the library's host decoder (hd_host_lzw_decode: C, no GPU involved)."""
+    import ctypes
+    from . import _lib
+    out = np.empty(nbytes, dtype=np.uint8)
+    src = np.frombuffer(raw, dtype=np.uint8)
+    n = _lib.load().hd_host_lzw_decode(ctypes.c_void_p(src.ctypes.data), len(raw), ctypes.c_void_p(out.ctypes.data), nbytes)
+    if n < 0:
+        raise GeoTiffError("corrupt LZW stream")
+    if n < nbytes:
+        out[n:] = 0
+    return out
+
+
 def _decode_block(raw, info, rows, cols):
-    if info.compression != 1:
+    es = info.dtype.itemsize
+    if info.compression == 5:
+        raw = _lzw(raw, rows * cols * es)
+    elif info.compression != 1:
         raw = zlib.decompress(raw)
+    if info.predictor == 3:
+        # floating-point predictor (Adobe TIFF TN3): per row the bytes are grouped by significance (all most significant
+        # bytes first) and then differenced byte-wise; undo both
+        b = np.frombuffer(raw, dtype=np.uint8, count=rows * cols * es).reshape(rows, cols * es)
+        b = np.cumsum(b, axis=1, dtype=np.uint8).reshape(rows, es, cols)
+        return np.ascontiguousarray(b.transpose(0, 2, 1)).view(">f" + str(es)).reshape(rows, cols)
     a = np.frombuffer(raw, dtype=info.dtype, count=rows * cols).reshape(rows, cols)
     if info.predictor == 2:
         if info.dtype.kind == "f":
@@ -271,19 +297,30 @@ def read_array(path, pinned=True, info=None):
             if info.dtype.byteorder == ">":
                 out.byteswap(inplace=True)
             return out
+        import os
         bw, bh = info.block_w, info.block_h
         across = -(-info.width // bw)
-        for k in range(len(info.offsets)):
+        fd = f.fileno()
+
+        def block(k):                                           # blocks land in disjoint parts of `out`
             by, bx = (k // across, k % across) if info.tiled else (k, 0)
             y0, x0 = by * bh, bx * bw
             if y0 >= info.height:
-                break
-            f.seek(int(info.offsets[k]))
-            raw = f.read(int(info.bytecounts[k]))
+                return
+            raw = os.pread(fd, int(info.bytecounts[k]), int(info.offsets[k]))
+            if len(raw) < int(info.bytecounts[k]):
+                raise GeoTiffError(f"{path}: truncated pixel data")
             rows_in_block = bh if info.tiled else min(bh, info.height - y0)
             blk = _decode_block(raw, info, rows_in_block, bw)
             ys, xs = min(bh, info.height - y0), min(bw, info.width - x0)
             out[y0:y0 + ys, x0:x0 + xs] = blk[:ys, :xs]
+
+        nblocks = len(info.offsets)
+        if nblocks > 1 and _io_threads() > 1:
+            list(_pool().map(block, range(nblocks)))             # zlib, the LZW decoder and pread release the GIL
+        else:
+            for k in range(nblocks):
+                block(k)
     return out
 
 

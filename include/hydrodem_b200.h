@@ -84,6 +84,9 @@ int hd_confusion_counts(const void* sim, int sim_dtype, int64_t sim_pitch, const
 int hd_pack_i16(const void* src, int64_t src_pitch, void* dst_dense, int64_t ny, int64_t nx, int* inexact_flag, void* stream);
 int hd_host_widen_f32_f64(double* dst, const float* src, int64_t n, int nthreads);
 int hd_host_widen_i16(void* dst, int dst_dtype, const int16_t* src, int64_t n, int nthreads);
+/* HOST helper of the GeoTIFF reader (hydrodem_b200/geotiff.py): TIFF 6.0 LZW (MSB-first codes, 9..12 bits, early change).
+ * Returns the number of bytes written to dst (at most cap) or a negative hd_status for a corrupt stream. */
+int64_t hd_host_lzw_decode(const uint8_t* src, int64_t nsrc, uint8_t* dst, int64_t cap);
 
 /* ---- elementwise filters (filters/simple_filters.py, extension_filters.py:12-130) -------------- */
 typedef enum {

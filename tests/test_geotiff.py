@@ -27,7 +27,10 @@ def _rng_raster(shape, dtype, seed=0):
 
 @pytest.mark.parametrize("mode,dtype,kw", [("F", np.float32, {}), ("F", np.float32, {"compression": "tiff_adobe_deflate"}),
                                            ("F", np.float32, {"big_tiff": True}), ("L", np.uint8, {}),
-                                           ("I;16", np.uint16, {}), ("F", np.float32, {"compression": "tiff_deflate"})])
+                                           ("I;16", np.uint16, {}), ("F", np.float32, {"compression": "tiff_deflate"}),
+                                           ("F", np.float32, {"compression": "tiff_lzw"}),
+                                           ("L", np.uint8, {"compression": "tiff_lzw"}),
+                                           ("I;16", np.uint16, {"compression": "tiff_lzw"})])
 def test_reads_what_libtiff_writes(tmp_path, mode, dtype, kw):
     a = _rng_raster((123, 77), dtype, 1)
     path = tmp_path / "a.tif"
@@ -149,9 +152,9 @@ def test_array2raster_copies_the_georeference_of_a_gdal_raster(tmp_path):
 
 def test_unsupported_files_fail_loudly(tmp_path):
     a = _rng_raster((40, 40), np.float32, 4)
-    p = tmp_path / "lzw.tif"
-    Image.fromarray(a).save(p, format="TIFF", compression="tiff_lzw")
-    with pytest.raises(geotiff.GeoTiffError, match="compression 5"):
+    p = tmp_path / "packbits.tif"
+    Image.fromarray(a).save(p, format="TIFF", compression="packbits")
+    with pytest.raises(geotiff.GeoTiffError, match="compression 32773"):
         geotiff.read_array(p, pinned=False)
     (tmp_path / "x.tif").write_bytes(b"not a tiff at all")
     with pytest.raises(geotiff.GeoTiffError, match="not a TIFF"):
@@ -193,3 +196,71 @@ def test_parallel_pieces(tmp_path, monkeypatch):
     p.write_bytes(data[:int(info.offsets[0]) + 5000] )
     with pytest.raises(geotiff.GeoTiffError):
         geotiff.read_array(p, pinned=False)
+
+
+@pytest.mark.parametrize("kind", ["smooth", "noise", "constant", "long"])
+def test_lzw_decoder_against_libtiff(tmp_path, kind):
+    """hd_host_lzw_decode on streams written by libtiff: compressible rasters (long strings, table resets after 4094
+    entries, every code width) and incompressible noise; strips of many rows so that one stream crosses several resets."""
+    rng = np.random.default_rng(11)
+    if kind == "smooth":
+        yy, xx = np.mgrid[0:400, 0:700]
+        a = np.round(100 + 20 * np.sin(xx / 40.0) + 15 * np.cos(yy / 55.0)).astype(np.int16).view(np.uint16)
+    elif kind == "noise":
+        a = rng.integers(0, 65535, (300, 500), dtype=np.uint16)
+    elif kind == "constant":
+        a = np.full((500, 900), 7, dtype=np.uint16)
+    else:
+        a = np.repeat(rng.integers(0, 4, (1, 250000), dtype=np.uint8), 2, axis=0).reshape(500, 1000).astype(np.uint16)
+    p = tmp_path / "l.tif"
+    Image.fromarray(a).save(p, format="TIFF", compression="tiff_lzw", tiffinfo={278: a.shape[0]})
+    info = geotiff.read_info(p)
+    assert info.compression == 5
+    np.testing.assert_array_equal(geotiff.read_array(p, pinned=False), a)
+    np.testing.assert_array_equal(np.array(Image.open(p)), a)
+
+
+def test_lzw_rejects_corrupt_streams():
+    import ctypes
+    from hydrodem_b200 import _lib
+    lib = _lib.load()
+    out = np.zeros(64, dtype=np.uint8)
+    bad = np.array([0x80, 0x3F, 0xFF, 0xFF, 0xFF], dtype=np.uint8)       # Clear, then a code far beyond the table
+    assert lib.hd_host_lzw_decode(ctypes.c_void_p(bad.ctypes.data), len(bad), ctypes.c_void_p(out.ctypes.data), 64) < 0
+    assert lib.hd_host_lzw_decode(None, 0, ctypes.c_void_p(out.ctypes.data), 64) < 0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_floating_point_predictor(tmp_path, dtype):
+    """PREDICTOR=3 (GDAL's choice for compressed float rasters): bytes grouped by significance, then differenced.  The
+    encoder here is the definition written out (TIFF Technical Note 3), strips compressed with Deflate."""
+    a = _rng_raster((50, 77), dtype, 13)
+    a[3, 4] = np.nan
+    es = a.itemsize
+    strips = []
+    for y in range(0, 50, 16):
+        rows = a[y:y + 16]
+        be = rows.astype(">f" + str(es)).view(np.uint8).reshape(rows.shape[0], 77, es)
+        planes = np.ascontiguousarray(be.transpose(0, 2, 1)).reshape(rows.shape[0], 77 * es)    # most significant bytes first
+        d = planes.copy()
+        d[:, 1:] = planes[:, 1:] - planes[:, :-1]
+        strips.append(zlib.compress(d.tobytes()))
+    tags = {256: (4, [77]), 257: (4, [50]), 258: (3, [8 * es]), 259: (3, [8]), 262: (3, [1]), 277: (3, [1]), 278: (4, [16]),
+            284: (3, [1]), 317: (3, [3]), 339: (3, [3])}
+    p = tmp_path / "fp.tif"
+    p.write_bytes(_build_tiff(strips, tags))
+    got = geotiff.read_array(p, pinned=False)
+    assert got.dtype == np.dtype(dtype)
+    np.testing.assert_array_equal(got, a)
+
+
+@pytest.mark.parametrize("comp", ["tiff_lzw", "tiff_adobe_deflate"])
+def test_horizontal_predictor_written_by_libtiff(tmp_path, comp):
+    """GDAL's COMPRESS=LZW|DEFLATE PREDICTOR=2 for integer elevation rasters, produced by libtiff itself."""
+    yy, xx = np.mgrid[0:300, 0:400]
+    a = np.round(100 + 20 * np.sin(xx / 40.0) + 15 * np.cos(yy / 55.0)).astype(np.int16).view(np.uint16)
+    p = tmp_path / "p2.tif"
+    Image.fromarray(a).save(p, format="TIFF", compression=comp, tiffinfo={317: 2})
+    info = geotiff.read_info(p)
+    assert info.predictor == 2 and len(info.offsets) > 1
+    np.testing.assert_array_equal(geotiff.read_array(p, pinned=False), a)
